@@ -1,0 +1,319 @@
+// extern "C" surface of libmps_b200 (declared in include/mpsb.h) and the launch sequences behind the
+// MPS entry points: update_double / update_single / svd_truncate / ortho_*_site / dot / corr of
+// DMRG/MPS.py.  The iDMRG entry points live in idmrg.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "../../include/mpsb.h"
+#include "common.cuh"
+#include "mpsb_internal.h"
+
+namespace mpsb {
+
+unsigned long long g_launch_count = 0;
+static thread_local char g_error[1024] = "";
+static thread_local int g_last_sweeps = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+    unsigned char* base;
+    size_t size, used;
+    Arena(void* p, size_t n) : base(static_cast<unsigned char*>(p)), size(n), used(0) {}
+    void* take(size_t bytes) {
+        void* r = base + used;
+        used += al(bytes);
+        return r;
+    }
+    bool ok() const { return used <= size; }
+};
+
+struct TebdLayout {
+    SvdPlan plan;
+    size_t theta0, thetaB, X, state, total;
+};
+int tebd_layout(int batch, int chil, int chi, int chir, int d, TebdLayout* L) {
+    (void)chi;
+    const int n = chil * d, l = d * chir;
+    int rc = svd_make_plan(batch, n, l, l, &L->plan);
+    if (rc) return rc;
+    const size_t mat = (size_t)n * l * sizeof(cplx);
+    L->theta0 = al(mat * batch);
+    L->thetaB = al(mat * batch);
+    L->X = al((size_t)L->plan.n_pad * L->plan.ld * sizeof(cplx) * batch);
+    L->state = al(svd_state_bytes(L->plan));
+    L->total = L->theta0 + L->thetaB + L->X + L->state;
+    return 0;
+}
+
+struct SvdLayout {
+    SvdPlan plan;
+    size_t X, state, total;
+};
+int svd_layout(int batch, int rows, int cols, int naug, SvdLayout* L) {
+    int rc = svd_make_plan(batch, rows, cols, cols + naug, &L->plan);
+    if (rc) return rc;
+    L->X = al((size_t)L->plan.n_pad * L->plan.ld * sizeof(cplx) * batch);
+    L->state = al(svd_state_bytes(L->plan));
+    L->total = L->X + L->state;
+    return 0;
+}
+
+}  // namespace
+}  // namespace mpsb
+
+using namespace mpsb;
+
+extern "C" {
+
+int mpsb_version(void) { return 100; }
+const char* mpsb_last_error(void) { return g_error; }
+unsigned long long mpsb_launch_count(void) { return g_launch_count; }
+int mpsb_last_svd_sweeps(void) { return g_last_sweeps; }
+
+int mpsb_zgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+               int ldc, int batch1, int batch2, long long sA1, long long sA2, long long sB1, long long sB2,
+               long long sC1, long long sC2, int accumulate, void* stream) {
+    GemmArgs p;
+    p.A = static_cast<const cplx*>(A);
+    p.B = static_cast<const cplx*>(B);
+    p.C = static_cast<cplx*>(C);
+    p.M = M; p.N = N; p.K = K;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.opA = opA; p.opB = opB;
+    p.batch1 = batch1; p.batch2 = batch2;
+    p.sA1 = sA1; p.sA2 = sA2; p.sB1 = sB1; p.sB2 = sB2; p.sC1 = sC1; p.sC2 = sC2;
+    p.accumulate = accumulate;
+    return zgemm(p, static_cast<cudaStream_t>(stream));
+}
+
+// ---- svd_truncate / halve ---------------------------------------------------------------------------
+size_t mpsb_svd_trunc_workspace(int batch, int rows, int cols, int want_u) {
+    SvdLayout L;
+    if (svd_layout(batch, rows, cols, want_u ? rows : 0, &L)) return 0;
+    return L.total;
+}
+
+int mpsb_svd_trunc(int batch, int rows, int cols, const void* A, int lda, long long sA, int trun, double err,
+                   int normalise, int k_cap, void* Vh, void* Uh, double* S, double* S_raw, int* rank, void* ws,
+                   size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(batch >= 1 && rows >= 1 && cols >= 1 && k_cap >= 1 && trun >= 0, "svd_trunc: bad arguments");
+    SvdLayout L;
+    int rc = svd_layout(batch, rows, cols, Uh ? rows : 0, &L);
+    if (rc) return rc;
+    MPSB_REQUIRE(ws && ws_bytes >= L.total, "svd_trunc: workspace %zu B < required %zu B", ws_bytes, L.total);
+    Arena ar(ws, ws_bytes);
+    cplx* X = static_cast<cplx*>(ar.take(L.X));
+    void* state = ar.take(L.state);
+    const SvdPlan& pl = L.plan;
+    const long long strideX = (long long)pl.n_pad * pl.ld;
+    for (int b = 0; b < batch; ++b) {
+        MatSrc dot = {static_cast<const cplx*>(A) + (size_t)b * sA, lda, 1, 0, nullptr, 1, 1};
+        MatSrc aug = {nullptr, 0, 0, 0, nullptr, 1, 1};
+        rc = pack_work_matrix(X + (size_t)b * strideX, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, Uh ? 1 : 0, st);
+        if (rc) return rc;
+    }
+    rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
+    if (rc) return rc;
+    SvdOutputs o;
+    memset(&o, 0, sizeof(o));
+    o.vh = static_cast<cplx*>(Vh); o.vh_stride = (long long)k_cap * cols; o.vh_ld = cols;
+    o.aug = static_cast<cplx*>(Uh); o.aug_stride = (long long)k_cap * rows; o.aug_ld = rows; o.aug_conj = 0;
+    o.s = S; o.s_stride = k_cap;
+    o.s_raw = S_raw; o.n_raw = rows < cols ? rows : cols; o.s_raw_stride = o.n_raw;
+    o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = normalise;
+    return svd_finalise(pl, X, state, o, st);
+}
+
+// ---- update_double -------------------------------------------------------------------------------------
+size_t mpsb_tebd_two_site_workspace(int batch, int chil, int chi, int chir, int d) {
+    TebdLayout L;
+    if (tebd_layout(batch, chil, chi, chir, d, &L)) return 0;
+    return L.total;
+}
+
+int mpsb_tebd_two_site(int batch, int chil, int chi, int chir, int d, const void* Bi, long long sBi, const void* Bj,
+                       long long sBj, const double* Sl, long long sSl, const void* U, long long sU, int trun,
+                       double err, int k_cap, void* Bi_out, long long sBio, void* Bj_out, long long sBjo,
+                       double* Sr_out, long long sSr, int* rank, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(batch >= 1 && chil >= 1 && chi >= 1 && chir >= 1 && d >= 1 && k_cap >= 1 && trun >= 0,
+                 "tebd_two_site: bad dims batch=%d chil=%d chi=%d chir=%d d=%d k_cap=%d", batch, chil, chi, chir, d, k_cap);
+    TebdLayout L;
+    int rc = tebd_layout(batch, chil, chi, chir, d, &L);
+    if (rc) return rc;
+    MPSB_REQUIRE(ws && ws_bytes >= L.total, "tebd_two_site: workspace %zu B < required %zu B", ws_bytes, L.total);
+    Arena ar(ws, ws_bytes);
+    cplx* theta0 = static_cast<cplx*>(ar.take(L.theta0));
+    cplx* thetaB = static_cast<cplx*>(ar.take(L.thetaB));
+    cplx* X = static_cast<cplx*>(ar.take(L.X));
+    void* state = ar.take(L.state);
+    const SvdPlan& pl = L.plan;
+    const int n = chil * d, l = d * chir;
+    const long long sTheta = (long long)n * l, sX = (long long)pl.n_pad * pl.ld;
+
+    // theta0[(l,c),(j,k)] = sum_r Bi[(l,c), r] Bj[r, (j,k)]        (DMRG/MPS.py:445, first two operands)
+    GemmArgs g;
+    g.A = static_cast<const cplx*>(Bi); g.B = static_cast<const cplx*>(Bj); g.C = theta0;
+    g.M = n; g.N = l; g.K = chi; g.lda = chi; g.ldb = l; g.ldc = l; g.opA = 0; g.opB = 0;
+    g.batch1 = batch; g.batch2 = 1; g.sA1 = sBi; g.sB1 = sBj; g.sC1 = sTheta; g.sA2 = g.sB2 = g.sC2 = 0;
+    g.accumulate = 0;
+    rc = zgemm(g, st);
+    if (rc) return rc;
+    if (pl.n_pad != n || pl.ld != l) MPSB_CHECK_CUDA(cudaMemsetAsync(X, 0, sizeof(cplx) * sX * batch, st));
+    // thetaB = U . theta0 ; X = Sl * thetaB                        (:445 third operand, :446)
+    rc = gate_scale(batch, chil, chir, d, theta0, sTheta, static_cast<const cplx*>(U), sU, Sl, sSl, thetaB, sTheta, X,
+                    sX, pl.ld, st);
+    if (rc) return rc;
+    // (s, Vh) = svd_truncate(X) -> Bj' = Vh, Sr = s, rank = k       (:448-452, :455)
+    rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
+    if (rc) return rc;
+    SvdOutputs o;
+    memset(&o, 0, sizeof(o));
+    o.vh = static_cast<cplx*>(Bj_out); o.vh_stride = sBjo; o.vh_ld = l;
+    o.s = Sr_out; o.s_stride = sSr;
+    o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
+    rc = svd_finalise(pl, X, state, o, st);
+    if (rc) return rc;
+    // Bi'[(l,a), m] = sum_{(b,k)} thetaB[(l,a),(b,k)] conj(Vh[m,(b,k)])   (:454)
+    g.A = thetaB; g.B = static_cast<const cplx*>(Bj_out); g.C = static_cast<cplx*>(Bi_out);
+    g.M = n; g.N = k_cap; g.K = l; g.lda = l; g.ldb = l; g.ldc = k_cap; g.opA = 0; g.opB = 2;
+    g.sA1 = sTheta; g.sB1 = sBjo; g.sC1 = sBio;
+    return zgemm(g, st);
+}
+
+int mpsb_one_site(int batch, int chil, int chir, int d, const void* M, long long sM, const void* U, long long sU,
+                  void* M_out, long long sMo, void* stream) {
+    return one_site(batch, chil, chir, d, static_cast<const cplx*>(M), sM, static_cast<const cplx*>(U), sU,
+                    static_cast<cplx*>(M_out), sMo, static_cast<cudaStream_t>(stream));
+}
+
+// ---- canon: gauge steps ------------------------------------------------------------------------------------
+// Left step: work matrix X = [ (Sl M_i)^H | M_next ], rows = right bond r (chir of them).  After the row
+// orthogonalisation  X = [ diag(s) U^H | Vh M_next ]  (DMRG/MPS.py:257-264).
+// Right step: X = [ M_i Sr | M_prev^H ], rows = left bond l; afterwards X = [ diag(s) Vh | (M_prev U)^H ]
+// (DMRG/MPS.py:277-284).
+size_t mpsb_gauge_workspace(int chil, int chir, int d, int nother, int k_cap) {
+    SvdLayout L, R;
+    if (svd_layout(1, chir, chil * d, nother, &L)) return 0;
+    if (svd_layout(1, chil, d * chir, nother, &R)) return 0;
+    const size_t left = L.total + al((size_t)k_cap * chil * d * sizeof(cplx));
+    const size_t right = R.total + al((size_t)k_cap * (nother > 0 ? nother : 1) * sizeof(cplx));
+    return left > right ? left : right;
+}
+
+int mpsb_gauge_left(int chil, int chir, int d, const void* M, const double* Sl, const void* M_next, int nnext,
+                    int trun, double err, int k_cap, void* M_out, double* Sr_out, void* M_next_out, int* rank,
+                    void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && nnext >= 0 && k_cap >= 1, "gauge_left: bad dims");
+    const int rows = chir, ldot = chil * d;
+    SvdLayout L;
+    int rc = svd_layout(1, rows, ldot, nnext, &L);
+    if (rc) return rc;
+    const size_t tmp_bytes = al((size_t)k_cap * ldot * sizeof(cplx));
+    MPSB_REQUIRE(ws && ws_bytes >= L.total + tmp_bytes, "gauge_left: workspace %zu B < required %zu B", ws_bytes,
+                 L.total + tmp_bytes);
+    Arena ar(ws, ws_bytes);
+    cplx* X = static_cast<cplx*>(ar.take(L.X));
+    void* state = ar.take(L.state);
+    cplx* tmp = static_cast<cplx*>(ar.take(tmp_bytes));
+    const SvdPlan& pl = L.plan;
+    // X[r][(l,c)] = conj(Sl[l] M[l,c,r]);   X[r][ldot + q] = M_next[r][q]
+    MatSrc dot = {static_cast<const cplx*>(M), 1, chir, 1, Sl, d, chil};
+    MatSrc aug = {static_cast<const cplx*>(M_next), nnext, 1, 0, nullptr, 1, 1};
+    rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, 0, st);
+    if (rc) return rc;
+    rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
+    if (rc) return rc;
+    SvdOutputs o;
+    memset(&o, 0, sizeof(o));
+    o.vh = tmp; o.vh_stride = 0; o.vh_ld = ldot;                       // rows i: conj(U[:, i])
+    o.aug = nnext ? static_cast<cplx*>(M_next_out) : nullptr; o.aug_stride = 0; o.aug_ld = nnext; o.aug_conj = 0;
+    o.s = Sr_out; o.s_stride = 0; o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
+    rc = svd_finalise(pl, X, state, o, st);
+    if (rc) return rc;
+    // M_out[(l,c)][i] = conj(tmp[i][(l,c)])
+    return transpose_conj(tmp, ldot, k_cap, ldot, static_cast<cplx*>(M_out), k_cap, 1, st);
+}
+
+int mpsb_gauge_right(int chil, int chir, int d, const void* M, const double* Sr, const void* M_prev, int nprev,
+                     int trun, double err, int k_cap, void* M_out, double* Sl_out, void* M_prev_out, int* rank,
+                     void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && nprev >= 0 && k_cap >= 1, "gauge_right: bad dims");
+    const int rows = chil, ldot = d * chir;
+    SvdLayout L;
+    int rc = svd_layout(1, rows, ldot, nprev, &L);
+    if (rc) return rc;
+    const size_t tmp_bytes = al((size_t)k_cap * (nprev > 0 ? nprev : 1) * sizeof(cplx));
+    MPSB_REQUIRE(ws && ws_bytes >= L.total + tmp_bytes, "gauge_right: workspace %zu B < required %zu B", ws_bytes,
+                 L.total + tmp_bytes);
+    Arena ar(ws, ws_bytes);
+    cplx* X = static_cast<cplx*>(ar.take(L.X));
+    void* state = ar.take(L.state);
+    cplx* tmp = static_cast<cplx*>(ar.take(tmp_bytes));
+    const SvdPlan& pl = L.plan;
+    // X[l][(c,r)] = M[l,c,r] Sr[r];   X[l][ldot + a] = conj(M_prev[a][l])
+    MatSrc dot = {static_cast<const cplx*>(M), ldot, 1, 0, Sr, 1, chir};
+    MatSrc aug = {static_cast<const cplx*>(M_prev), 1, chil, 1, nullptr, 1, 1};
+    rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, 0, st);
+    if (rc) return rc;
+    rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
+    if (rc) return rc;
+    SvdOutputs o;
+    memset(&o, 0, sizeof(o));
+    o.vh = static_cast<cplx*>(M_out); o.vh_stride = 0; o.vh_ld = ldot;
+    o.aug = nprev ? tmp : nullptr; o.aug_stride = 0; o.aug_ld = nprev; o.aug_conj = 1;   // tmp[i][a] = (M_prev U)[a][i]
+    o.s = Sl_out; o.s_stride = 0; o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
+    rc = svd_finalise(pl, X, state, o, st);
+    if (rc) return rc;
+    if (nprev == 0) return 0;
+    return transpose_conj(tmp, nprev, k_cap, nprev, static_cast<cplx*>(M_prev_out), k_cap, 0, st);
+}
+
+// ---- dot / corr: transfer-matrix step -----------------------------------------------------------------------
+size_t mpsb_transfer_workspace(int ka, int kb, int d, int oa, int rb) {
+    (void)kb; (void)oa;
+    return al((size_t)ka * d * rb * sizeof(cplx)) * 2;
+}
+
+int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, const void* A, const void* B,
+                       const void* Op, void* E_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t need = mpsb_transfer_workspace(ka, kb, d, oa, rb);
+    MPSB_REQUIRE(ws && ws_bytes >= need, "transfer_step: workspace %zu B < required %zu B", ws_bytes, need);
+    Arena ar(ws, ws_bytes);
+    cplx* T = static_cast<cplx*>(ar.take((size_t)ka * d * rb * sizeof(cplx)));
+    cplx* T2 = static_cast<cplx*>(ar.take((size_t)ka * d * rb * sizeof(cplx)));
+    // T[k][(j,r)] = sum_l E[k][l] B[l][(j,r)]
+    GemmArgs g;
+    g.A = static_cast<const cplx*>(E); g.B = static_cast<const cplx*>(B); g.C = T;
+    g.M = ka; g.N = d * rb; g.K = kb; g.lda = kb; g.ldb = d * rb; g.ldc = d * rb; g.opA = 0; g.opB = 0;
+    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    int rc = zgemm(g, st);
+    if (rc) return rc;
+    const cplx* Tuse = T;
+    if (Op) {   // T2[k][i][r] = sum_j Op[i][j] T[k][j][r]
+        rc = one_site(1, ka, rb, d, T, 0, static_cast<const cplx*>(Op), 0, T2, 0, st);
+        if (rc) return rc;
+        Tuse = T2;
+    }
+    // E'[o][r] = sum_{(k,i)} conj(A[(k,i)][o]) T[(k,i)][r]
+    g.A = static_cast<const cplx*>(A); g.B = Tuse; g.C = static_cast<cplx*>(E_out);
+    g.M = oa; g.N = rb; g.K = ka * d; g.lda = oa; g.ldb = rb; g.ldc = rb; g.opA = 2; g.opB = 0;
+    return zgemm(g, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// Layout and BLAS-1 helpers around the GEMM / Jacobi kernels.  All HBM-bound, written for coalesced
+// 16-byte accesses; none of them has a counterpart in the reference, which leaves index shuffling
+// to np.einsum (DMRG/MPS.py:257-284, DMRG/iDMRG.py:40-60) and vector algebra to ARPACK.
+#include "common.cuh"
+#include "mpsb_internal.h"
+
+namespace mpsb {
+
+namespace {
+
+__device__ __forceinline__ cplx fetch(const MatSrc& m, int i, int j) {
+    cplx v = m.src[(long long)i * m.rs + (long long)j * m.cs];
+    if (m.conj) v.y = -v.y;
+    if (m.scale) {
+        const double s = m.scale[(j / m.sdiv) % m.smod];
+        v.x *= s;
+        v.y *= s;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+pack_kernel(cplx* __restrict__ X, int n_pad, int ld, int rows, int ldot, int ltot, MatSrc dot, MatSrc aug,
+            int identity) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_pad * ld) return;
+    const int j = (int)(e % ld), i = (int)(e / ld);
+    cplx v = make_double2(0.0, 0.0);
+    if (i < rows) {
+        if (j < ldot) v = fetch(dot, i, j);
+        else if (j < ltot) {
+            if (aug.src) v = fetch(aug, i, j - ldot);
+            else if (identity && (j - ldot) == i) v = make_double2(1.0, 0.0);
+        }
+    }
+    X[e] = v;
+}
+
+// 32x32 tile transpose through shared memory (padded against bank conflicts).
+__global__ void __launch_bounds__(256)
+transpose_kernel(const cplx* __restrict__ in, int ldi, int rows, int cols, cplx* __restrict__ out, int ldo,
+                 int conj) {
+    __shared__ cplx tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + tx;
+        if (i < rows && j < cols) tile[r][tx] = in[(size_t)i * ldi + j];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, i = i0 + tx;
+        if (i < rows && j < cols) {
+            cplx v = tile[tx][r];
+            if (conj) v.y = -v.y;
+            out[(size_t)j * ldo + i] = v;
+        }
+    }
+}
+
+constexpr int DOT_THREADS = 256;
+// part[j][chunk] = sum over the chunk of conj(V[j][i]) w[i]
+__global__ void __launch_bounds__(DOT_THREADS)
+dot_partial_kernel(const cplx* __restrict__ V, long long ldv, long long n, const cplx* __restrict__ w,
+                   cplx* __restrict__ part, int nchunk) {
+    __shared__ double sr[DOT_THREADS / 32], si[DOT_THREADS / 32];
+    const int j = blockIdx.y, ch = blockIdx.x;
+    const long long per = (n + nchunk - 1) / nchunk;
+    const long long lo = (long long)ch * per, hi = lo + per < n ? lo + per : n;
+    const cplx* v = V + (size_t)j * ldv;
+    double re = 0.0, im = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += DOT_THREADS) {
+        const cplx a = v[i], b = w[i];
+        re = fma(a.x, b.x, fma(a.y, b.y, re));
+        im = fma(a.x, b.y, fma(-a.y, b.x, im));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sr[threadIdx.x >> 5] = re; si[threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < DOT_THREADS / 32; ++q) { a += sr[q]; b += si[q]; }
+        part[(size_t)j * nchunk + ch] = make_double2(a, b);
+    }
+}
+__global__ void dot_final_kernel(const cplx* __restrict__ part, int nchunk, int m, cplx* __restrict__ y) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < nchunk; ++q) { a += part[(size_t)j * nchunk + q].x; b += part[(size_t)j * nchunk + q].y; }
+    y[j] = make_double2(a, b);
+}
+
+__global__ void __launch_bounds__(256)
+axpy_multi_kernel(const cplx* __restrict__ V, long long ldv, int m, long long n, const cplx* __restrict__ c,
+                  cplx* __restrict__ w) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx acc = w[i];
+    for (int j = 0; j < m; ++j) {
+        const cplx cj = c[j], v = V[(size_t)j * ldv + i];
+        acc.x = fma(cj.x, v.x, fma(-cj.y, v.y, acc.x));
+        acc.y = fma(cj.x, v.y, fma(cj.y, v.x, acc.y));
+    }
+    w[i] = acc;
+}
+
+__global__ void __launch_bounds__(256) dscal_kernel(long long n, double alpha, cplx* __restrict__ w) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx v = w[i];
+    v.x *= alpha;
+    v.y *= alpha;
+    w[i] = v;
+}
+
+}  // namespace
+
+int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, const MatSrc& dot, const MatSrc& aug,
+                     int identity, cudaStream_t st) {
+    const long long total = (long long)n_pad * ld;
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, n_pad, ld, rows, ldot, ltot, dot, aug, identity);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    MPSB_REQUIRE(grid.y <= 65535, "transpose: %d rows exceed grid.y", rows);
+    transpose_kernel<<<grid, 256, 0, st>>>(in, ldi, rows, cols, out, ldo, conj);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int perm_last_to_first(const cplx* in, int n_ab, int n_c, cplx* out, cudaStream_t st) {
+    return transpose_conj(in, n_c, n_ab, n_c, out, n_ab, 0, st);
+}
+int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_t st) {
+    return transpose_conj(in, n_ab, n_c, n_ab, out, n_c, 0, st);
+}
+
+int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
+                cudaStream_t st) {
+    if (m == 0) return 0;
+    MPSB_REQUIRE(m <= 65535 && nchunk >= 1, "zdotc_multi: bad m=%d nchunk=%d", m, nchunk);
+    dim3 grid(nchunk, m);
+    dot_partial_kernel<<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk);
+    MPSB_COUNT_LAUNCH();
+    dot_final_kernel<<<(m + 63) / 64, 64, 0, st>>>(part, nchunk, m, y);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, cplx* w, cudaStream_t st) {
+    if (m == 0 || n == 0) return 0;
+    axpy_multi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, ldv, m, n, c, w);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int zdscal(long long n, double alpha, cplx* w, cudaStream_t st) {
+    if (n == 0) return 0;
+    dscal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, alpha, w);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mpsb

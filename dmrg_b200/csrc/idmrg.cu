@@ -1,0 +1,404 @@
+// iDMRG growth step (reference DMRG/iDMRG.py:38-61) without ever forming the dense effective
+// Hamiltonian:
+//   mpsb_heff_matvec      out = H_eff theta as  GEMM(L) -> fused W.W kernel -> GEMM(R)      (replaces :38-40 + the
+//                         dense matvec ARPACK performs inside eigsh, :57)
+//   mpsb_lanczos_ground   restarted Lanczos with full (twice-applied) reorthogonalisation   (replaces eigsh, :57)
+//   mpsb_env_left/right   environment growth as GEMM -> W kernel -> GEMM                    (replaces :59-60)
+// Index conventions: L[A,a,i] (bra, ket, mpo), R[D,d,k], W[i,j,B,b] (mpo-row, mpo-col, bra, ket),
+// theta[a,b,c,d] (left bond, phys1, phys2, right bond).
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../include/mpsb.h"
+#include "common.cuh"
+#include "mpsb_internal.h"
+
+namespace mpsb {
+
+namespace {
+
+inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+// WW[i][k][B][C][b][c] = sum_j W[i][j][B][b] W[j][k][C][c]
+__global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, cplx* __restrict__ WW) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = w * w * d * d * d * d;
+    if (e >= total) return;
+    int r = e;
+    const int c = r % d; r /= d;
+    const int b = r % d; r /= d;
+    const int C = r % d; r /= d;
+    const int B = r % d; r /= d;
+    const int k = r % w;
+    const int i = r / w;
+    double re = 0.0, im = 0.0;
+    for (int j = 0; j < w; ++j) {
+        const cplx x = W[((size_t)(i * w + j) * d + B) * d + b];
+        const cplx y = W[((size_t)(j * w + k) * d + C) * d + c];
+        re += x.x * y.x - x.y * y.y;
+        im += x.x * y.y + x.y * y.x;
+    }
+    WW[e] = make_double2(re, im);
+}
+
+// T3[A][B][C][dr][k] = sum_{i,b,c} WW[i][k][B][C][b][c] T1[i][A][b][c][dr]
+// One thread per (A, B, C, dr) producing the w values of k (contiguous store).  Zero blocks of the
+// (lower-triangular, mostly empty) MPO are skipped; the test is uniform across the warp.
+__global__ void __launch_bounds__(256)
+ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, const cplx* __restrict__ T1,
+                cplx* __restrict__ T3) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)chil * d * d * chir;
+    if (e >= total) return;
+    const int dr = (int)(e % chir);
+    long long r = e / chir;
+    const int C = (int)(r % d); r /= d;
+    const int B = (int)(r % d);
+    const int A = (int)(r / d);
+    const size_t t1_row = (size_t)d * d * chir;          // elements per (i, A)
+    for (int k = 0; k < w; ++k) {
+        double re = 0.0, im = 0.0;
+        for (int i = 0; i < w; ++i) {
+            const cplx* t1 = T1 + ((size_t)i * chil + A) * t1_row + dr;
+            const cplx* g0 = WW + ((((size_t)i * w + k) * d + B) * d + C) * d * d;
+            for (int b = 0; b < d; ++b)
+                for (int c = 0; c < d; ++c) {
+                    const cplx g = g0[b * d + c];
+                    if (g.x == 0.0 && g.y == 0.0) continue;
+                    const cplx x = t1[(size_t)(b * d + c) * chir];
+                    re = fma(g.x, x.x, fma(-g.y, x.y, re));
+                    im = fma(g.x, x.y, fma(g.y, x.x, im));
+                }
+        }
+        T3[(size_t)e * w + k] = make_double2(re, im);
+    }
+}
+
+// Left environment:  T2[C][i][l][B] = sum_{k,m} W[k][C][l][m] T1[k][i][m][B]
+// Right environment: T2[C][l][i][B] = sum_{k,m} W[C][k][l][m] T1[k][i][B][m]
+__global__ void __launch_bounds__(256)
+env_w_kernel(int right, int chi, int chin, int d, int w, const cplx* __restrict__ W, const cplx* __restrict__ T1,
+             cplx* __restrict__ T2) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)w * chi * d * chin;
+    if (e >= total) return;
+    const int B = (int)(e % chin);
+    long long r = e / chin;
+    int i, l;
+    if (!right) { l = (int)(r % d); r /= d; i = (int)(r % chi); r /= chi; }
+    else        { i = (int)(r % chi); r /= chi; l = (int)(r % d); r /= d; }
+    const int C = (int)r;
+    double re = 0.0, im = 0.0;
+    for (int k = 0; k < w; ++k)
+        for (int m = 0; m < d; ++m) {
+            const cplx g = right ? W[((size_t)(C * w + k) * d + l) * d + m] : W[((size_t)(k * w + C) * d + l) * d + m];
+            if (g.x == 0.0 && g.y == 0.0) continue;
+            const cplx x = right ? T1[(((size_t)k * chi + i) * chin + B) * d + m]
+                                 : T1[(((size_t)k * chi + i) * d + m) * chin + B];
+            re = fma(g.x, x.x, fma(-g.y, x.y, re));
+            im = fma(g.x, x.y, fma(g.y, x.x, im));
+        }
+    T2[e] = make_double2(re, im);
+}
+
+struct Heff {
+    int chil, chir, d, w;
+    const cplx* R;      // as given: [D][dr][k]
+    cplx *Lt, *WW, *T1, *T3;
+    size_t n;           // chil*d*d*chir
+};
+size_t heff_bytes(int chil, int chir, int d, int w) {
+    const size_t n = (size_t)chil * d * d * chir;
+    return al((size_t)w * chil * chil * sizeof(cplx)) + al((size_t)w * w * d * d * d * d * sizeof(cplx)) +
+           al(n * w * sizeof(cplx)) * 2;
+}
+int heff_prepare(Heff& h, int chil, int chir, int d, int w, const cplx* L, const cplx* W, const cplx* R, void* ws,
+                 cudaStream_t st) {
+    h.chil = chil; h.chir = chir; h.d = d; h.w = w; h.R = R;
+    h.n = (size_t)chil * d * d * chir;
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    h.Lt = reinterpret_cast<cplx*>(p); p += al((size_t)w * chil * chil * sizeof(cplx));
+    h.WW = reinterpret_cast<cplx*>(p); p += al((size_t)w * w * d * d * d * d * sizeof(cplx));
+    h.T1 = reinterpret_cast<cplx*>(p); p += al(h.n * w * sizeof(cplx));
+    h.T3 = reinterpret_cast<cplx*>(p);
+    int rc = perm_last_to_first(L, chil * chil, w, h.Lt, st);   // Lt[i][A][a] = L[A][a][i]
+    if (rc) return rc;
+    const int total = w * w * d * d * d * d;
+    ww_build_kernel<<<(total + 127) / 128, 128, 0, st>>>(w, d, W, h.WW);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int heff_apply(const Heff& h, const cplx* theta, cplx* out, cudaStream_t st) {
+    const int ncol = h.d * h.d * h.chir;
+    GemmArgs g;
+    // T1[(i,A)][(b,c,dr)] = sum_a Lt[(i,A)][a] theta[a][(b,c,dr)]
+    g.A = h.Lt; g.B = theta; g.C = h.T1;
+    g.M = h.w * h.chil; g.N = ncol; g.K = h.chil; g.lda = h.chil; g.ldb = ncol; g.ldc = ncol; g.opA = 0; g.opB = 0;
+    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    int rc = zgemm(g, st);
+    if (rc) return rc;
+    ww_apply_kernel<<<(unsigned)((h.n + 255) / 256), 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.T1, h.T3);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    // out[(A,B,C)][D] = sum_{(dr,k)} T3[(A,B,C)][(dr,k)] R[D][(dr,k)]
+    g.A = h.T3; g.B = h.R; g.C = out;
+    g.M = h.chil * h.d * h.d; g.N = h.chir; g.K = h.chir * h.w; g.lda = g.K; g.ldb = g.K; g.ldc = h.chir;
+    g.opA = 0; g.opB = 1;
+    return zgemm(g, st);
+}
+
+// Symmetric eigenproblem of a small dense real matrix by cyclic Jacobi (host; m <= a few dozen).
+void sym_eig_host(int m, std::vector<double>& a, std::vector<double>& v) {
+    v.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; ++i) v[(size_t)i * m + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) (i == j ? diag : off) += a[(size_t)i * m + j] * a[(size_t)i * m + j];
+        if (off <= 1e-34 * (diag + off)) break;
+        for (int p = 0; p < m - 1; ++p)
+            for (int q = p + 1; q < m; ++q) {
+                const double apq = a[(size_t)p * m + q];
+                if (apq == 0.0) continue;
+                const double tau = (a[(size_t)q * m + q] - a[(size_t)p * m + p]) / (2.0 * apq);
+                const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+                for (int k = 0; k < m; ++k) {
+                    const double akp = a[(size_t)k * m + p], akq = a[(size_t)k * m + q];
+                    a[(size_t)k * m + p] = c * akp - s * akq;
+                    a[(size_t)k * m + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < m; ++k) {
+                    const double apk = a[(size_t)p * m + k], aqk = a[(size_t)q * m + k];
+                    a[(size_t)p * m + k] = c * apk - s * aqk;
+                    a[(size_t)q * m + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < m; ++k) {
+                    const double vkp = v[(size_t)k * m + p], vkq = v[(size_t)k * m + q];
+                    v[(size_t)k * m + p] = c * vkp - s * vkq;
+                    v[(size_t)k * m + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+}  // namespace
+}  // namespace mpsb
+
+using namespace mpsb;
+
+extern "C" {
+
+size_t mpsb_heff_workspace(int chil, int chir, int d, int w) { return heff_bytes(chil, chir, d, w); }
+
+int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
+                     void* out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && w >= 1, "heff_matvec: bad dims");
+    const size_t need = heff_bytes(chil, chir, d, w);
+    MPSB_REQUIRE(ws && ws_bytes >= need, "heff_matvec: workspace %zu B < required %zu B", ws_bytes, need);
+    Heff h;
+    int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
+                          static_cast<const cplx*>(R), ws, st);
+    if (rc) return rc;
+    return heff_apply(h, static_cast<const cplx*>(theta), static_cast<cplx*>(out), st);
+}
+
+size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
+    const size_t n = (size_t)chil * d * d * chir;
+    const int nchunk = 64;
+    return heff_bytes(chil, chir, d, w) + al(n * sizeof(cplx)) * (size_t)(krylov + 2) +
+           al((size_t)(krylov + 2) * nchunk * sizeof(cplx)) + al((size_t)(krylov + 2) * sizeof(cplx)) * 3;
+}
+
+int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
+                        int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
+                        int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && w >= 1 && krylov >= 2 && max_restarts >= 1,
+                 "lanczos_ground: bad arguments");
+    const size_t need = mpsb_lanczos_workspace(chil, chir, d, w, krylov);
+    MPSB_REQUIRE(ws && ws_bytes >= need, "lanczos_ground: workspace %zu B < required %zu B", ws_bytes, need);
+    const size_t n = (size_t)chil * d * d * chir;
+    const int nchunk = 64;
+    int m = krylov;
+    if ((size_t)m > n) m = (int)n;
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    Heff h;
+    int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
+                          static_cast<const cplx*>(R), p, st);
+    if (rc) return rc;
+    p += heff_bytes(chil, chir, d, w);
+    const size_t vstride = al(n * sizeof(cplx)) / sizeof(cplx);
+    cplx* V = reinterpret_cast<cplx*>(p);                 p += al(n * sizeof(cplx)) * (size_t)(krylov + 2);
+    cplx* part = reinterpret_cast<cplx*>(p);              p += al((size_t)(krylov + 2) * nchunk * sizeof(cplx));
+    cplx* c1 = reinterpret_cast<cplx*>(p);                p += al((size_t)(krylov + 2) * sizeof(cplx));
+    cplx* c2 = reinterpret_cast<cplx*>(p);                p += al((size_t)(krylov + 2) * sizeof(cplx));
+    cplx* c3 = reinterpret_cast<cplx*>(p);
+    cplx* th = static_cast<cplx*>(theta);
+    std::vector<cplx> hc((size_t)krylov + 2);
+    std::vector<double> alpha, beta, T, Y;
+    int n_mv = 0;
+    double E = 0.0, resid = 0.0;
+
+    // normalise the start vector into V[0]
+    rc = zdotc_multi(th, 0, 1, (long long)n, th, c1, part, nchunk, st);
+    if (rc) return rc;
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+    MPSB_REQUIRE(hc[0].x > 0.0 && std::isfinite(hc[0].x), "lanczos_ground: start vector has norm^2 = %g", hc[0].x);
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    rc = zdscal((long long)n, 1.0 / std::sqrt(hc[0].x), V, st);
+    if (rc) return rc;
+
+    for (int restart = 0; restart < max_restarts; ++restart) {
+        alpha.clear();
+        beta.clear();
+        int mm = 0;
+        for (int j = 0; j < m; ++j) {
+            cplx* wv = V + (size_t)(j + 1) * vstride;
+            rc = heff_apply(h, V + (size_t)j * vstride, wv, st);
+            if (rc) return rc;
+            ++n_mv;
+            // two passes of classical Gram-Schmidt against V[0..j]
+            for (int pass = 0; pass < 2; ++pass) {
+                cplx* c = pass == 0 ? c1 : c2;
+                rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, st);
+                if (rc) return rc;
+                MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c, sizeof(cplx) * (j + 1), cudaMemcpyDeviceToHost, st));
+                MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+                if (pass == 0) alpha.push_back(hc[j].x);
+                else alpha.back() += hc[j].x;
+                for (int q = 0; q <= j; ++q) { hc[q].x = -hc[q].x; hc[q].y = -hc[q].y; }
+                MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx) * (j + 1), cudaMemcpyHostToDevice, st));
+                rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c3, wv, st);
+                if (rc) return rc;
+                MPSB_CHECK_CUDA(cudaStreamSynchronize(st));   // hc is reused by the next pass
+            }
+            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, c1, part, nchunk, st);
+            if (rc) return rc;
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+            MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+            const double bj = std::sqrt(hc[0].x > 0.0 ? hc[0].x : 0.0);
+            beta.push_back(bj);
+            mm = j + 1;
+            if (!(bj > 1e-14 * (std::fabs(alpha[0]) + 1e-300))) break;   // invariant subspace reached
+            rc = zdscal((long long)n, 1.0 / bj, wv, st);
+            if (rc) return rc;
+        }
+        // Ritz pair of the mm x mm tridiagonal matrix
+        T.assign((size_t)mm * mm, 0.0);
+        for (int i = 0; i < mm; ++i) {
+            T[(size_t)i * mm + i] = alpha[i];
+            if (i + 1 < mm) T[(size_t)i * mm + i + 1] = T[(size_t)(i + 1) * mm + i] = beta[i];
+        }
+        sym_eig_host(mm, T, Y);
+        int best = 0;
+        for (int i = 1; i < mm; ++i)
+            if (T[(size_t)i * mm + i] < T[(size_t)best * mm + best]) best = i;
+        E = T[(size_t)best * mm + best];
+        resid = std::fabs(beta[mm - 1] * Y[(size_t)(mm - 1) * mm + best]);
+        // theta = sum_j y_j V[j]
+        for (int i = 0; i < mm; ++i) hc[i] = make_double2(Y[(size_t)i * mm + best], 0.0);
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx) * mm, cudaMemcpyHostToDevice, st));
+        MPSB_CHECK_CUDA(cudaMemsetAsync(th, 0, n * sizeof(cplx), st));
+        rc = zaxpy_multi(V, (long long)vstride, mm, (long long)n, c3, th, st);
+        if (rc) return rc;
+        // renormalise (guards against drift) and restart from it
+        rc = zdotc_multi(th, 0, 1, (long long)n, th, c1, part, nchunk, st);
+        if (rc) return rc;
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+        rc = zdscal((long long)n, 1.0 / std::sqrt(hc[0].x), th, st);
+        if (rc) return rc;
+        if (resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0) || mm < m) break;
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    }
+    // true residual ||H theta - E theta|| with one more product
+    cplx* hv = V + (size_t)1 * vstride;
+    rc = heff_apply(h, th, hv, st);
+    if (rc) return rc;
+    ++n_mv;
+    rc = zdotc_multi(th, 0, 1, (long long)n, hv, c1, part, nchunk, st);
+    if (rc) return rc;
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+    E = hc[0].x;                                   // Rayleigh quotient of the returned vector
+    hc[0] = make_double2(-E, 0.0);
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx), cudaMemcpyHostToDevice, st));
+    rc = zaxpy_multi(th, 0, 1, (long long)n, c3, hv, st);
+    if (rc) return rc;
+    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, c1, part, nchunk, st);
+    if (rc) return rc;
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+    resid = std::sqrt(hc[0].x > 0.0 ? hc[0].x : 0.0);
+    if (energy_host) *energy_host = E;
+    if (resid_host) *resid_host = resid;
+    if (n_matvec_host) *n_matvec_host = n_mv;
+    return 0;
+}
+
+size_t mpsb_env_workspace(int chi, int chin, int d, int w) {
+    return al((size_t)w * chi * chi * sizeof(cplx)) + al((size_t)w * chi * d * chin * sizeof(cplx)) * 2 +
+           al((size_t)w * chin * chin * sizeof(cplx));
+}
+
+static int env_common(int right, int chi, int chin, int d, int w, const void* E, const void* UV, const void* W,
+                      int swap_conj, void* E_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(chi >= 1 && chin >= 1 && d >= 1 && w >= 1, "env: bad dims");
+    const size_t need = mpsb_env_workspace(chi, chin, d, w);
+    MPSB_REQUIRE(ws && ws_bytes >= need, "env: workspace %zu B < required %zu B", ws_bytes, need);
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    cplx* Et = reinterpret_cast<cplx*>(p); p += al((size_t)w * chi * chi * sizeof(cplx));
+    cplx* T1 = reinterpret_cast<cplx*>(p); p += al((size_t)w * chi * d * chin * sizeof(cplx));
+    cplx* T2 = reinterpret_cast<cplx*>(p); p += al((size_t)w * chi * d * chin * sizeof(cplx));
+    cplx* Ot = reinterpret_cast<cplx*>(p);
+    const cplx* X = static_cast<const cplx*>(UV);
+    // Et[k][i][j] = E[i][j][k]
+    int rc = perm_last_to_first(static_cast<const cplx*>(E), chi * chi, w, Et, st);
+    if (rc) return rc;
+    GemmArgs g;
+    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    // ket leg (index j of the environment) meets the un-conjugated tensor unless swap_conj
+    if (!right) {
+        // T1[(k,i)][(m,B)] = sum_j Et[(k,i)][j] U[j][(m,B)]
+        g.A = Et; g.B = X; g.C = T1; g.M = w * chi; g.N = d * chin; g.K = chi;
+        g.lda = chi; g.ldb = d * chin; g.ldc = d * chin; g.opA = 0; g.opB = swap_conj ? 3 : 0;
+    } else {
+        // T1[(k,i)][(B,m)] = sum_j Et[(k,i)][j] V[(B,m)][j]
+        g.A = Et; g.B = X; g.C = T1; g.M = w * chi; g.N = chin * d; g.K = chi;
+        g.lda = chi; g.ldb = chi; g.ldc = chin * d; g.opA = 0; g.opB = swap_conj ? 2 : 1;
+    }
+    rc = zgemm(g, st);
+    if (rc) return rc;
+    const long long total = (long long)w * chi * d * chin;
+    env_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(right, chi, chin, d, w, static_cast<const cplx*>(W),
+                                                                  T1, T2);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    // bra leg:  Ot[C][A][B] = sum_{K} op(X)[A][K] T2[C][K][B]
+    g.B = T2; g.C = Ot; g.M = chin; g.N = chin; g.K = chi * d; g.ldb = chin; g.ldc = chin;
+    g.batch1 = w; g.sA1 = 0; g.sB1 = (long long)chi * d * chin; g.sC1 = (long long)chin * chin;
+    g.A = X;
+    if (!right) { g.lda = chin; g.opA = swap_conj ? 1 : 2; }      // U as [(i,l)][A]
+    else        { g.lda = chi * d; g.opA = swap_conj ? 0 : 3; }   // V as [A][(l,i)]
+    g.opB = 0;
+    rc = zgemm(g, st);
+    if (rc) return rc;
+    // E_out[A][B][C] = Ot[C][A][B]
+    return perm_first_to_last(Ot, w, chin * chin, static_cast<cplx*>(E_out), st);
+}
+
+int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U, const void* W, int swap_conj,
+                  void* L_out, void* ws, size_t ws_bytes, void* stream) {
+    return env_common(0, chi, chin, d, w, L, U, W, swap_conj, L_out, ws, ws_bytes, stream);
+}
+int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
+                   void* R_out, void* ws, size_t ws_bytes, void* stream) {
+    return env_common(1, chi, chin, d, w, R, V, W, swap_conj, R_out, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,605 @@
+// Batched truncated SVD for the two-site update: Householder-QR preconditioning followed by a
+// parallel-ordered one-sided (Hestenes) Jacobi iteration on the ROWS of the work matrix.
+//
+// Replaces  scipy.linalg.svd + truncate  in the reference:
+//   svd_truncate            DMRG/MPS.py:41-45   (update_double :448, ortho_*_site :260,:280)
+//   truncate                DMRG/MPS.py:14-38
+//   halve                   DMRG/iDMRG.py:17-35
+//
+// Why rows: left rotations Q^H m = diag(s) Vh leave the singular values in the row norms and the
+// right singular vectors in the normalised rows, which is all update_double needs (its `u` is never
+// used, DMRG/MPS.py:451).  When U or a gauge carry is wanted the caller appends columns to the
+// work matrix (identity, or the neighbouring site tensor); they receive the same rotations.
+//
+// Pipeline per problem:  qr_precond_kernel (columns in descending-norm order; makes the row Gram
+// matrix scaled-diagonally dominant so Jacobi needs ~8 sweeps even for exponentially decaying
+// Schmidt spectra instead of 30+)  ->  jacobi_round_kernel x (sweeps x rounds)  ->  finalise_kernel
+// (row norms, bitonic sort, reference truncation rule, coalesced scatter into the MPS tensors).
+//
+// Data movement: every Jacobi CTA owns two blocks of `bsz` rows; the rows are pulled into shared
+// memory with the TMA engine's 1-D bulk copy (cp.async.bulk, SASS UBLKCP) and pushed back the same
+// way.  One warp rotates one row pair: inner products by warp shuffles, rotation in place in smem.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include "common.cuh"
+#include "mpsb_internal.h"
+
+namespace mpsb {
+
+namespace {
+
+constexpr int QR_THREADS = 1024;
+constexpr int FIN_THREADS = 256;
+
+struct SvdState {           // device scratch, carved out of the caller's workspace
+    int* rot;               // [batch] rotations applied in the current sweep
+    int* done;              // [batch] 1 once a sweep applied no rotation
+    double* frob2;          // [batch] squared Frobenius norm of the dot part
+    int* n_active;          // [1]
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+SvdState carve_state(void* state, int batch) {
+    unsigned char* p = static_cast<unsigned char*>(state);
+    SvdState s;
+    s.rot = reinterpret_cast<int*>(p);            p += align_up(sizeof(int) * batch, 256);
+    s.done = reinterpret_cast<int*>(p);           p += align_up(sizeof(int) * batch, 256);
+    s.frob2 = reinterpret_cast<double*>(p);       p += align_up(sizeof(double) * batch, 256);
+    s.n_active = reinterpret_cast<int*>(p);
+    return s;
+}
+
+// ---- block reductions ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Sum over the CTA; every thread receives the same value.  `red` holds >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// ---- Householder QR, one CTA per problem ----------------------------------------------------------
+// Reflectors are built from the dot columns in descending-norm order (a static stand-in for column
+// pivoting) and applied to all ltot columns.  Thread (cg, cj) owns rows i == cg (mod G) of column
+// cj (+ strips of CW columns), so global accesses are coalesced along a row.
+__global__ void __launch_bounds__(QR_THREADS, 1)
+qr_precond_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, int ltot, int ld, int G,
+                  int CW, double* __restrict__ frob2) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    cplx* v = reinterpret_cast<cplx*>(smraw);                      // [n]
+    cplx* wpart = v + align_up(n, 8);                               // [G][ld]
+    double* cn = reinterpret_cast<double*>(wpart + (size_t)G * ld); // [ldot]
+    int* order = reinterpret_cast<int*>(cn + align_up(ldot, 8));    // [ldot]
+    unsigned char* colDone = reinterpret_cast<unsigned char*>(order + align_up(ldot, 8));  // [ld]
+    __shared__ double red[33];
+
+    const int tid = threadIdx.x, NT = blockDim.x;
+    cplx* X = Xall + (size_t)blockIdx.x * strideX;
+    const int cg = tid / CW, cj = tid % CW;
+    const bool active = cg < G;
+    const int nstrips = (ltot + CW - 1) / CW;
+
+    // column norms of the dot part
+    double* cpart = reinterpret_cast<double*>(wpart);               // [G][ld] doubles
+    for (int s = 0; s < nstrips; ++s) {
+        const int j = s * CW + cj;
+        if (active && j < ldot) {
+            double acc = 0.0;
+#pragma unroll 4
+            for (int i = cg; i < n; i += G) {
+                const cplx x = X[(size_t)i * ld + j];
+                acc = fma(x.x, x.x, fma(x.y, x.y, acc));
+            }
+            cpart[cg * ld + j] = acc;
+        }
+    }
+    for (int j = tid; j < ld; j += NT) colDone[j] = 0;
+    __syncthreads();
+    double fl = 0.0;
+    for (int j = tid; j < ldot; j += NT) {
+        double acc = 0.0;
+        for (int g = 0; g < G; ++g) acc += cpart[g * ld + j];
+        cn[j] = acc;
+        fl += acc;
+    }
+    const double F2 = block_sum(fl, red);
+    if (tid == 0) frob2[blockIdx.x] = F2;
+    // rank sort, descending, ties by index
+    for (int j = tid; j < ldot; j += NT) {
+        const double me = cn[j];
+        int r = 0;
+        for (int q = 0; q < ldot; ++q) {
+            const double o = cn[q];
+            r += (o > me) || (o == me && q < j);
+        }
+        order[r] = j;
+    }
+    __syncthreads();
+
+    const int nsteps = n < ldot ? n : ldot;
+    for (int k = 0; k < nsteps; ++k) {
+        const int pc = order[k];
+        for (int i = k + tid; i < n; i += NT) v[i] = X[(size_t)i * ld + pc];
+        __syncthreads();
+        double loc = 0.0;
+        for (int i = k + 1 + tid; i < n; i += NT) {
+            const cplx x = v[i];
+            loc = fma(x.x, x.x, fma(x.y, x.y, loc));
+        }
+        const cplx alpha = v[k];
+        const double sigma = block_sum(loc, red);          // contains the barriers that order v[k] reads
+        const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+        const double normx2 = a2 + sigma;
+        if (!(normx2 > 0.0)) {                              // zero column: nothing to annihilate
+            if (tid == 0) colDone[pc] = 1;
+            __syncthreads();
+            continue;
+        }
+        const double normx = sqrt(normx2), absa = sqrt(a2);
+        cplx phase = make_double2(1.0, 0.0);
+        if (absa > 0.0) phase = make_double2(alpha.x / absa, alpha.y / absa);
+        const cplx beta = make_double2(-phase.x * normx, -phase.y * normx);
+        const cplx vk = make_double2(phase.x * (absa + normx), phase.y * (absa + normx));
+        const double vhv = (absa + normx) * (absa + normx) + sigma;
+        const double tau = 2.0 / vhv;
+        if (tid == 0) v[k] = vk;
+        __syncthreads();
+        // pass 1: partial w_j = sum_i conj(v_i) X[i][j]
+        for (int s = 0; s < nstrips; ++s) {
+            const int j = s * CW + cj;
+            if (active && j < ltot && j != pc && !(j < ldot && colDone[j])) {
+                double wr = 0.0, wi = 0.0;
+#pragma unroll 4
+                for (int i = k + cg; i < n; i += G) {
+                    const cplx x = X[(size_t)i * ld + j];
+                    const cplx vi = v[i];
+                    wr = fma(vi.x, x.x, fma(vi.y, x.y, wr));
+                    wi = fma(vi.x, x.y, fma(-vi.y, x.x, wi));
+                }
+                wpart[(size_t)cg * ld + j] = make_double2(wr, wi);
+            }
+        }
+        __syncthreads();
+        // pass 2: X[i][j] -= tau v_i w_j
+        for (int s = 0; s < nstrips; ++s) {
+            const int j = s * CW + cj;
+            if (active && j < ltot && j != pc && !(j < ldot && colDone[j])) {
+                double wr = 0.0, wi = 0.0;
+                for (int g = 0; g < G; ++g) {
+                    const cplx t = wpart[(size_t)g * ld + j];
+                    wr += t.x;
+                    wi += t.y;
+                }
+                wr *= tau;
+                wi *= tau;
+#pragma unroll 4
+                for (int i = k + cg; i < n; i += G) {
+                    const cplx vi = v[i];
+                    cplx x = X[(size_t)i * ld + j];
+                    x.x -= vi.x * wr - vi.y * wi;
+                    x.y -= vi.x * wi + vi.y * wr;
+                    X[(size_t)i * ld + j] = x;
+                }
+            }
+        }
+        for (int i = k + tid; i < n; i += NT)
+            X[(size_t)i * ld + pc] = (i == k) ? beta : make_double2(0.0, 0.0);
+        if (tid == 0) colDone[pc] = 1;
+        __syncthreads();
+    }
+}
+
+// ---- Jacobi -----------------------------------------------------------------------------------------
+// Round-robin (circle method) pairing of m (even) players: round r in [0, m-1), slot s in [0, m/2).
+__device__ __forceinline__ void rr_pair(int m, int r, int s, int& p, int& q) {
+    const int mm = m - 1;
+    if (s == 0) { p = mm; q = r % mm; return; }
+    int a = (r + s) % mm, b = (r - s) % mm;
+    if (b < 0) b += mm;
+    p = a; q = b;
+}
+
+// One warp makes rows P and Q orthogonal over their first `ldot` entries and applies the rotation to
+// all `ltot_r` entries.  Returns 1 if a rotation was applied.  All lanes take the same branch because
+// the butterfly reduction leaves bit-identical sums in every lane.
+__device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restrict__ Q, int ldot, int ltot_r,
+                                           double F2, double tol2, double eabs2, int lane) {
+    double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+    for (int c = lane; c < ldot; c += 32) {
+        const cplx x = P[c], y = Q[c];
+        a = fma(x.x, x.x, fma(x.y, x.y, a));
+        b = fma(y.x, y.x, fma(y.y, y.y, b));
+        cr = fma(x.x, y.x, fma(x.y, y.y, cr));     // x * conj(y)
+        ci = fma(x.y, y.x, fma(-x.x, y.y, ci));
+    }
+    a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
+    const double ac2 = cr * cr + ci * ci;
+    if (!(ac2 > tol2 * a * b) || !(ac2 > eabs2 * F2 * fmax(a, b))) return 0;
+    const double ac = sqrt(ac2);
+    const double tau = (b - a) / (2.0 * ac);
+    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+    const double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
+    const double gr = sn * cr / ac, gi = sn * ci / ac;   // g = sn * c/|c|
+    // P' = cs P - g Q ;  Q' = conj(g) P + cs Q
+    for (int c = lane; c < ltot_r; c += 32) {
+        const cplx x = P[c], y = Q[c];
+        cplx xn, yn;
+        xn.x = cs * x.x - (gr * y.x - gi * y.y);
+        xn.y = cs * x.y - (gr * y.y + gi * y.x);
+        yn.x = (gr * x.x + gi * x.y) + cs * y.x;
+        yn.y = (gr * x.y - gi * x.x) + cs * y.y;
+        P[c] = xn;
+        Q[c] = yn;
+    }
+    return 1;
+}
+
+// grid = (nblk/2, problems in the chunk); block = 32*B threads.
+// full != 0: the CTA plays a complete tournament among its 2B rows (used for round 0 of a sweep, so
+// intra-block pairs are covered); full == 0: only the B*B cross pairs between the two blocks.
+template <int B>
+__global__ void __launch_bounds__(32 * B)
+jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r,
+                    int nblk, int round, int full, int inner_sweeps, const double* __restrict__ frob2,
+                    int* __restrict__ rot, const int* __restrict__ done, double tol2, double eabs2) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    cplx* rows = reinterpret_cast<cplx*>(smraw);            // [2B][ltot_r]
+    __shared__ __align__(8) uint64_t bar;
+
+    const int mat = mat0 + blockIdx.y;
+    if (done[mat]) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int bI, bJ;
+    rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    cplx* X = Xall + (size_t)mat * strideX;
+    const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, rowbytes * 2 * B);
+        for (int r = 0; r < B; ++r) {
+            bulk_g2s(rows + (size_t)r * ltot_r, X + (size_t)(bI * B + r) * ld, rowbytes, &bar);
+            bulk_g2s(rows + (size_t)(B + r) * ltot_r, X + (size_t)(bJ * B + r) * ld, rowbytes, &bar);
+        }
+    }
+    if (!mbar_wait(&bar, 0)) __trap();
+
+    const double F2 = frob2[mat];
+    int nrot_total = 0;
+    for (int sw = 0; sw < inner_sweeps; ++sw) {
+        int nrot = 0;
+        if (full) {
+            for (int s = 0; s < 2 * B - 1; ++s) {
+                int p, q;
+                rr_pair(2 * B, s, w, p, q);
+                nrot += rotate_pair(rows + (size_t)p * ltot_r, rows + (size_t)q * ltot_r, ldot, ltot_r, F2, tol2,
+                                    eabs2, lane);
+                __syncthreads();
+            }
+        } else {
+            for (int s = 0; s < B; ++s) {
+                const int p = w, q = B + ((w + s) % B);
+                nrot += rotate_pair(rows + (size_t)p * ltot_r, rows + (size_t)q * ltot_r, ldot, ltot_r, F2, tol2,
+                                    eabs2, lane);
+                __syncthreads();
+            }
+        }
+        nrot_total += nrot;
+        if (!__syncthreads_or(nrot > 0)) break;
+    }
+    const int any = __syncthreads_or(nrot_total > 0);
+    if (!any) return;
+    if (lane == 0 && nrot_total > 0) atomicAdd(&rot[mat], nrot_total);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int r = 0; r < B; ++r) {
+            bulk_s2g(X + (size_t)(bI * B + r) * ld, rows + (size_t)r * ltot_r, rowbytes);
+            bulk_s2g(X + (size_t)(bJ * B + r) * ld, rows + (size_t)(B + r) * ltot_r, rowbytes);
+        }
+        bulk_commit();
+        bulk_wait_all();
+    }
+}
+
+__global__ void sweep_begin_kernel(int* rot, int* done, int* n_active, int batch, int reset_done) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_active = 0;
+    if (i < batch) {
+        rot[i] = 0;
+        if (reset_done) done[i] = 0;
+    }
+}
+__global__ void sweep_end_kernel(int* rot, int* done, int* n_active, int mat0, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const int m = mat0 + i;
+        if (!done[m]) {
+            if (rot[m] == 0) done[m] = 1;
+            else atomicAdd(n_active, 1);
+        }
+        rot[m] = 0;
+    }
+}
+
+// ---- finalise: row norms -> sort -> truncate -> scatter ------------------------------------------------
+__global__ void __launch_bounds__(FIN_THREADS)
+finalise_kernel(const cplx* __restrict__ Xall, long long strideX, int n, int n_pad, int npow2, int ldot, int ltot,
+                int ld, SvdOutputs o) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* key = reinterpret_cast<double*>(smraw);              // [npow2]
+    int* idx = reinterpret_cast<int*>(key + npow2);              // [npow2]
+    __shared__ int s_k;
+    __shared__ double s_scale;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = FIN_THREADS / 32;
+    const int mat = blockIdx.x;
+    const cplx* X = Xall + (size_t)mat * strideX;
+
+    for (int i = warp; i < npow2; i += nw) {
+        double acc = 0.0;
+        if (i < n_pad) {
+            const cplx* row = X + (size_t)i * ld;
+            for (int c = lane; c < ldot; c += 32) {
+                const cplx x = row[c];
+                acc = fma(x.x, x.x, fma(x.y, x.y, acc));
+            }
+            acc = warp_sum(acc);
+        }
+        if (lane == 0) {
+            key[i] = (i < n_pad) ? acc : -1.0;   // padding sorts last
+            idx[i] = i;
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending by key
+    for (int size = 2; size <= npow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < npow2; i += FIN_THREADS) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = ((i & size) == 0);
+                    const double ki = key[i], kj = key[j];
+                    const bool swap = desc ? (ki < kj) : (ki > kj);
+                    if (swap) {
+                        key[i] = kj; key[j] = ki;
+                        const int t = idx[i]; idx[i] = idx[j]; idx[j] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // truncation rule.  Reference `truncate` (DMRG/MPS.py:33-38): s /= s[0]; k = min(#(s > err), trun);
+    // s = s[:k] / ||s[:k]||.   Reference `halve` (DMRG/iDMRG.py:26-31): k = min(trunc, S.size), raw S.
+    const int nsv = n < ldot ? n : ldot;
+    if (tid == 0) {
+        const double s0 = key[0] > 0.0 ? sqrt(key[0]) : 0.0;
+        int k = 0;
+        if (o.normalise) {
+            if (s0 > 0.0)
+                for (int i = 0; i < nsv; ++i) k += (sqrt(fmax(key[i], 0.0)) / s0 > o.err);
+        } else {
+            k = nsv;
+        }
+        if (k > o.trun) k = o.trun;
+        if (k > o.k_cap) k = o.k_cap;
+        double nrm2 = 0.0;
+        for (int i = 0; i < k; ++i) {
+            const double r = sqrt(fmax(key[i], 0.0)) / s0;
+            nrm2 += r * r;
+        }
+        s_k = k;
+        s_scale = (k > 0) ? 1.0 / (s0 * sqrt(nrm2)) : 0.0;
+        o.rank[mat] = k;
+    }
+    __syncthreads();
+    const int k = s_k;
+    for (int i = tid; i < o.k_cap; i += FIN_THREADS) {
+        const double si = (i < k) ? sqrt(fmax(key[i], 0.0)) : 0.0;
+        o.s[(size_t)mat * o.s_stride + i] = o.normalise ? si * s_scale : si;
+    }
+    if (o.s_raw)
+        for (int i = tid; i < o.n_raw; i += FIN_THREADS)
+            o.s_raw[(size_t)mat * o.s_raw_stride + i] = (i < nsv) ? sqrt(fmax(key[i], 0.0)) : 0.0;
+    const int naug = ltot - ldot;
+    for (int i = warp; i < o.k_cap; i += nw) {
+        const bool keep = i < k && key[i] > 0.0;
+        const cplx* row = X + (size_t)(keep ? idx[i] : 0) * ld;
+        const double inv = keep ? 1.0 / sqrt(key[i]) : 0.0;
+        if (o.vh) {
+            cplx* dst = o.vh + (size_t)mat * o.vh_stride + (size_t)i * o.vh_ld;
+            for (int c = lane; c < ldot; c += 32) {
+                cplx x = make_double2(0.0, 0.0);
+                if (keep) { x = row[c]; x.x *= inv; x.y *= inv; }
+                dst[c] = x;
+            }
+        }
+        if (o.aug && naug > 0) {
+            cplx* dst = o.aug + (size_t)mat * o.aug_stride + (size_t)i * o.aug_ld;
+            for (int c = lane; c < naug; c += 32) {
+                cplx x = make_double2(0.0, 0.0);
+                if (keep) { x = row[ldot + c]; if (o.aug_conj) x.y = -x.y; }
+                dst[c] = x;
+            }
+        }
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return atoi(s);
+}
+
+template <int B>
+int launch_round(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
+                 int inner, double tol2, double eabs2, cudaStream_t st) {
+    const int ltot_r = round_up(pl.ltot, 32);
+    const size_t smem = (size_t)2 * B * ltot_r * sizeof(cplx);
+    static size_t configured = 0;
+    if (smem > configured) {
+        MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_round_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+        configured = smem;
+    }
+    const int nblk = pl.n_pad / pl.bsz;
+    dim3 grid(nblk / 2, count);
+    jacobi_round_kernel<B><<<grid, 32 * B, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
+                                                      nblk, round, full, inner, s.frob2, s.rot, s.done, tol2, eabs2);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
+                     int inner, double tol2, double eabs2, cudaStream_t st) {
+    switch (pl.bsz) {
+        case 1: return launch_round<1>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
+        case 2: return launch_round<2>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
+        case 4: return launch_round<4>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
+        case 8: return launch_round<8>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
+        case 16: return launch_round<16>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
+    }
+    set_error("svd: unsupported block size %d", pl.bsz);
+    return 1;
+}
+
+}  // namespace
+
+int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
+    MPSB_REQUIRE(batch >= 1 && n >= 1 && ldot >= 1 && ltot >= ldot, "svd: bad dims batch=%d n=%d ldot=%d ltot=%d",
+                 batch, n, ldot, ltot);
+    SvdPlan p;
+    p.batch = batch;
+    p.n = n;
+    p.ldot = ldot;
+    p.ltot = ltot;
+    p.ld = round_up(ltot, 32);
+    const size_t rowbytes = (size_t)p.ld * sizeof(cplx);
+    const size_t smem_budget = 200 * 1024;
+    const int rows_fit = (int)(smem_budget / rowbytes);
+    MPSB_REQUIRE(rows_fit >= 2, "svd: row of %d elements does not fit shared memory", p.ld);
+    int bcap = env_int("MPSB_JACOBI_BSZ", 8);
+    if (bcap < 1) bcap = 1;
+    if (bcap > 16) bcap = 16;
+    int b = 1;
+    while (b * 2 <= bcap && 2 * (b * 2) <= rows_fit && b < (n + 1) / 2) b *= 2;
+    p.bsz = b;
+    p.n_pad = round_up(n, 2 * b);
+    const size_t matbytes = (size_t)p.n_pad * rowbytes;
+    const size_t l2_budget = (size_t)env_int("MPSB_SVD_L2_MB", 80) * 1024 * 1024;
+    int chunk = (int)std::max<size_t>(1, l2_budget / matbytes);
+    chunk = env_int("MPSB_SVD_CHUNK", chunk);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if (chunk > 65535) chunk = 65535;
+    p.chunk = chunk;
+    p.max_sweeps = env_int("MPSB_SVD_MAX_SWEEPS", 40);
+    *plan = p;
+    return 0;
+}
+
+size_t svd_state_bytes(const SvdPlan& plan) {
+    return align_up(sizeof(int) * plan.batch, 256) * 2 + align_up(sizeof(double) * plan.batch, 256) + 256;
+}
+
+int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, int* sweeps_out) {
+    const SvdState s = carve_state(state, pl.batch);
+    const long long strideX = (long long)pl.n_pad * pl.ld;
+    sweep_begin_kernel<<<(pl.batch + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, pl.batch, 1);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+
+    // QR preconditioning for the whole batch
+    {
+        int CW = std::min(pl.ld, QR_THREADS);
+        int G = QR_THREADS / CW;
+        const size_t wbudget = 96 * 1024;
+        G = std::max(1, std::min<int>(G, (int)(wbudget / ((size_t)pl.ld * sizeof(cplx)))));
+        G = std::min(G, std::max(1, pl.n));
+        const size_t smem = align_up(pl.n, 8) * sizeof(cplx) + (size_t)G * pl.ld * sizeof(cplx) +
+                            align_up(pl.ldot, 8) * sizeof(double) + align_up(pl.ldot, 8) * sizeof(int) + pl.ld + 64;
+        MPSB_REQUIRE(smem <= 220 * 1024, "svd: QR scratch %zu B exceeds shared memory", smem);
+        static size_t configured = 0;
+        if (smem > configured) {
+            MPSB_CHECK_CUDA(cudaFuncSetAttribute(qr_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem));
+            configured = smem;
+        }
+        qr_precond_kernel<<<pl.batch, QR_THREADS, smem, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, G, CW,
+                                                             s.frob2);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+    }
+
+    const double eps = 2.220446049250313e-16;
+    const double tol = sqrt((double)pl.ldot) * eps;
+    const double eabs = 1e-15;
+    const double tol2 = tol * tol, eabs2 = eabs * eabs;
+    const int nblk = pl.n_pad / pl.bsz;
+    const int rounds = nblk - 1;
+    const int inner = (nblk == 2) ? pl.max_sweeps : 1;
+    int max_sweeps_seen = 0;
+    for (int mat0 = 0; mat0 < pl.batch; mat0 += pl.chunk) {
+        const int count = std::min(pl.chunk, pl.batch - mat0);
+        int sweep = 0;
+        for (; sweep < pl.max_sweeps; ++sweep) {
+            for (int r = 0; r < rounds; ++r) {
+                int rc = launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, st);
+                if (rc) return rc;
+            }
+            MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
+            sweep_end_kernel<<<(count + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, mat0, count);
+            MPSB_COUNT_LAUNCH();
+            MPSB_CHECK_CUDA(cudaGetLastError());
+            int n_active = 0;
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (n_active == 0) { ++sweep; break; }
+        }
+        max_sweeps_seen = std::max(max_sweeps_seen, sweep);
+    }
+    if (sweeps_out) *sweeps_out = max_sweeps_seen;
+    return 0;
+}
+
+int svd_finalise(const SvdPlan& pl, const cplx* X, void* state, const SvdOutputs& out, cudaStream_t st) {
+    (void)state;
+    MPSB_REQUIRE(out.s && out.rank && out.k_cap >= 1, "svd_finalise: s, rank and k_cap are required");
+    int npow2 = 1;
+    while (npow2 < pl.n_pad) npow2 <<= 1;
+    const size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
+    MPSB_REQUIRE(smem <= 200 * 1024, "svd_finalise: %d rows exceed the sort buffer", pl.n_pad);
+    static size_t configured = 0;
+    if (smem > configured && smem > 48 * 1024) {
+        MPSB_CHECK_CUDA(cudaFuncSetAttribute(finalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    finalise_kernel<<<pl.batch, FIN_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, pl.n, pl.n_pad, npow2,
+                                                        pl.ldot, pl.ltot, pl.ld, out);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mpsb

@@ -1,0 +1,98 @@
+// Internal (C++) interfaces between the translation units of libmps_b200.  The public surface is
+// include/mpsb.h; nothing here crosses the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include "common.cuh"
+
+namespace mpsb {
+
+// ---- batched complex128 GEMM (zgemm.cu) ------------------------------------------------------
+// C[z1,z2] = op(A[z1,z2]) * op(B[z1,z2]) (+ C[z1,z2]); op: 0 = N, 1 = T, 2 = C (conj-transpose),
+// 3 = J (conjugate, no transpose).  M, N, K are the dimensions of the product (after op).
+struct GemmArgs {
+    const cplx* A;
+    const cplx* B;
+    cplx* C;
+    int M, N, K;
+    int lda, ldb, ldc;
+    int opA, opB;
+    int batch1, batch2;            // grid.z = batch1 * batch2, z1 = z / batch2, z2 = z % batch2
+    long long sA1, sA2, sB1, sB2, sC1, sC2;  // element strides of the two batch levels
+    int accumulate;
+};
+int zgemm(const GemmArgs& p, cudaStream_t st);
+
+// ---- truncated SVD by QR-preconditioned one-sided Jacobi (jacobi_svd.cu) -----------------------
+// The work matrix X of one problem is n_pad x ld complex128, row-major.  Its first `ldot` columns
+// hold the matrix m whose rows get orthogonalised (Q^H m = S Vh); columns [ldot, ltot) ride along
+// (they receive the same left rotations), which is how U (identity carried) or the gauge carry
+// Vh.M[i+1] are produced without a separate accumulation.
+struct SvdPlan {
+    int batch;       // number of problems
+    int n;           // real rows of m
+    int n_pad;       // rows of X, multiple of 2*bsz
+    int ldot;        // columns entering the inner products
+    int ltot;        // columns rotated (>= ldot)
+    int ld;          // row pitch of X in elements, multiple of 32, >= ltot
+    int bsz;         // rows per Jacobi block (power of two, 1..16)
+    int chunk;       // problems swept together (L2 residency)
+    int max_sweeps;
+};
+int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan);
+size_t svd_state_bytes(const SvdPlan& plan);   // per-call scratch besides X (flags, counters, order)
+// Runs QR preconditioning + Jacobi sweeps on X in place.  `state` is svd_state_bytes() of scratch.
+int svd_orthogonalise(const SvdPlan& plan, cplx* X, void* state, cudaStream_t st, int* sweeps_out);
+// Sorts rows by norm, applies the reference truncation rule (DMRG/MPS.py:33-38) and scatters:
+//   vh_out[b][i][0:ldot]   = X[row_i][0:ldot] / s_i          (i < k; rows k..k_cap-1 zeroed)
+//   aug_out[b][i][0:ltot-ldot] = X[row_i][ldot:ltot]         (i < k; rows k..k_cap-1 zeroed)
+//   s_out[b][i]            = normalised kept values (zeros beyond k),  s_raw[b][i] = raw row norms
+struct SvdOutputs {
+    cplx* vh;   long long vh_stride;  int vh_ld;    // may be null
+    cplx* aug;  long long aug_stride; int aug_ld;   // may be null
+    int aug_conj;                                    // conjugate the carried part on output
+    double* s;  long long s_stride;                  // k_cap values per problem
+    double* s_raw; long long s_raw_stride; int n_raw;  // may be null; n_raw values per problem
+    int* rank;                                       // one int per problem
+    int k_cap;                                       // rows written per problem (>= trun not required)
+    int trun; double err;
+    int normalise;                                   // 1: reference `truncate`; 0: iDMRG `halve` (no eps, raw S)
+};
+int svd_finalise(const SvdPlan& plan, const cplx* X, void* state, const SvdOutputs& out, cudaStream_t st);
+
+// ---- small fused element-wise kernels (tebd.cu, gauge.cu, heff.cu) ------------------------------
+int gate_scale(int batch, int chil, int chir, int d, const cplx* theta0, long long s_theta0,
+               const cplx* U, long long s_U, const double* Sl, long long s_Sl, cplx* thetaB,
+               long long s_thetaB, cplx* X, long long s_X, int ldX, cudaStream_t st);
+
+int one_site(int batch, int chil, int chir, int d, const cplx* M, long long sM, const cplx* U, long long sU,
+             cplx* Mo, long long sMo, cudaStream_t st);
+
+// ---- layout helpers (aux.cu) ---------------------------------------------------------------------
+// Describes how an (i, j) element of a logical matrix is fetched from memory:
+//   value = conj?( src[i * rs + j * cs] ) * (scale ? scale[(j / sdiv) % smod] : 1)
+struct MatSrc {
+    const cplx* src;
+    long long rs, cs;
+    int conj;
+    const double* scale;   // may be null; indexed by column j as (j / sdiv) % smod
+    int sdiv, smod;
+};
+// X[i][0:ldot] <- dot (rows x ldot), X[i][ldot:ltot] <- aug (rows x (ltot-ldot)) or identity when
+// aug.src == nullptr and identity != 0; everything else in the n_pad x ld buffer is zeroed.
+int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, const MatSrc& dot, const MatSrc& aug,
+                     int identity, cudaStream_t st);
+// out[j * ldo + i] = conj?(in[i * ldi + j]),  i < rows, j < cols
+int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st);
+// out[c][a][b] = in[a][b][c]  (n_ab = a*b merged)   and the inverse
+int perm_last_to_first(const cplx* in, int n_ab, int n_c, cplx* out, cudaStream_t st);
+int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_t st);
+// y[j] = sum_i conj(V[j][i]) w[i]  for j < m (deterministic two-pass reduction); part: m * nchunk scratch
+int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
+                cudaStream_t st);
+// w[i] += sum_j c[j] V[j][i]   (c on device, m entries; sign folded into c by the caller)
+int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, cplx* w, cudaStream_t st);
+// w[i] = alpha * w[i]  (alpha real, on host)
+int zdscal(long long n, double alpha, cplx* w, cudaStream_t st);
+
+}  // namespace mpsb

@@ -1,0 +1,131 @@
+/* libmps_b200 — C ABI of the B200-native matrix-product-state two-site update.
+ *
+ * The reference (peijunz-archive/DMRG) is pure Python and has no FFI of its own; the boundary it
+ * offers is its Python API.  Each entry point below replaces the numerical body of
+ * one reference function; the Python shim in dmrg_b200/ keeps the reference's names and signatures
+ * and reaches these symbols through ctypes (see INTEGRATION.md for the binding a maintainer of the
+ * reference would add).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; mpsb_last_error() gives the message;
+ *  - all pointers are DEVICE pointers unless the name ends in `_host`; complex numbers are numpy's
+ *    complex128 layout (interleaved re, im doubles); tensors are C-contiguous unless a leading
+ *    dimension / stride is passed; strides are in ELEMENTS of the pointed-to type;
+ *  - the library never allocates device memory: scratch comes from the caller (`ws`, sized by the
+ *    matching *_workspace() query) — PyTorch tensors are the allocator;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous
+ *    except where noted (the SVD polls a convergence counter once per Jacobi sweep);
+ *  - thread-safety: one host thread per (device, stream).
+ */
+#ifndef MPSB_H
+#define MPSB_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int mpsb_version(void);
+const char* mpsb_last_error(void);
+/* number of kernels launched by the library in this process (bench.py: gpu_launches) */
+unsigned long long mpsb_launch_count(void);
+
+/* Batched complex128 GEMM on FP64 tensor cores:  C[b] = op(A[b]) op(B[b]) (+ C[b]).
+ * op codes: 0 = N, 1 = T, 2 = C (conjugate transpose), 3 = J (conjugate).  Two batch levels
+ * (batch1 x batch2) with independent element strides.  Replaces the reference's multi-operand
+ * np.einsum loops: DMRG/MPS.py:264,284,325,351-355,384-388,423,445,454; DMRG/iDMRG.py:40,59,60. */
+int mpsb_zgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+               int ldc, int batch1, int batch2, long long sA1, long long sA2, long long sB1, long long sB2,
+               long long sC1, long long sC2, int accumulate, void* stream);
+
+/* Truncated SVD  m = U diag(s) Vh  of `batch` matrices (rows x cols, row pitch lda, batch stride sA).
+ * Replaces svd_truncate / truncate (DMRG/MPS.py:14-45) when normalise = 1:
+ *     s /= s[0];  k = min(#{s > err}, trun);  s = s[:k] / ||s[:k]||
+ * and halve's SVD (DMRG/iDMRG.py:23-31) when normalise = 0:  k = min(trun, min(rows, cols)), raw s.
+ * Outputs (k_cap = rows of capacity per problem; entries beyond the rank k are zero):
+ *     Vh  [batch][k_cap][cols]   (pitch cols)           — always
+ *     Uh  [batch][k_cap][rows]   = U^H (pitch rows)      — if Uh != NULL
+ *     S   [batch][k_cap]          kept values (normalised when normalise = 1)
+ *     S_raw [batch][min(rows,cols)] all singular values, unnormalised — if S_raw != NULL
+ *     rank[batch]
+ * Singular vectors carry an arbitrary phase per singular value (as LAPACK's do). */
+size_t mpsb_svd_trunc_workspace(int batch, int rows, int cols, int want_u);
+int mpsb_svd_trunc(int batch, int rows, int cols, const void* A, int lda, long long sA, int trun, double err,
+                   int normalise, int k_cap, void* Vh, void* Uh, double* S, double* S_raw, int* rank, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* TEBD two-site update, batched over independent bonds (MPS.update_double, DMRG/MPS.py:428-457):
+ *     thetaB[l,a,b,k] = sum_{c,j,r} Bi[l,c,r] Bj[r,j,k] U[a,b,c,j]          (:445)
+ *     m = Sl[l] * thetaB;  (s, Vh) = svd_truncate(m as (chil*d) x (d*chir), trun, err)   (:446-449)
+ *     Bi'[l,a,m] = sum_{b,k} thetaB[l,a,b,k] conj(Vh[m,b,k]);   Bj' = Vh;   Sr = s       (:453-455)
+ * Shapes (k_cap = capacity of the new middle bond, k_cap >= min(trun, d*chil, d*chir) recommended):
+ *     Bi [chil][d][chi]  Bj [chi][d][chir]  Sl [chil]  U [d][d][d][d]      (batch strides sBi, sBj, sSl, sU;
+ *                                                                            sU = 0 shares one gate)
+ *     Bi_out [chil][d][k_cap]   Bj_out [k_cap][d][chir]   Sr_out [k_cap]   rank [1]   (strides sBio, sBjo, sSr)
+ * Outputs may alias the inputs (the inputs are consumed before anything is written).
+ * Entries beyond the new rank are written as zeros, so zero-padded tensors stay zero-padded and the
+ * result does not depend on the padding. */
+size_t mpsb_tebd_two_site_workspace(int batch, int chil, int chi, int chir, int d);
+int mpsb_tebd_two_site(int batch, int chil, int chi, int chir, int d, const void* Bi, long long sBi, const void* Bj,
+                       long long sBj, const double* Sl, long long sSl, const void* U, long long sU, int trun,
+                       double err, int k_cap, void* Bi_out, long long sBio, void* Bj_out, long long sBjo,
+                       double* Sr_out, long long sSr, int* rank, void* ws, size_t ws_bytes, void* stream);
+
+/* One-site gate (MPS.update_single, DMRG/MPS.py:423):  M'[l,e,r] = sum_c U[e,c] M[l,c,r].  In place allowed. */
+int mpsb_one_site(int batch, int chil, int chir, int d, const void* M, long long sM, const void* U, long long sU,
+                  void* M_out, long long sMo, void* stream);
+
+/* Gauge steps of MPS.canon (DMRG/MPS.py:246-284).  Left step on site i:
+ *     m = (Sl * M_i) as (chil*d) x chir;  u, s, vh = svd_truncate(m);  M_i <- u;  Sr <- s;  M_next <- vh . M_next
+ * Right step on site i:
+ *     m = (M_i * Sr) as chil x (d*chir);  M_i <- vh;  Sl <- s;  M_prev <- M_prev . u
+ * M_next is [chir][nnext] (any trailing shape flattened), M_prev is [nprev][chil].
+ * Outputs are written with the new bond dimension padded to k_cap (zeros beyond the rank). */
+size_t mpsb_gauge_workspace(int chil, int chir, int d, int nother, int k_cap);
+int mpsb_gauge_left(int chil, int chir, int d, const void* M, const double* Sl, const void* M_next, int nnext,
+                    int trun, double err, int k_cap, void* M_out, double* Sr_out, void* M_next_out, int* rank,
+                    void* ws, size_t ws_bytes, void* stream);
+int mpsb_gauge_right(int chil, int chir, int d, const void* M, const double* Sr, const void* M_prev, int nprev,
+                     int trun, double err, int k_cap, void* M_out, double* Sl_out, void* M_prev_out, int* rank,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* Transfer-matrix step shared by MPS.dot and MPS.corr (DMRG/MPS.py:351-355, 384-388):
+ *     E'[o,r] = sum_{k,l,i,j} E[k,l] conj(A[k,i,o]) Op[i,j] B[l,j,r]      (Op = NULL means identity)
+ * A is [ka][d][oa], B is [kb][d][rb], E is [ka][kb], E' is [oa][rb]. */
+size_t mpsb_transfer_workspace(int ka, int kb, int d, int oa, int rb);
+int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, const void* A, const void* B,
+                       const void* Op, void* E_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Matrix-free effective-Hamiltonian product (replaces building DMRG/iDMRG.py:38-40 and the dense
+ * matvec inside eigsh, :57):
+ *     out[A,B,C,D] = sum L[A,a,i] W[i,j,B,b] W[j,k,C,c] R[D,d,k] theta[a,b,c,d]
+ * L [chil][chil][w], R [chir][chir][w], W [w][w][d][d], theta/out [chil][d][d][chir]. */
+size_t mpsb_heff_workspace(int chil, int chir, int d, int w);
+int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
+                     void* out, void* ws, size_t ws_bytes, void* stream);
+
+/* Lowest eigenpair of the effective Hamiltonian by Lanczos with full reorthogonalisation and
+ * restarts (replaces eigsh(k=1, which='SA'), DMRG/iDMRG.py:57).  theta holds the start vector on
+ * entry (must be non-zero) and the normalised ground vector on exit.  Results (host pointers):
+ * energy_host, resid_host (||H v - E v||), n_matvec_host.  Synchronous. */
+size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov);
+int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
+                        int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
+                        int* n_matvec_host, void* ws, size_t ws_bytes, void* stream);
+
+/* Environment growth (DMRG/iDMRG.py:59-60, with the conjugation on the bra leg — SURVEY App. B1):
+ *     L'[A,B,C] = sum L[i,j,k] conj(U[i,l,A]) U[j,m,B] W[k,C,l,m]        U [chi][d][chin]
+ *     R'[A,B,C] = sum R[i,j,k] conj(V[A,l,i]) V[B,m,j] W[C,k,l,m]        V [chin][d][chi]
+ * swap_conj = 1 reproduces the reference's as-written conjugation (identical for real U, V). */
+size_t mpsb_env_workspace(int chi, int chin, int d, int w);
+int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U, const void* W, int swap_conj,
+                  void* L_out, void* ws, size_t ws_bytes, void* stream);
+int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
+                   void* R_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Diagnostics of the last SVD call on this thread: number of Jacobi sweeps of the slowest problem. */
+int mpsb_last_svd_sweeps(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPSB_H */
