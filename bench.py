@@ -1,0 +1,288 @@
+"""Benchmark of the hot path: batched TEBD two-site updates (fp64 complex, chi = 128, d = 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--chains C] [--impl reference]
+
+One step = one call of mpsb_tebd_two_site over C independent chi = 128 bonds resident on the GPU (the
+per-GPU shard of BASELINE config 4: 4096 chains / 8 GPUs = 512).  Weak scaling: every rank owns C chains, no
+data-path collective.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHI, D, TRUN, ERR = 128, 2, 128, 1e-14
+METRIC = "two-site updates/sec (fp64, chi=128, batched)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(n, seed0):
+    """n synthetic saturated bonds (host, complex128).  Recipe shared with the CPU leg (oracle/cpu_bench.py) but
+    re-stated here so the GPU arm does not import anything under oracle/."""
+    import scipy.linalg as la
+    Bi = np.empty((n, CHI, D, CHI), dtype=complex)
+    Bj = np.empty((n, CHI, D, CHI), dtype=complex)
+    Sl = np.empty((n, CHI))
+    U = np.empty((n, D, D, D, D), dtype=complex)
+    for c in range(n):
+        rs = np.random.RandomState(seed0 + c)
+        for B in (Bi, Bj):
+            q, _ = np.linalg.qr(rs.randn(D * CHI, CHI) + 1j * rs.randn(D * CHI, CHI))
+            B[c] = q.conj().T.reshape(CHI, D, CHI)
+        s = np.linalg.svd(rs.randn(CHI, CHI) + 1j * rs.randn(CHI, CHI), compute_uv=False)
+        Sl[c] = s / np.linalg.norm(s)
+        A = rs.randn(D * D, D * D) + 1j * rs.randn(D * D, D * D)
+        U[c] = la.expm(-0.05j * (A + A.conj().T)).reshape([D] * 4)
+    return Bi, Bj, Sl, U
+
+
+def cpu_leg(per_worker):
+    from oracle import cpu_bench
+    ups, cores, total, wall = cpu_bench.run(per_worker, CHI, D, TRUN, ERR)
+    return {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
+            "sample": f"{total} update_double calls on synthetic chi={CHI} d={D} bonds ({per_worker} per worker, one "
+                      f"worker per core, OMP_NUM_THREADS=1), oracle/mps_oracle.py (numpy tensordot + LAPACK zgesdd); "
+                      f"wall {wall:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the box's host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    times = []
+    for _ in range(args.warmup):
+        cpu_leg(2)
+    cb = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cb = cpu_leg(args.cpu_updates)
+        times.append(time.perf_counter() - t0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": {"workload": f"TEBD two-site update, chi={CHI}, d={D}, complex128, saturated bonds",
+                       "chains_per_step": cb["cores"] * args.cpu_updates},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "updates/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chains", type=int, default=512, help="independent chi=128 bonds per GPU per step")
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-updates", type=int, default=24, help="oracle updates per CPU worker in the baseline leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    g.build()
+    from dmrg_b200 import _lib as L
+    lib = L.load()
+    import ctypes
+
+    n = args.chains
+    Bi_h, Bj_h, Sl_h, U_h = make_inputs(n, 1000 + rank * n)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    Bi_p, Bj_p, Sl_p, U_p = pin(Bi_h), pin(Bj_h), pin(Sl_h), pin(U_h)
+    dev = torch.device("cuda", local)
+    Bi, Bj, Sl, U = (t.to(dev) for t in (Bi_p, Bj_p, Sl_p, U_p))
+    Bio, Bjo = torch.empty_like(Bi), torch.empty_like(Bj)
+    Sro = torch.empty((n, CHI), dtype=torch.float64, device=dev)
+    rk = torch.empty((n,), dtype=torch.int32, device=dev)
+    Bio_p, Bjo_p = torch.empty_like(Bi_p).pin_memory(), torch.empty_like(Bj_p).pin_memory()
+    Sro_p, rk_p = torch.empty((n, CHI), dtype=torch.float64).pin_memory(), torch.empty((n,), dtype=torch.int32).pin_memory()
+    ws, wsn = L.workspace(lib.mpsb_tebd_two_site_workspace(n, CHI, CHI, CHI, D))
+    site = CHI * D * CHI
+
+    def step():
+        L.check(lib.mpsb_tebd_two_site(n, CHI, CHI, CHI, D, L.ptr(Bi), site, L.ptr(Bj), site, L.ptr(Sl), CHI, L.ptr(U),
+                                       D ** 4, TRUN, ERR, CHI, L.ptr(Bio), site, L.ptr(Bjo), site, L.ptr(Sro), CHI,
+                                       L.ptr(rk), ws, wsn, L.stream_ptr()), "mpsb_tebd_two_site")
+
+    def e2e_step():
+        Bi.copy_(Bi_p, non_blocking=True); Bj.copy_(Bj_p, non_blocking=True)
+        Sl.copy_(Sl_p, non_blocking=True); U.copy_(U_p, non_blocking=True)
+        step()
+        Bio_p.copy_(Bio, non_blocking=True); Bjo_p.copy_(Bjo, non_blocking=True)
+        Sro_p.copy_(Sro, non_blocking=True); rk_p.copy_(rk, non_blocking=True)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k):
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        fence()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    # --- device-resident throughput, with phase timing on the library's stream --------------------------------
+    lib.mpsb_profile_enable(1)
+    phases = np.zeros(6)
+    rot = sweeps = 0
+    launches0 = L.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    fence()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        ph = (ctypes.c_double * 6)()
+        r_, s_ = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        L.check(lib.mpsb_profile_read(ph, ctypes.byref(r_), ctypes.byref(s_)), "mpsb_profile_read")
+        phases += np.array(list(ph)); rot += r_.value; sweeps += s_.value
+    e1.record()
+    fence()
+    clocks = sampler.stop()
+    launches = L.launch_count() - launches0
+    lib.mpsb_profile_enable(0)
+    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    value = world * n * args.steps / (ms_total * 1e-3)
+    ranks_ok = bool((rk == CHI).all().item())
+    sv_sweeps = lib.mpsb_last_svd_sweeps()
+
+    # --- end to end through host buffers ---------------------------------------------------------------------------
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (Bi_p, Bj_p, Sl_p, U_p))
+    d2h = sum(t.numel() * t.element_size() for t in (Bio_p, Bjo_p, Sro_p, rk_p))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # --- FP64 roofline denominator: cuBLAS DGEMM measured here (MEASURED_PEAKS.json has no FP64 entry) ---------
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(); torch.matmul(a, b); t1.record(); torch.cuda.synchronize()
+        best = min(best, t0.elapsed_time(t1))
+    fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+
+    nrow, ncol = CHI * D, D * CHI
+    npairs = nrow * (nrow - 1) // 2
+    k_steps = args.steps
+    jac_flop = sweeps * npairs * 16.0 * ncol + rot * 24.0 * ncol          # algorithmic flops of the Jacobi phase
+    jac_s = phases[3] * 1e-3
+    gemm_flop = k_steps * n * 8.0 * (nrow * CHI * ncol + nrow * ncol * CHI)
+    gemm_s = (phases[0] + phases[5]) * 1e-3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    roofline = {"kernel": "jacobi_round_kernel (all sweeps of one step)", "bound": "fp64", "achieved": jac_flop / jac_s / 1e12,
+                "peak": fp64_peak, "unit": "TFLOP/s", "frac": jac_flop / jac_s / 1e12 / fp64_peak, "traffic": None,
+                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "share_of_step": float(phases[3] / phases.sum())}
+    roof_gemm = {"kernel": "zgemm_kernel (theta formation + back-projection, DMMA m8n8k4)", "bound": "tensor",
+                 "achieved": gemm_flop / gemm_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                 "frac": gemm_flop / gemm_s / 1e12 / fp64_peak, "traffic": None,
+                 "share_of_step": float((phases[0] + phases[5]) / phases.sum())}
+    hbm_bytes = k_steps * n * (2 * site * 16 + CHI * 8 + 2 * site * 16 + CHI * 8)
+    line = {"metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": {"workload": f"config 4 shard: {n} independent chains/GPU, one saturated chi={CHI} d={D} complex128 "
+                                   f"two-site update each per step (trun={TRUN}, err={ERR})",
+                       "chains_per_gpu": n, "chi": CHI, "d": D,
+                       "inputs": "right-isometric B tensors, Gaussian Schmidt spectrum, per-chain GUE gate dt=0.05",
+                       "l2": f"inputs {2 * n * site * 16 / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)",
+                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": roofline, "roofline_contractions": roof_gemm,
+            "phases_ms_per_step": {k: float(v / k_steps) for k, v in zip(
+                ["theta_gemm", "gate", "qr", "jacobi", "finalise", "backproj_gemm"], phases)},
+            "svd": {"sweeps_slowest_problem": int(sv_sweeps), "rotations_per_update": rot / (k_steps * n),
+                    "sweeps_per_update": sweeps / (k_steps * n), "all_ranks_full": ranks_ok},
+            "hbm_mandatory_gbs": hbm_bytes / (ms_total * 1e-3) / 1e9,
+            "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_leg(args.cpu_updates)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

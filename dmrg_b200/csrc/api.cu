@@ -14,6 +14,16 @@ unsigned long long g_launch_count = 0;
 static thread_local char g_error[1024] = "";
 static thread_local int g_last_sweeps = 0;
 
+Profile g_prof = {};
+void prof_mark(int idx, cudaStream_t st) {
+    if (!g_prof.enabled) return;
+    if (!g_prof.have_events) {
+        for (int i = 0; i < 8; ++i) cudaEventCreate(&g_prof.ev[i]);
+        g_prof.have_events = 1;
+    }
+    cudaEventRecord(g_prof.ev[idx], st);
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -80,6 +90,20 @@ int mpsb_version(void) { return 100; }
 const char* mpsb_last_error(void) { return g_error; }
 unsigned long long mpsb_launch_count(void) { return g_launch_count; }
 int mpsb_last_svd_sweeps(void) { return g_last_sweeps; }
+
+void mpsb_profile_enable(int on) { g_prof.enabled = on; }
+int mpsb_profile_read(double* phase_ms, unsigned long long* rotations, unsigned long long* problem_sweeps) {
+    MPSB_REQUIRE(g_prof.enabled && g_prof.have_events, "profile_read: profiling was not enabled for the last call");
+    MPSB_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[6]));
+    for (int i = 0; i < 6; ++i) {
+        float ms = 0.f;
+        MPSB_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+        phase_ms[i] = ms;
+    }
+    if (rotations) *rotations = g_prof.rotations;
+    if (problem_sweeps) *problem_sweeps = g_prof.problem_sweeps;
+    return 0;
+}
 
 int mpsb_zgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
                int ldc, int batch1, int batch2, long long sA1, long long sA2, long long sB1, long long sB2,
@@ -164,6 +188,7 @@ int mpsb_tebd_two_site(int batch, int chil, int chi, int chir, int d, const void
     const long long sTheta = (long long)n * l, sX = (long long)pl.n_pad * pl.ld;
 
     // theta0[(l,c),(j,k)] = sum_r Bi[(l,c), r] Bj[r, (j,k)]        (DMRG/MPS.py:445, first two operands)
+    prof_mark(0, st);
     GemmArgs g;
     g.A = static_cast<const cplx*>(Bi); g.B = static_cast<const cplx*>(Bj); g.C = theta0;
     g.M = n; g.N = l; g.K = chi; g.lda = chi; g.ldb = l; g.ldc = l; g.opA = 0; g.opB = 0;
@@ -171,11 +196,13 @@ int mpsb_tebd_two_site(int batch, int chil, int chi, int chir, int d, const void
     g.accumulate = 0;
     rc = zgemm(g, st);
     if (rc) return rc;
+    prof_mark(1, st);
     if (pl.n_pad != n || pl.ld != l) MPSB_CHECK_CUDA(cudaMemsetAsync(X, 0, sizeof(cplx) * sX * batch, st));
     // thetaB = U . theta0 ; X = Sl * thetaB                        (:445 third operand, :446)
     rc = gate_scale(batch, chil, chir, d, theta0, sTheta, static_cast<const cplx*>(U), sU, Sl, sSl, thetaB, sTheta, X,
                     sX, pl.ld, st);
     if (rc) return rc;
+    prof_mark(2, st);
     // (s, Vh) = svd_truncate(X) -> Bj' = Vh, Sr = s, rank = k       (:448-452, :455)
     rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
     if (rc) return rc;
@@ -186,11 +213,19 @@ int mpsb_tebd_two_site(int batch, int chil, int chi, int chir, int d, const void
     o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
     rc = svd_finalise(pl, X, state, o, st);
     if (rc) return rc;
+    prof_mark(5, st);
     // Bi'[(l,a), m] = sum_{(b,k)} thetaB[(l,a),(b,k)] conj(Vh[m,(b,k)])   (:454)
     g.A = thetaB; g.B = static_cast<const cplx*>(Bj_out); g.C = static_cast<cplx*>(Bi_out);
     g.M = n; g.N = k_cap; g.K = l; g.lda = l; g.ldb = l; g.ldc = k_cap; g.opA = 0; g.opB = 2;
     g.sA1 = sTheta; g.sB1 = sBjo; g.sC1 = sBio;
-    return zgemm(g, st);
+    rc = zgemm(g, st);
+    prof_mark(6, st);
+    return rc;
+}
+
+int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int ldo, int conj, void* stream) {
+    return transpose_conj(static_cast<const cplx*>(in), ldi, rows, cols, static_cast<cplx*>(out), ldo, conj,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int mpsb_one_site(int batch, int chil, int chir, int d, const void* M, long long sM, const void* U, long long sU,

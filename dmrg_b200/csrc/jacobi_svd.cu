@@ -37,6 +37,8 @@ struct SvdState {           // device scratch, carved out of the caller's worksp
     int* done;              // [batch] 1 once a sweep applied no rotation
     double* frob2;          // [batch] squared Frobenius norm of the dot part
     int* n_active;          // [1]
+    unsigned long long* rot_total;      // [1] rotations applied over the whole call
+    unsigned long long* sweep_total;    // [1] sum over problems of sweeps executed
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -48,6 +50,8 @@ SvdState carve_state(void* state, int batch) {
     s.done = reinterpret_cast<int*>(p);           p += align_up(sizeof(int) * batch, 256);
     s.frob2 = reinterpret_cast<double*>(p);       p += align_up(sizeof(double) * batch, 256);
     s.n_active = reinterpret_cast<int*>(p);
+    s.rot_total = reinterpret_cast<unsigned long long*>(p + 64);
+    s.sweep_total = reinterpret_cast<unsigned long long*>(p + 128);
     return s;
 }
 
@@ -321,21 +325,24 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
     }
 }
 
-__global__ void sweep_begin_kernel(int* rot, int* done, int* n_active, int batch, int reset_done) {
+__global__ void sweep_begin_kernel(int* rot, int* done, int* n_active, unsigned long long* rot_total,
+                                   unsigned long long* sweep_total, int batch, int reset_done) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *n_active = 0;
+    if (i == 0) { *n_active = 0; *rot_total = 0ull; *sweep_total = 0ull; }
     if (i < batch) {
         rot[i] = 0;
         if (reset_done) done[i] = 0;
     }
 }
-__global__ void sweep_end_kernel(int* rot, int* done, int* n_active, int mat0, int count) {
+__global__ void sweep_end_kernel(int* rot, int* done, int* n_active, unsigned long long* rot_total,
+                                 unsigned long long* sweep_total, int mat0, int count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) {
         const int m = mat0 + i;
         if (!done[m]) {
+            atomicAdd(sweep_total, 1ull);
             if (rot[m] == 0) done[m] = 1;
-            else atomicAdd(n_active, 1);
+            else { atomicAdd(n_active, 1); atomicAdd(rot_total, (unsigned long long)rot[m]); }
         }
         rot[m] = 0;
     }
@@ -526,7 +533,8 @@ size_t svd_state_bytes(const SvdPlan& plan) {
 int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, int* sweeps_out) {
     const SvdState s = carve_state(state, pl.batch);
     const long long strideX = (long long)pl.n_pad * pl.ld;
-    sweep_begin_kernel<<<(pl.batch + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, pl.batch, 1);
+    sweep_begin_kernel<<<(pl.batch + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, s.rot_total, s.sweep_total,
+                                                               pl.batch, 1);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
 
@@ -552,6 +560,7 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         MPSB_CHECK_CUDA(cudaGetLastError());
     }
 
+    prof_mark(3, st);
     const double eps = 2.220446049250313e-16;
     const double tol = sqrt((double)pl.ldot) * eps;
     const double eabs = 1e-15;
@@ -569,7 +578,8 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
                 if (rc) return rc;
             }
             MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
-            sweep_end_kernel<<<(count + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, mat0, count);
+            sweep_end_kernel<<<(count + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, s.rot_total, s.sweep_total,
+                                                                  mat0, count);
             MPSB_COUNT_LAUNCH();
             MPSB_CHECK_CUDA(cudaGetLastError());
             int n_active = 0;
@@ -580,6 +590,15 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         max_sweeps_seen = std::max(max_sweeps_seen, sweep);
     }
     if (sweeps_out) *sweeps_out = max_sweeps_seen;
+    prof_mark(4, st);
+    if (g_prof.enabled) {
+        unsigned long long h[2] = {0ull, 0ull};
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(&h[0], s.rot_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(&h[1], s.sweep_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+        g_prof.rotations = h[0];
+        g_prof.problem_sweeps = h[1];
+    }
     return 0;
 }
 

@@ -7,6 +7,19 @@
 
 namespace mpsb {
 
+// ---- optional phase timing (api.cu); bench.py reads it through mpsb_profile_* -------------------
+// Phase boundaries of mpsb_tebd_two_site: 0 start | 1 theta GEMM | 2 gate | 3 QR | 4 Jacobi sweeps |
+// 5 finalise | 6 back-projection GEMM.  CUDA events on the caller's stream, only when enabled.
+struct Profile {
+    int enabled;
+    cudaEvent_t ev[8];
+    int have_events;
+    unsigned long long rotations;       // Jacobi rotations applied in the last SVD
+    unsigned long long problem_sweeps;  // sum over problems of sweeps executed in the last SVD
+};
+extern Profile g_prof;
+void prof_mark(int idx, cudaStream_t st);
+
 // ---- batched complex128 GEMM (zgemm.cu) ------------------------------------------------------
 // C[z1,z2] = op(A[z1,z2]) * op(B[z1,z2]) (+ C[z1,z2]); op: 0 = N, 1 = T, 2 = C (conj-transpose),
 // 3 = J (conjugate, no transpose).  M, N, K are the dimensions of the product (after op).

@@ -122,8 +122,18 @@ int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U,
 int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
                    void* R_out, void* ws, size_t ws_bytes, void* stream);
 
+/* out[j * ldo + i] = conj?(in[i * ldi + j]) for i < rows, j < cols (layout helper of the shim). */
+int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int ldo, int conj, void* stream);
+
 /* Diagnostics of the last SVD call on this thread: number of Jacobi sweeps of the slowest problem. */
 int mpsb_last_svd_sweeps(void);
+
+/* Phase timing of mpsb_tebd_two_site for the roofline report (bench.py).  When enabled, CUDA events are
+ * recorded on the caller's stream at the phase boundaries; mpsb_profile_read returns the 6 phase
+ * durations in ms (theta GEMM, gate, QR, Jacobi sweeps, finalise, back-projection GEMM) of the last
+ * call plus the Jacobi work counters of its SVD. */
+void mpsb_profile_enable(int on);
+int mpsb_profile_read(double* phase_ms, unsigned long long* rotations, unsigned long long* problem_sweeps);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,117 @@
+"""GPU: matrix-free effective Hamiltonian, Lanczos ground state, SVD split and environment growth against the
+oracle and the golden energies generated from the reference's next_LR."""
+import numpy as np
+import pytest
+
+from oracle import idmrg_oracle as io_
+
+pytestmark = pytest.mark.gpu
+
+
+def crand(rs, *shape):
+    return rs.randn(*shape) + 1j * rs.randn(*shape)
+
+
+def test_heff_matvec_golden_and_random(lib, golden):
+    from dmrg_b200 import iDMRG
+    g = golden("heff_small.npz")
+    np.testing.assert_allclose(iDMRG.heff_matvec(g["L"], g["W"], g["R"], g["theta"]), g["out"], atol=1e-12)
+    rs = np.random.RandomState(5)
+    for xl, xr, d, w in ((1, 1, 2, 3), (7, 5, 3, 4), (32, 32, 2, 5), (40, 24, 2, 3)):
+        L, R, W, th = crand(rs, xl, xl, w), crand(rs, xr, xr, w), crand(rs, w, w, d, d), crand(rs, xl, d, d, xr)
+        W[0, 1:] = 0                                        # exercise the zero-block skip
+        ref = io_.heff_matvec(L, W, R, th)
+        np.testing.assert_allclose(iDMRG.heff_matvec(L, W, R, th), ref, atol=1e-11 * np.abs(ref).max())
+
+
+def test_dense_hamiltonian_small(lib, golden):
+    from dmrg_b200 import iDMRG
+    g = golden("heff_small.npz")
+    H = iDMRG.matrixify(iDMRG.Hamiltonian(g["L"][:3, :3], g["W"], g["R"][:2, :2]))
+    ref = io_.heff_dense(g["L"][:3, :3], g["W"], g["R"][:2, :2])
+    np.testing.assert_allclose(H, ref, atol=1e-12)
+
+
+def test_env_updates(lib, golden):
+    from dmrg_b200 import iDMRG
+    g = golden("heff_small.npz")
+    for swap in (True, False):
+        Ln = iDMRG._env(True, lib.to_device(g["L"]), lib.to_device(g["U"]), lib.to_device(g["W"]), swap)
+        Rn = iDMRG._env(False, lib.to_device(g["R"]), lib.to_device(g["V"]), lib.to_device(g["W"]), swap)
+        np.testing.assert_allclose(lib.to_host(Ln), io_.env_left(g["L"], g["U"], g["W"], swap), atol=1e-12)
+        np.testing.assert_allclose(lib.to_host(Rn), io_.env_right(g["R"], g["V"], g["W"], swap), atol=1e-12)
+    np.testing.assert_allclose(lib.to_host(iDMRG._env(True, lib.to_device(g["L"]), lib.to_device(g["U"]),
+                                                     lib.to_device(g["W"]), True)), g["Lnext_ref"], atol=1e-12)
+
+
+def test_halve_matches_lapack(lib):
+    from dmrg_b200 import iDMRG
+    rs = np.random.RandomState(6)
+    psi = crand(rs, 6, 2, 2, 5)
+    U, S, V = iDMRG.halve(psi.ravel(), psi.shape, trunc=4)
+    Uo, So, Vo = io_.halve(psi, psi.shape, 4)
+    assert U.shape == (6, 2, 4) and V.shape == (4, 2, 5) and S.shape == So.shape
+    np.testing.assert_allclose(S, So, rtol=1e-11)
+    Pg = np.tensordot(U, U.conj(), axes=([2], [2]))
+    Po = np.tensordot(Uo, Uo.conj(), axes=([2], [2]))
+    np.testing.assert_allclose(Pg, Po, atol=1e-10)
+
+
+def test_lanczos_ground_state_vs_dense(lib):
+    from dmrg_b200 import iDMRG
+    rs = np.random.RandomState(7)
+    xl, xr, d, w = 6, 5, 2, 3
+    W = io_.tfim_mpo()
+    # hermitian environments from a short real iDMRG run
+    L, R = io_.boundary(3)
+    for _ in range(3):
+        L, R, _ = io_.next_LR(L, R, W, trunc=8)
+    E, theta = iDMRG.ground_state(lib.to_device(L), lib.to_device(W), lib.to_device(R), seed=1)
+    Hd = io_.heff_dense(L, W, R)
+    evals = np.linalg.eigvalsh(Hd)
+    assert abs(E - evals[0]) < 1e-11 * max(1, abs(evals[0]))
+    th = lib.to_host(theta).ravel()
+    assert abs(np.linalg.norm(th) - 1) < 1e-12
+    assert np.linalg.norm(Hd @ th - E * th) < 1e-9
+    assert iDMRG.last_info["residual"] < 1e-9
+
+
+def test_idmrg_tfim_energies_vs_reference_golden(lib, golden):
+    """The reference's shipped driver (DMRG/iDMRG.py:64-76): TFIM, 40 growth steps at trunc = 10, and 12 at 16."""
+    from dmrg_b200 import iDMRG
+    from dmrg_b200.MPO import MPO
+    g = golden("idmrg_energies.npz")
+    W = (-MPO('sx') - MPO('sz') ** 2).tomatrix()
+    np.testing.assert_array_equal(W, g["W"])
+    for trunc, steps in ((10, 40), (16, 12)):
+        L, R = np.array([[[0, 0, 1]]]), np.array([[[1, 0, 0]]])
+        e = []
+        for i in range(steps):
+            L, R, val = iDMRG.next_LR(L, R, W, trunc=trunc)
+            e.append(val / (2 * i + 2))
+        np.testing.assert_allclose(e, g[f"tfim_e_trunc{trunc}"][:steps], rtol=1e-9)
+    # default trunc = 10 like the reference's halve
+    L, R = np.array([[[0, 0, 1]]]), np.array([[[1, 0, 0]]])
+    for i in range(6):
+        L, R, val = iDMRG.next_LR(L, R, W)
+    assert L.shape == (10, 10, 3)
+    assert abs(val / 12 - g["tfim_e_trunc10"][5]) < 1e-10
+    # entanglement entropy of the last split vs the oracle on the same environments
+    S = iDMRG.last_info["S"]
+    assert abs(io_.entropy_from_S(S, 10) - io_.entropy_from_S(S[:10])) < 1e-14
+
+
+def test_idmrg_heisenberg_real_mpo(lib, golden):
+    from dmrg_b200 import iDMRG
+    g = golden("idmrg_energies.npz")
+    Wh = g["heis_W"]
+    L, R = np.zeros((1, 1, 5)), np.zeros((1, 1, 5))
+    L[0, 0, 4] = 1; R[0, 0, 0] = 1
+    e = []
+    for i in range(7):
+        L, R, val = iDMRG.next_LR(L, R, Wh, trunc=10)
+        e.append(val)
+    np.testing.assert_allclose(e[:4], g["heis_e_total"][:4], rtol=1e-10)      # before truncation: exact agreement
+    np.testing.assert_allclose(e, g["heis_e_total"], rtol=1e-6)              # trunc cuts a multiplet: SURVEY App. B1
+    ed = [-3, -6.464102, -9.974309, -13.499730, -17.032141, -20.568363]
+    np.testing.assert_allclose(e[:6], ed, atol=6e-5)

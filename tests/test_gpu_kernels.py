@@ -1,0 +1,201 @@
+"""GPU: each C-ABI entry point against numpy / the oracle on seeded inputs (run with -m gpu)."""
+import numpy as np
+import pytest
+import scipy.linalg as la
+
+from oracle.mps_oracle import OracleMPS, svd_truncate as oracle_svd_truncate
+
+pytestmark = pytest.mark.gpu
+
+
+def crand(rs, *shape):
+    return rs.randn(*shape) + 1j * rs.randn(*shape)
+
+
+OPS = {0: lambda a: a, 1: lambda a: a.T, 2: lambda a: a.conj().T, 3: lambda a: a.conj()}
+
+
+@pytest.mark.parametrize("opA", [0, 1, 2, 3])
+@pytest.mark.parametrize("opB", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 7, 3), (64, 64, 16), (70, 130, 33), (256, 256, 128)])
+def test_zgemm_ops(lib, opA, opB, shape):
+    M, N, K = shape
+    rs = np.random.RandomState(M * 1000 + N * 10 + K + opA * 4 + opB)
+    A = crand(rs, *((M, K) if opA in (0, 3) else (K, M)))
+    B = crand(rs, *((K, N) if opB in (0, 3) else (N, K)))
+    C = lib.matmul(lib.to_device(A), lib.to_device(B), opA, opB)
+    ref = OPS[opA](A) @ OPS[opB](B)
+    np.testing.assert_allclose(lib.to_host(C), ref, rtol=0, atol=1e-13 * K * 4)
+
+
+def test_zgemm_batched_strided_accumulate(lib):
+    rs = np.random.RandomState(3)
+    b1, b2, M, N, K = 3, 2, 20, 24, 9
+    A = crand(rs, b1, b2, M, K)
+    B = crand(rs, b2, K, N)                 # shared over b1 (stride 0)
+    C0 = crand(rs, b1, b2, M, N)
+    Cd = lib.to_device(C0)
+    lib.zgemm(lib.to_device(A), lib.to_device(B), Cd, M, N, K, K, N, N, batch1=b1, batch2=b2, sA=(b2 * M * K, M * K),
+              sB=(0, K * N), sC=(b2 * M * N, M * N), accumulate=True)
+    ref = C0 + np.einsum('xymk,ykn->xymn', A, B)
+    np.testing.assert_allclose(lib.to_host(Cd), ref, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 5), (6, 6), (17, 9), (32, 32), (40, 64), (64, 40), (128, 128),
+                                   (256, 256)])
+def test_svd_trunc_matches_lapack(lib, shape):
+    from dmrg_b200.MPS import svd_truncate
+    rows, cols = shape
+    rs = np.random.RandomState(rows * 31 + cols)
+    m = crand(rs, rows, cols)
+    u, s, vh = svd_truncate(m, trun=10 ** 6, err=1e-13)
+    uo, so, vo = oracle_svd_truncate(m, trun=10 ** 6, err=1e-13)
+    assert s.shape == so.shape
+    np.testing.assert_allclose(s, so, rtol=1e-11, atol=1e-15)
+    k = len(s)
+    s_raw = la.svd(m, compute_uv=False)[:k]
+    np.testing.assert_allclose((u * s_raw) @ vh, m, atol=1e-12 * s_raw[0])          # full rank kept -> exact reconstruction
+    np.testing.assert_allclose(u.conj().T @ u, np.eye(k), atol=1e-12)
+    np.testing.assert_allclose(vh @ vh.conj().T, np.eye(k), atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["decay", "lowrank", "zero", "rowgraded", "degenerate"])
+def test_svd_trunc_hard_spectra(lib, kind):
+    from dmrg_b200.MPS import svd_truncate
+    n = 96
+    rs = np.random.RandomState(17)
+    qu, _ = np.linalg.qr(crand(rs, n, n))
+    qv, _ = np.linalg.qr(crand(rs, n, n))
+    if kind == "decay":            # exponentially decaying Schmidt spectrum over 17 decades
+        m = (qu * np.exp(-np.arange(n) * 40.0 / n)) @ qv
+    elif kind == "lowrank":
+        m = crand(rs, n, n // 3) @ crand(rs, n // 3, n)
+    elif kind == "zero":
+        m = np.zeros((n, n), dtype=complex)
+    elif kind == "rowgraded":
+        m = np.exp(-np.arange(n) * 30.0 / n)[:, None] * crand(rs, n, n)
+    else:                          # AKLT-like exactly degenerate pairs
+        m = (qu * np.repeat(np.exp(-np.arange(n // 2) * 0.5), 2)) @ qv
+    trun, err = 64, 1e-10
+    u, s, vh = svd_truncate(m, trun=trun, err=err)
+    uo, so, vo = oracle_svd_truncate(m, trun=trun, err=err)
+    assert len(s) == len(so)
+    if len(s) == 0:
+        return
+    np.testing.assert_allclose(s, so, rtol=1e-10, atol=1e-14)
+    # projector onto the kept right singular space is gauge invariant when the cut is not inside a multiplet
+    if kind != "degenerate":
+        np.testing.assert_allclose(vh.conj().T @ vh, vo.conj().T @ vo, atol=1e-6)
+    np.testing.assert_allclose(vh @ vh.conj().T, np.eye(len(s)), atol=1e-11)
+    assert lib.load().mpsb_last_svd_sweeps() <= 16
+
+
+def test_one_site_gate(lib):
+    rs = np.random.RandomState(2)
+    for d in (2, 3, 5):
+        M = crand(rs, 3, 7, d, 11)
+        U = crand(rs, 3, d, d)
+        Md = lib.to_device(M)
+        lib.check(lib.load().mpsb_one_site(3, 7, 11, d, lib.ptr(Md), 7 * d * 11, lib.ptr(lib.to_device(U)), d * d,
+                                           lib.ptr(Md), 7 * d * 11, lib.stream_ptr()), "one_site")
+        np.testing.assert_allclose(lib.to_host(Md), np.einsum('blcr,bdc->bldr', M, U), atol=1e-13)
+
+
+def _tebd_call(lib, Bi, Bj, Sl, U, trun, err, kcap):
+    """Batched mpsb_tebd_two_site on host arrays [b, ...]; returns host outputs."""
+    L = lib.load()
+    b, xl, d, x = Bi.shape
+    xr = Bj.shape[3]
+    per_chain_gate = (U.ndim == 5)
+    bio, bjo = lib.empty((b, xl, d, kcap)), lib.empty((b, kcap, d, xr))
+    sro, rank = lib.empty((b, kcap), "f64"), lib.empty((b,), "i32")
+    ws, wsn = lib.workspace(L.mpsb_tebd_two_site_workspace(b, xl, x, xr, d))
+    lib.check(L.mpsb_tebd_two_site(b, xl, x, xr, d, lib.ptr(lib.to_device(Bi)), xl * d * x, lib.ptr(lib.to_device(Bj)),
+                                   x * d * xr, lib.ptr(lib.to_device(Sl, np.float64)), xl, lib.ptr(lib.to_device(U)),
+                                   d ** 4 if per_chain_gate else 0, trun, err, kcap, lib.ptr(bio), xl * d * kcap,
+                                   lib.ptr(bjo), kcap * d * xr, lib.ptr(sro), kcap, lib.ptr(rank), ws, wsn,
+                                   lib.stream_ptr()), "tebd_two_site")
+    return lib.to_host(bio), lib.to_host(bjo), lib.to_host(sro), lib.to_host(rank)
+
+
+def _oracle_update(Bi, Bj, Sl, U, trun, err):
+    o = OracleMPS([Bi, Bj], trun=trun, err=err)
+    o.s[0] = Sl
+    o.update_double(U, 0)
+    return o.M[0], o.M[1], o.s[1]
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1, 2), (2, 4, 2, 2), (8, 16, 8, 2), (5, 7, 6, 3), (32, 32, 32, 2), (16, 16, 16, 3)])
+def test_tebd_two_site_batch_vs_oracle(lib, dims):
+    xl, x, xr, d = dims
+    rs = np.random.RandomState(sum(dims))
+    b = 5
+    Bi, Bj = crand(rs, b, xl, d, x), crand(rs, b, x, d, xr)
+    Sl = np.abs(rs.randn(b, xl)) + 0.1
+    U = np.stack([la.expm(-0.1j * (h + h.conj().T)).reshape([d] * 4) for h in crand(rs, b, d * d, d * d)])
+    trun, err = 24, 1e-10
+    kcap = max(1, min(trun, d * xl, d * xr))
+    bio, bjo, sro, rank = _tebd_call(lib, Bi, Bj, Sl, U, trun, err, kcap)
+    for c in range(b):
+        Mi, Mj, s = _oracle_update(Bi[c], Bj[c], Sl[c], U[c], trun, err)
+        k = len(s)
+        assert rank[c] == k
+        np.testing.assert_allclose(sro[c, :k], s, rtol=1e-10, atol=1e-15)
+        assert np.all(sro[c, k:] == 0) and np.all(bio[c, :, :, k:] == 0) and np.all(bjo[c, k:] == 0)
+        th_g = np.tensordot(bio[c, :, :, :k], bjo[c, :k], axes=([2], [0]))
+        th_o = np.tensordot(Mi, Mj, axes=([2], [0]))
+        np.testing.assert_allclose(th_g, th_o, atol=1e-9 * max(1.0, np.abs(th_o).max()))
+
+
+def test_tebd_result_independent_of_zero_padding(lib):
+    """Same bond embedded in a zero-padded chi = 24 buffer gives the same Schmidt values and two-site tensor."""
+    rs = np.random.RandomState(9)
+    xl, x, xr, d, P = 6, 9, 7, 2, 24
+    Bi, Bj, Sl = crand(rs, 1, xl, d, x), crand(rs, 1, x, d, xr), np.abs(rs.randn(1, xl)) + 0.1
+    h = crand(rs, 4, 4)
+    U = la.expm(-0.2j * (h + h.conj().T)).reshape(2, 2, 2, 2)
+    trun, err = 24, 1e-12
+    a = _tebd_call(lib, Bi, Bj, Sl, U, trun, err, min(trun, d * xl, d * xr))
+    Bip, Bjp, Slp = np.zeros((1, P, d, P), complex), np.zeros((1, P, d, P), complex), np.zeros((1, P))
+    Bip[0, :xl, :, :x], Bjp[0, :x, :, :xr], Slp[0, :xl] = Bi[0], Bj[0], Sl[0]
+    p = _tebd_call(lib, Bip, Bjp, Slp, U, trun, err, P)
+    k = int(a[3][0])
+    assert int(p[3][0]) == k
+    np.testing.assert_allclose(p[2][0, :k], a[2][0, :k], rtol=1e-11)
+    th_a = np.tensordot(a[0][0, :, :, :k], a[1][0, :k], axes=([2], [0]))
+    th_p = np.tensordot(p[0][0, :xl, :, :k], p[1][0, :k, :, :xr], axes=([2], [0]))
+    np.testing.assert_allclose(th_p, th_a, atol=1e-11)
+    assert np.all(p[0][0, xl:] == 0) and np.all(p[1][0, :, :, xr:] == 0)
+
+
+def test_chi128_bench_unit_golden(lib, golden):
+    """The benchmark's unit of work at full size: chi = 128 bond of the seed-1000 chain (golden from the reference)."""
+    g = golden("chi128_bond7_seed1000.npz")
+    L, d = 16, 2
+    chis = [min(2 ** i, 2 ** (L - i), 128) for i in range(L + 1)]
+    rs = np.random.RandomState(1000)
+    Ms = [crand(rs, chis[i], d, chis[i + 1]) for i in range(L)]
+    A = crand(rs, 4, 4)
+    U = la.expm(-1j * 0.05 * (A + A.conj().T)).reshape([d] * 4)
+    o = OracleMPS(Ms, trun=128, err=1e-14)
+    o.canon()
+    np.testing.assert_allclose(o.s[8], g["s_in"], atol=1e-13)
+    bio, bjo, sro, rank = _tebd_call(lib, o.M[7][None], o.M[8][None], o.s[7][None], U, 128, 1e-14, 128)
+    assert int(rank[0]) == int(g["k"])
+    np.testing.assert_allclose(sro[0], g["Sr"], rtol=1e-10, atol=1e-16)
+    th = np.tensordot(bio[0], bjo[0], axes=([2], [0]))
+    assert abs(la.norm(th) - float(g["theta_fro"])) < 1e-10
+    np.testing.assert_allclose(th[::17, :, :, ::19], g["theta_probe"], atol=1e-11)
+    p = sro[0] ** 2
+    assert abs(-np.sum(p * np.log(p)) + np.sum(g["Sr"] ** 2 * np.log(g["Sr"] ** 2))) < 1e-10     # entanglement entropy
+
+
+def test_transfer_step(lib):
+    from dmrg_b200.MPS import MPS
+    rs = np.random.RandomState(4)
+    ka, kb, d, oa, rb = 5, 6, 3, 7, 4
+    E, A, B, Op = crand(rs, ka, kb), crand(rs, ka, d, oa), crand(rs, kb, d, rb), crand(rs, d, d)
+    out = MPS._transfer(lib.to_device(E), lib.to_device(A), lib.to_device(B), Op)
+    np.testing.assert_allclose(lib.to_host(out), np.einsum('kl,kio,ij,ljr->or', E, A.conj(), Op, B), atol=1e-12)
+    out = MPS._transfer(lib.to_device(E), lib.to_device(A), lib.to_device(B), None)
+    np.testing.assert_allclose(lib.to_host(out), np.einsum('kl,kio,lir->or', E, A.conj(), B), atol=1e-12)

@@ -1,0 +1,183 @@
+"""GPU: the reference's own MPS tests (DMRG/MPS_test.py) ported verbatim onto dmrg_b200.MPS, plus the golden
+vectors generated from the reference and oracle comparisons at larger bond dimension."""
+import numpy as np
+import pytest
+import scipy.linalg as la
+
+from oracle.mps_oracle import OracleMPS
+
+pytestmark = pytest.mark.gpu
+
+
+def test_canon_reference_case(lib, golden):                    # DMRG/MPS_test.py:10-28
+    from dmrg_b200.MPS import MPS
+    s = MPS((1, 2, 2))
+    s.M[0][0, :, :] = np.array([[1, 2 + 1j], [9j, 6j]])
+    s.M[1][:, :, 0] = np.array([[- 1j, 2 - 3j], [0.3, 4]])
+    s.M[1][:, :, 1] = np.array([[5 - 1j, 2 - 3j], [0.3, 4]])
+    s.canon()
+    assert abs(s.dot(s) - 1) < 1e-12
+    for i in s.s:
+        assert abs(la.norm(i) - 1) < 1e-12
+    for i in range(s.L):
+        S = s.block_single(i)
+        TSS = np.einsum("ijk, ijn->kn", S.conj(), S)
+        SST = np.einsum("ijk, ljk->il", S, S.conj())
+        assert la.norm(TSS - np.diag(s.Sr[i]) ** 2) < 1e-12
+        assert la.norm(SST - np.diag(s.Sl[i]) ** 2) < 1e-12
+    s.testCanon(err=1e-12)
+    g = golden("canon_testcanon.npz")
+    for b in range(3):
+        np.testing.assert_allclose(np.asarray(s.s[b], dtype=float), g[f"s{b}"], rtol=1e-10, atol=1e-14)
+
+
+def test_two_body_reference_case(lib, golden):                 # DMRG/MPS_test.py:30-50
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200.spin import sigma
+    s = MPS.naive([1 + 3j, 1], [1 - 8j, 1 - 2j])
+    eig_states = [[0, 0], [0, 1], [1, 0], [1, 1]]
+    eig_vals = np.array([1, -1, -1, 1])
+    s.canon()
+    n = 20
+    H = np.kron(sigma[3], sigma[3])
+    U = la.expm(np.pi / n * 1j * H).reshape([2, 2, 2, 2])
+    phi = np.exp(np.pi / n * 1j * eig_vals)
+    L0 = np.array([s[eig_states[j]] for j in range(4)])
+    H0 = s.corr((0, sigma[3]), (1, sigma[3]))
+    g = golden("two_body.npz")
+    for i in range(n):
+        s.update_double(U, 0)
+        assert abs(H0 - s.corr((0, sigma[3]), (1, sigma[3]))) < 1e-10
+        assert abs(H0 - s.measure(0, H)) < 1e-10
+        L = np.array([s[eig_states[j]] for j in range(4)])
+        L0 *= phi
+        assert la.norm(L - L0) < 1e-10
+        np.testing.assert_allclose(L, g["amps"][i], atol=1e-11)
+    assert abs(H0 - g["zz"]) < 1e-11
+
+
+def test_aklt_reference_case(lib, golden, capsys):             # DMRG/MPS_test.py:52-64
+    from dmrg_b200 import AKLT as ak
+    N = 11
+    s = ak.AKLT_State(N)
+    E = ak.Energy(s)
+    assert abs(E / (N - 1) + 2 / 3) < 1e-12
+    s.canon()
+    n = 5
+    l1 = ak.evolve(s, n=n, time=1, k=10)
+    l2 = np.exp(-1j * E * (np.arange(n) + 1))
+    np.testing.assert_allclose(l1, l2, rtol=1e-7)
+    ak.correlator(s)
+    g = golden("aklt_N11.npz")
+    assert abs(E - g["energy"]) < 1e-11
+    for b in range(N + 1):
+        np.testing.assert_allclose(np.asarray(s.s[b], dtype=float), g[f"s_{b}"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(ak.Z(s), g["sz"], atol=1e-11)
+    np.testing.assert_allclose(l1[:3], g["overlaps"], atol=1e-9)
+    np.testing.assert_allclose([s.corr(*ak.string_op(2, j)) for j in range(3, 9)], g["string"], atol=1e-11)
+
+
+def test_update_double_golden_every_bond(lib, golden):
+    from dmrg_b200.MPS import MPS
+    g = golden("update_double_L6.npz")
+    L = 6
+    for i in range(L - 1):
+        s = MPS([g[f"M_in_{k}"] for k in range(L)], 2, trun=int(g["trun"]), err=float(g["err"]))
+        for b in range(L + 1):
+            s.s[b] = g[f"s_in_{b}"]
+        s.update_double(g["U"], i)
+        assert int(s.xr[i]) == int(g[f"k_out_{i}"])
+        np.testing.assert_allclose(s.Sr[i], g[f"Sr_out_{i}"], rtol=1e-10, atol=1e-15)
+        th = np.tensordot(s.M[i], s.M[i + 1], axes=([2], [0]))
+        np.testing.assert_allclose(th, g[f"theta_out_{i}"], atol=1e-11)
+        s.verify_shape()
+
+
+def test_tfim_quench_golden_and_ed(lib, golden):
+    """iTEBD_double (batched half sweeps) on an L = 10 quench: <Z_i> and all Schmidt spectra vs the reference."""
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200.spin import sigma
+    g = golden("tfim_quench_L10.npz")
+    L = 10
+    s = MPS.naive([[1, 0]] * L)
+    s.trun, s.err = 32, 1e-12
+    s.canon()
+    s.iTEBD_double(g["Hb"], float(g["T"]), int(g["n"]))
+    s.canon()
+    z = np.array([s.corr((i, sigma[3])) for i in range(L)])
+    np.testing.assert_allclose(z, g["z"], rtol=1e-9, atol=1e-10)
+    assert np.max(np.abs(z - g["z_ed"])) < 2e-4
+    for b in range(L + 1):
+        a, r = np.asarray(s.s[b], dtype=float), g[f"s_{b}"]
+        assert len(a) == len(r)
+        np.testing.assert_allclose(a, r, rtol=1e-8, atol=1e-12)
+    ent = lambda v: -np.sum(v ** 2 * np.log(v ** 2))
+    assert abs(ent(np.asarray(s.s[5], dtype=float)) - ent(g["s_5"])) < 1e-10
+
+
+def test_canon_random_chain_vs_oracle(lib):
+    """canon() at bond dimension up to 32 (d = 2) and a d = 3 chain: Schmidt spectra, overlaps, observables."""
+    from dmrg_b200.MPS import MPS
+    for d, chis, seed in ((2, [1, 2, 4, 8, 16, 32, 32, 16, 8, 4, 2, 1], 21), (3, [1, 3, 9, 12, 9, 3, 1], 22)):
+        rs = np.random.RandomState(seed)
+        Ms = [rs.randn(chis[i], d, chis[i + 1]) + 1j * rs.randn(chis[i], d, chis[i + 1]) for i in range(len(chis) - 1)]
+        o = OracleMPS([m.copy() for m in Ms], trun=32, err=1e-12)
+        o.canon()
+        s = MPS([m.copy() for m in Ms], d, trun=32, err=1e-12)
+        s.canon()
+        s.testCanon(err=1e-11)
+        for b in range(len(chis)):
+            np.testing.assert_allclose(np.asarray(s.s[b], dtype=float), o.s[b], rtol=1e-10, atol=1e-14)
+        op = rs.randn(d, d) + 1j * rs.randn(d, d)
+        op = op + op.conj().T
+        site = len(Ms) // 2
+        assert abs(s.corr((site, op)) - o.corr((site, op))) < 1e-11
+        assert abs(s.corr((1, op), (site, op)) - o.corr((1, op), (site, op))) < 1e-11
+        op2 = np.kron(op, op.T)
+        assert abs(s.measure(site, op2) - o.measure(site, op2)) < 1e-11
+        # overlap with a second state
+        Ms2 = [m + 0.1 * (rs.randn(*m.shape) + 1j * rs.randn(*m.shape)) for m in Ms]
+        o2 = OracleMPS(Ms2, trun=32, err=1e-12); o2.canon()
+        s2 = MPS(Ms2, d, trun=32, err=1e-12); s2.canon()
+        assert abs(abs(s.dot(s2)) - abs(o.dot(o2))) < 1e-11
+
+
+def test_update_single_and_copy(lib):
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200 import spin
+    rs = np.random.RandomState(8)
+    Ms = [rs.randn(1, 2, 2) + 0j, rs.randn(2, 2, 2) + 0j, rs.randn(2, 2, 1) + 0j]
+    s = MPS(Ms, 2)
+    s.canon()
+    p = s.copy()
+    U = la.expm(0.3j * spin.sigma[1])
+    p.update_single(U, 1)
+    o = OracleMPS(Ms, trun=20, err=1e-6); o.canon()
+    q = o.copy(); q.update_single(U, 1)
+    assert abs(abs(s.dot(p)) - abs(o.dot(q))) < 1e-12
+    assert abs(s.dot(s) - 1) < 1e-12                       # the copy did not alias the original
+
+
+def test_chain_batch_matches_per_chain_mps(lib):
+    """ChainBatch (padded, in place, one gate per chain) == independent MPS objects, after a short TFIM sweep."""
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200.batched import ChainBatch
+    from dmrg_b200.spin import sigma
+    L, n, cap = 8, 3, 16
+    Z, X, I2 = sigma[3], sigma[1], np.eye(2)
+    gs = [0.5, 1.0, 1.5]
+    Hs = np.stack([-np.kron(Z, Z) - 0.5 * g * (np.kron(X, I2) + np.kron(I2, X)) for g in gs])
+    cb = ChainBatch.product([[1, 0]] * L, n, cap, trun=cap, err=1e-12)
+    cb.tebd(Hs, 0.6, 6, order=2)
+    ent = cb.entropies()
+    for c, g in enumerate(gs):
+        s = MPS.naive([[1, 0]] * L)
+        s.trun, s.err = cap, 1e-12
+        s.canon()
+        s.iTEBD_double(Hs[c], 0.6, 6)
+        Ms, ss = cb.chain(c)
+        for b in range(L + 1):
+            a = np.asarray(s.s[b], dtype=float)
+            assert len(ss[b]) == len(a)
+            np.testing.assert_allclose(ss[b], a, rtol=1e-9, atol=1e-13)
+        assert abs(ent[c, L // 2] + np.sum(np.asarray(s.s[L // 2]) ** 2 * np.log(np.asarray(s.s[L // 2]) ** 2))) < 1e-10
