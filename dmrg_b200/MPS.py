@@ -257,7 +257,8 @@ class MPS:
         s_out = _lib.empty((kcap,), "f64")
         rank = _lib.empty((1,), "i32")
         ws, wsn = _lib.workspace(lib.mpsb_gauge_workspace(xl, xr, d, nnext, kcap))
-        _lib.check(lib.mpsb_gauge_left(xl, xr, d, _lib.ptr(self._dev[i]), _lib.ptr(self._schmidt(i)), _lib.ptr(nxt), nnext,
+        sl = self._schmidt(i)
+        _lib.check(lib.mpsb_gauge_left(xl, xr, d, _lib.ptr(self._dev[i]), _lib.ptr(sl), _lib.ptr(nxt), nnext,
                                        int(self.trun), float(self.err), kcap, _lib.ptr(m_out), _lib.ptr(s_out),
                                        _lib.ptr(nxt_out), _lib.ptr(rank), ws, wsn, _lib.stream_ptr()), "mpsb_gauge_left")
         k = int(rank.item())
@@ -279,7 +280,8 @@ class MPS:
         s_out = _lib.empty((kcap,), "f64")
         rank = _lib.empty((1,), "i32")
         ws, wsn = _lib.workspace(lib.mpsb_gauge_workspace(xl, xr, d, nprev, kcap))
-        _lib.check(lib.mpsb_gauge_right(xl, xr, d, _lib.ptr(self._dev[i]), _lib.ptr(self._schmidt(i + 1)), _lib.ptr(prv),
+        sr = self._schmidt(i + 1)
+        _lib.check(lib.mpsb_gauge_right(xl, xr, d, _lib.ptr(self._dev[i]), _lib.ptr(sr), _lib.ptr(prv),
                                         nprev, int(self.trun), float(self.err), kcap, _lib.ptr(m_out), _lib.ptr(s_out),
                                         _lib.ptr(prv_out), _lib.ptr(rank), ws, wsn, _lib.stream_ptr()), "mpsb_gauge_right")
         k = int(rank.item())

@@ -341,7 +341,16 @@ int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, con
     if (rc) return rc;
     const cplx* Tuse = T;
     if (Op) {   // T2[k][i][r] = sum_j Op[i][j] T[k][j][r]
-        rc = one_site(1, ka, rb, d, T, 0, static_cast<const cplx*>(Op), 0, T2, 0, st);
+        if (d <= 16) {
+            rc = one_site(1, ka, rb, d, T, 0, static_cast<const cplx*>(Op), 0, T2, 0, st);
+        } else {   // fused multi-site operators (measure on n sites: d^n x d^n): one small GEMM per left index
+            GemmArgs h;
+            h.A = static_cast<const cplx*>(Op); h.B = T; h.C = T2;
+            h.M = d; h.N = rb; h.K = d; h.lda = d; h.ldb = rb; h.ldc = rb; h.opA = 0; h.opB = 0;
+            h.batch1 = ka; h.batch2 = 1; h.sA1 = 0; h.sB1 = (long long)d * rb; h.sC1 = (long long)d * rb;
+            h.sA2 = h.sB2 = h.sC2 = 0; h.accumulate = 0;
+            rc = zgemm(h, st);
+        }
         if (rc) return rc;
         Tuse = T2;
     }

@@ -563,7 +563,7 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     prof_mark(3, st);
     const double eps = 2.220446049250313e-16;
     const double tol = sqrt((double)pl.ldot) * eps;
-    const double eabs = 1e-15;
+    const double eabs = 0.0;   // purely relative criterion: kept right singular vectors must be orthonormal to ~tol
     const double tol2 = tol * tol, eabs2 = eabs * eabs;
     const int nblk = pl.n_pad / pl.bsz;
     const int rounds = nblk - 1;
