@@ -181,7 +181,7 @@ def main():
     for _ in range(args.warmup):
         step()
     # --- device-resident throughput, with phase timing on the library's stream --------------------------------
-    lib.mpsb_profile_enable(1)
+    lib.mpsb_profile_enable(int(os.environ.get('MPSB_PROFILE_LEVEL', '1')))
     phases = np.zeros(6)
     rot = sweeps = 0
     launches0 = L.launch_count()

@@ -21,6 +21,7 @@
 // way.  One warp rotates one row pair: inner products by warp shuffles, rotation in place in smem.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
 #include "mpsb_internal.h"
@@ -39,6 +40,7 @@ struct SvdState {           // device scratch, carved out of the caller's worksp
     int* n_active;          // [1]
     unsigned long long* rot_total;      // [1] rotations applied over the whole call
     unsigned long long* sweep_total;    // [1] sum over problems of sweeps executed
+    unsigned long long* phase_clk;      // [4] debug: summed SM clocks of load / rotate / store phases + CTA count
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -52,6 +54,7 @@ SvdState carve_state(void* state, int batch) {
     s.n_active = reinterpret_cast<int*>(p);
     s.rot_total = reinterpret_cast<unsigned long long*>(p + 64);
     s.sweep_total = reinterpret_cast<unsigned long long*>(p + 128);
+    s.phase_clk = reinterpret_cast<unsigned long long*>(p + 192);
     return s;
 }
 
@@ -218,11 +221,73 @@ __device__ __forceinline__ void rr_pair(int m, int r, int s, int& p, int& q) {
     p = a; q = b;
 }
 
+// Rotation parameters from the 2x2 Gram block [[a, c], [conj(c), b]]: the small-angle Jacobi rotation
+//   P' = cs P - g Q,   Q' = conj(g) P + cs Q,   g = sn c/|c|,
+// with t = sgn(z)|c| / (|z| + sqrt(z^2 + |c|^2)), z = (b - a)/2.  One sqrt, one reciprocal, one rsqrt
+// (FP64 div/sqrt are ~20-40 instruction sequences, executed by every lane).
+__device__ __forceinline__ void jacobi_angle(double a, double b, double cr, double ci, double ac2, double& cs,
+                                             double& gr, double& gi) {
+    const double z = 0.5 * (b - a);
+    const double denom = fabs(z) + sqrt(fma(z, z, ac2));       // > 0 because ac2 > 0
+    cs = denom * rsqrt(fma(denom, denom, ac2));
+    const double f = (z >= 0.0 ? cs : -cs) / denom;
+    gr = f * cr;
+    gi = f * ci;
+}
+
 // One warp makes rows P and Q orthogonal over their first `ldot` entries and applies the rotation to
 // all `ltot_r` entries.  Returns 1 if a rotation was applied.  All lanes take the same branch because
 // the butterfly reduction leaves bit-identical sums in every lane.
+// Fast path (ltot_r <= 256): both rows are pulled into registers once (8 complex per lane per row, all
+// loads in flight together), the inner products and the rotation run from registers.
 __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restrict__ Q, int ldot, int ltot_r,
                                            double F2, double tol2, double eabs2, int lane) {
+    (void)F2; (void)eabs2;
+    if (ltot_r <= 256) {
+        cplx x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < ltot_r) { x[j] = P[c]; y[j] = Q[c]; }
+            else { x[j] = make_double2(0.0, 0.0); y[j] = make_double2(0.0, 0.0); }
+        }
+        double a0 = 0.0, b0 = 0.0, cr0 = 0.0, ci0 = 0.0, a1 = 0.0, b1 = 0.0, cr1 = 0.0, ci1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            if (lane + 32 * j < ldot) {
+                a0 = fma(x[j].x, x[j].x, fma(x[j].y, x[j].y, a0));
+                b0 = fma(y[j].x, y[j].x, fma(y[j].y, y[j].y, b0));
+                cr0 = fma(x[j].x, y[j].x, fma(x[j].y, y[j].y, cr0));
+                ci0 = fma(x[j].y, y[j].x, fma(-x[j].x, y[j].y, ci0));
+            }
+            if (lane + 32 * (j + 1) < ldot) {
+                a1 = fma(x[j + 1].x, x[j + 1].x, fma(x[j + 1].y, x[j + 1].y, a1));
+                b1 = fma(y[j + 1].x, y[j + 1].x, fma(y[j + 1].y, y[j + 1].y, b1));
+                cr1 = fma(x[j + 1].x, y[j + 1].x, fma(x[j + 1].y, y[j + 1].y, cr1));
+                ci1 = fma(x[j + 1].y, y[j + 1].x, fma(-x[j + 1].x, y[j + 1].y, ci1));
+            }
+        }
+        const double a = warp_sum(a0 + a1), b = warp_sum(b0 + b1);
+        const double cr = warp_sum(cr0 + cr1), ci = warp_sum(ci0 + ci1);
+        const double ac2 = cr * cr + ci * ci;
+        if (!(ac2 > tol2 * a * b)) return 0;
+        double cs, gr, gi;
+        jacobi_angle(a, b, cr, ci, ac2, cs, gr, gi);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < ltot_r) {
+                cplx xn, yn;
+                xn.x = fma(cs, x[j].x, fma(gi, y[j].y, -gr * y[j].x));
+                xn.y = fma(cs, x[j].y, -fma(gr, y[j].y, gi * y[j].x));
+                yn.x = fma(cs, y[j].x, fma(gr, x[j].x, gi * x[j].y));
+                yn.y = fma(cs, y[j].y, fma(gr, x[j].y, -gi * x[j].x));
+                P[c] = xn;
+                Q[c] = yn;
+            }
+        }
+        return 1;
+    }
     double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
     for (int c = lane; c < ldot; c += 32) {
         const cplx x = P[c], y = Q[c];
@@ -233,20 +298,16 @@ __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restric
     }
     a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
     const double ac2 = cr * cr + ci * ci;
-    if (!(ac2 > tol2 * a * b) || !(ac2 > eabs2 * F2 * fmax(a, b))) return 0;
-    const double ac = sqrt(ac2);
-    const double tau = (b - a) / (2.0 * ac);
-    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-    const double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
-    const double gr = sn * cr / ac, gi = sn * ci / ac;   // g = sn * c/|c|
-    // P' = cs P - g Q ;  Q' = conj(g) P + cs Q
+    if (!(ac2 > tol2 * a * b)) return 0;
+    double cs, gr, gi;
+    jacobi_angle(a, b, cr, ci, ac2, cs, gr, gi);
     for (int c = lane; c < ltot_r; c += 32) {
         const cplx x = P[c], y = Q[c];
         cplx xn, yn;
-        xn.x = cs * x.x - (gr * y.x - gi * y.y);
-        xn.y = cs * x.y - (gr * y.y + gi * y.x);
-        yn.x = (gr * x.x + gi * x.y) + cs * y.x;
-        yn.y = (gr * x.y - gi * x.x) + cs * y.y;
+        xn.x = fma(cs, x.x, fma(gi, y.y, -gr * y.x));
+        xn.y = fma(cs, x.y, -fma(gr, y.y, gi * y.x));
+        yn.x = fma(cs, y.x, fma(gr, x.x, gi * x.y));
+        yn.y = fma(cs, y.y, fma(gr, x.y, -gi * x.x));
         P[c] = xn;
         Q[c] = yn;
     }
@@ -260,9 +321,11 @@ template <int B>
 __global__ void __launch_bounds__(32 * B)
 jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r,
                     int nblk, int round, int full, int inner_sweeps, const double* __restrict__ frob2,
-                    int* __restrict__ rot, const int* __restrict__ done, double tol2, double eabs2) {
+                    int* __restrict__ rot, const int* __restrict__ done, double tol2, double eabs2,
+                    unsigned long long* __restrict__ phase_clk) {
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rows = reinterpret_cast<cplx*>(smraw);            // [2B][ltot_r]
+    const long long t_start = phase_clk ? clock64() : 0;
     __shared__ __align__(8) uint64_t bar;
 
     const int mat = mat0 + blockIdx.y;
@@ -286,6 +349,7 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
         }
     }
     if (!mbar_wait(&bar, 0)) __trap();
+    const long long t_loaded = phase_clk ? clock64() : 0;
 
     const double F2 = frob2[mat];
     int nrot_total = 0;
@@ -311,7 +375,15 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
         if (!__syncthreads_or(nrot > 0)) break;
     }
     const int any = __syncthreads_or(nrot_total > 0);
-    if (!any) return;
+    const long long t_rotated = phase_clk ? clock64() : 0;
+    if (!any) {
+        if (phase_clk && tid == 0) {
+            atomicAdd(&phase_clk[0], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
+            atomicAdd(&phase_clk[3], 1ull);
+        }
+        return;
+    }
     if (lane == 0 && nrot_total > 0) atomicAdd(&rot[mat], nrot_total);
     fence_async_smem();
     __syncthreads();
@@ -322,6 +394,12 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
         }
         bulk_commit();
         bulk_wait_all();
+        if (phase_clk) {
+            atomicAdd(&phase_clk[0], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
+            atomicAdd(&phase_clk[2], (unsigned long long)(clock64() - t_rotated));
+            atomicAdd(&phase_clk[3], 1ull);
+        }
     }
 }
 
@@ -329,6 +407,7 @@ __global__ void sweep_begin_kernel(int* rot, int* done, int* n_active, unsigned 
                                    unsigned long long* sweep_total, int batch, int reset_done) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { *n_active = 0; *rot_total = 0ull; *sweep_total = 0ull; }
+    if (i < 4) rot_total[16 + i] = 0ull;   // phase_clk lives 128 bytes after rot_total
     if (i < batch) {
         rot[i] = 0;
         if (reset_done) done[i] = 0;
@@ -472,7 +551,8 @@ int launch_round(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int co
     const int nblk = pl.n_pad / pl.bsz;
     dim3 grid(nblk / 2, count);
     jacobi_round_kernel<B><<<grid, 32 * B, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
-                                                      nblk, round, full, inner, s.frob2, s.rot, s.done, tol2, eabs2);
+                                                      nblk, round, full, inner, s.frob2, s.rot, s.done, tol2, eabs2,
+                                                      g_prof.enabled > 1 ? s.phase_clk : nullptr);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -598,6 +678,13 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
         g_prof.rotations = h[0];
         g_prof.problem_sweeps = h[1];
+        if (g_prof.enabled > 1) {
+            unsigned long long c[4];
+            MPSB_CHECK_CUDA(cudaMemcpy(c, s.phase_clk, sizeof(c), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[mpsb] jacobi CTA phases (mean SM clocks): load %.0f rotate %.0f store %.0f over %llu CTAs\n",
+                    (double)c[0] / (double)(c[3] ? c[3] : 1), (double)c[1] / (double)(c[3] ? c[3] : 1),
+                    (double)c[2] / (double)(c[3] ? c[3] : 1), c[3]);
+        }
     }
     return 0;
 }
