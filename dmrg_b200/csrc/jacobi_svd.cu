@@ -403,11 +403,248 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
     }
 }
 
+// ---- Gram-assisted round (block of 16 rows per CTA, FP64 tensor cores) -------------------------------
+// Same outer schedule as jacobi_round_kernel<8>, but the long-row arithmetic runs on DMMA:
+//   A. G = P P^H (16x16 Hermitian) over the first ldot columns            -- DMMA, K split over the 8 warps
+//   B. one full round-robin tournament (15 steps x 8 disjoint pairs) of two-sided Jacobi rotations on G,
+//      accumulated into the unitary Q (16x16); angles from the maintained G, relative test as above
+//   C. P <- Q^H P over all ltot_r columns                                   -- DMMA, columns split over the warps
+// No inner products by warp shuffles, no per-pair pass over the long rows.  Rotations computed from the
+// maintained Gram block keep relative accuracy (errors scale with sqrt(g_pp g_qq), as in two-sided Jacobi on a
+// scaled-diagonally-dominant matrix), and the convergence test of every later visit uses a freshly computed G.
+constexpr int GR = 16;                 // rows per CTA
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_PAD = 2;            // row pitch = ltot_r + 2 elements: conflict-free B fragments in phase C
+
+struct GramSmem {
+    cplx G[GR][GR];                    // Gram block; also the K-half-0 partial during phase A
+    cplx Q[GR][GR];                    // accumulated rotations; also the K-half-1 partial during phase A
+    double cs[8], gr[8], gi[8];
+    int partner[GR], role[GR], rix[GR];
+    int nrot;
+    uint64_t bar;
+};
+
+// Division-free rotation parameters (see jacobi_angle): f = +-1/sqrt(denom^2 + |c|^2), cs = denom * |f|.
+__device__ __forceinline__ void jacobi_angle_fast(double a, double b, double cr, double ci, double ac2, double& cs,
+                                                  double& gr, double& gi) {
+    const double z = 0.5 * (b - a);
+    const double denom = fabs(z) + sqrt(fma(z, z, ac2));
+    const double h = rsqrt(fma(denom, denom, ac2));
+    cs = denom * h;
+    const double f = z >= 0.0 ? h : -h;
+    gr = f * cr;
+    gi = f * ci;
+}
+
+__global__ void __launch_bounds__(GRAM_THREADS, 3)
+jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
+                   int round, int inner_sweeps, int* __restrict__ rot, const int* __restrict__ done, double tol2,
+                   unsigned long long* __restrict__ phase_clk) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GramSmem& sm = *reinterpret_cast<GramSmem*>(smraw);
+    cplx* rows = reinterpret_cast<cplx*>(smraw + ((sizeof(GramSmem) + 127) / 128) * 128);   // [GR][pitch]
+    const int pitch = ltot_r + GRAM_PAD;
+
+    const int mat = mat0 + blockIdx.y;
+    if (done[mat]) return;
+    const long long t_start = phase_clk ? clock64() : 0;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bI, bJ;
+    rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    cplx* X = Xall + (size_t)mat * strideX;
+    const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
+
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+        sm.nrot = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&sm.bar, rowbytes * GR);
+        for (int r = 0; r < 8; ++r) {
+            bulk_g2s(rows + (size_t)r * pitch, X + (size_t)(bI * 8 + r) * ld, rowbytes, &sm.bar);
+            bulk_g2s(rows + (size_t)(8 + r) * pitch, X + (size_t)(bJ * 8 + r) * ld, rowbytes, &sm.bar);
+        }
+    }
+    if (!mbar_wait(&sm.bar, 0)) __trap();
+    const long long t_loaded = phase_clk ? clock64() : 0;
+
+    // Round 0 of a sweep (and the single-CTA case) plays the complete 16-row tournament so that pairs inside a
+    // block are covered; later rounds only need the 8 x 8 cross pairs between the two blocks.
+    const int nsteps = (round == 0 || nblk == 2) ? GR - 1 : 8;
+    const int ei = tid >> 4, ej = tid & 15;          // element of G / Q owned by this thread
+    int total_rot = 0;
+    for (int sw = 0; sw < inner_sweeps; ++sw) {
+        // ---- A. Gram matrix: warp -> (tile, K half); partials land in sm.G (half 0) and sm.Q (half 1) ----
+        const long long tA = phase_clk ? clock64() : 0;
+        {
+            const int tile = w & 3, khalf = w >> 2;
+            const int ti = tile >> 1, tj = tile & 1;
+            double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+            const int ksteps = (ldot + 3) >> 2;
+            const cplx* ra = rows + (size_t)(8 * ti + g) * pitch + t;
+            const cplx* rb = rows + (size_t)(8 * tj + g) * pitch + t;
+#pragma unroll 4
+            for (int ks = khalf; ks < ksteps; ks += 2) {
+                cplx a = ra[4 * ks], b = rb[4 * ks];
+                if (4 * ks + t >= ldot) { a = make_double2(0.0, 0.0); b = make_double2(0.0, 0.0); }
+                dmma884(re0, re1, a.x, b.x);
+                dmma884(re0, re1, a.y, b.y);
+                dmma884(im0, im1, a.y, b.x);
+                dmma884(im0, im1, -a.x, b.y);
+            }
+            cplx* dst = khalf == 0 ? &sm.G[8 * ti + g][8 * tj + 2 * t] : &sm.Q[8 * ti + g][8 * tj + 2 * t];
+            dst[0] = make_double2(re0, im0);
+            dst[1] = make_double2(re1, im1);
+        }
+        __syncthreads();
+        {
+            cplx v = sm.G[ei][ej];
+            const cplx u = sm.Q[ei][ej];
+            v.x += u.x;
+            v.y = (ei == ej) ? 0.0 : v.y + u.y;
+            sm.G[ei][ej] = v;
+            sm.Q[ei][ej] = make_double2(ei == ej ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+        // ---- B. tournament on G ------------------------------------------------------------------------
+        const long long tB = phase_clk ? clock64() : 0;
+        int my_rot = 0;
+        for (int s = 0; s < nsteps; ++s) {
+            if (tid < 8) {
+                int p, q;
+                if (nsteps == GR - 1) rr_pair(GR, s, tid, p, q);
+                else { p = tid; q = 8 + ((tid + s) & 7); }
+                const double a = sm.G[p][p].x, b = sm.G[q][q].x;
+                const cplx c = sm.G[p][q];
+                const double ac2 = c.x * c.x + c.y * c.y;
+                double cs = 1.0, gr = 0.0, gi = 0.0;
+                if (ac2 > tol2 * a * b) {
+                    jacobi_angle_fast(a, b, c.x, c.y, ac2, cs, gr, gi);
+                    ++my_rot;
+                }
+                sm.cs[tid] = cs; sm.gr[tid] = gr; sm.gi[tid] = gi;
+                sm.partner[p] = q; sm.role[p] = 0; sm.rix[p] = tid;
+                sm.partner[q] = p; sm.role[q] = 1; sm.rix[q] = tid;
+            }
+            __syncthreads();
+            cplx gn, qn;
+            {
+                const int ip = sm.partner[ei], jp = sm.partner[ej];
+                const int ri = sm.rix[ei], rj = sm.rix[ej];
+                const double csi = sm.cs[ri], csj = sm.cs[rj];
+                // rows:    P' = cs P - g Q,  Q' = conj(g) P + cs Q   -> partner coefficient w_i = -g | conj(g)
+                // columns: Hermitian conjugate of the row transform     -> partner coefficient conj(w_j)
+                const double wri = sm.role[ei] == 0 ? -sm.gr[ri] : sm.gr[ri];
+                const double wii = -sm.gi[ri];
+                const double wrj = sm.role[ej] == 0 ? -sm.gr[rj] : sm.gr[rj];
+                const double wij = sm.gi[rj];
+                const cplx g00 = sm.G[ei][ej], g10 = sm.G[ip][ej], g01 = sm.G[ei][jp], g11 = sm.G[ip][jp];
+                cplx Tj, Tjp;
+                Tj.x = fma(csi, g00.x, fma(wri, g10.x, -wii * g10.y));
+                Tj.y = fma(csi, g00.y, fma(wri, g10.y, wii * g10.x));
+                Tjp.x = fma(csi, g01.x, fma(wri, g11.x, -wii * g11.y));
+                Tjp.y = fma(csi, g01.y, fma(wri, g11.y, wii * g11.x));
+                gn.x = fma(csj, Tj.x, fma(wrj, Tjp.x, -wij * Tjp.y));
+                gn.y = fma(csj, Tj.y, fma(wrj, Tjp.y, wij * Tjp.x));
+                if (ei == ej) gn.y = 0.0;
+                const cplx q0 = sm.Q[ei][ej], q1 = sm.Q[ei][jp];
+                qn.x = fma(csj, q0.x, fma(wrj, q1.x, -wij * q1.y));
+                qn.y = fma(csj, q0.y, fma(wrj, q1.y, wij * q1.x));
+            }
+            __syncthreads();
+            sm.G[ei][ej] = gn;
+            sm.Q[ei][ej] = qn;
+            __syncthreads();
+        }
+        if (tid < 8 && my_rot > 0) atomicAdd(&sm.nrot, my_rot);
+        __syncthreads();
+        const int nrot = sm.nrot;
+        __syncthreads();
+        if (tid == 0) sm.nrot = 0;
+        const long long tC = phase_clk ? clock64() : 0;
+        if (phase_clk && tid == 0) {
+            atomicAdd(&phase_clk[4], (unsigned long long)(tB - tA));
+            atomicAdd(&phase_clk[5], (unsigned long long)(tC - tB));
+        }
+        if (nrot == 0) break;
+        total_rot += nrot;
+        // ---- C. P <- Q^H P ------------------------------------------------------------------------------
+        {
+            cplx af[2][4];            // A[m][k] = conj(Q[k][m]); row tiles m0 = 0, 8; k steps k0 = 0, 4, 8, 12
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const cplx v = sm.Q[4 * ks + t][8 * mt + g];
+                    af[mt][ks] = make_double2(v.x, -v.y);
+                }
+            const int ntiles = ltot_r >> 3;
+            for (int nt = w; nt < ntiles; nt += 8) {
+                const int n0 = nt * 8;
+                cplx bf[4];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) bf[ks] = rows[(size_t)(4 * ks + t) * pitch + n0 + g];
+                double cre[2][2], cim[2][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) { cre[mt][0] = cre[mt][1] = cim[mt][0] = cim[mt][1] = 0.0; }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        dmma884(cre[mt][0], cre[mt][1], af[mt][ks].x, bf[ks].x);
+                        dmma884(cre[mt][0], cre[mt][1], -af[mt][ks].y, bf[ks].y);
+                        dmma884(cim[mt][0], cim[mt][1], af[mt][ks].x, bf[ks].y);
+                        dmma884(cim[mt][0], cim[mt][1], af[mt][ks].y, bf[ks].x);
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    cplx* dst = rows + (size_t)(8 * mt + g) * pitch + n0 + 2 * t;
+                    dst[0] = make_double2(cre[mt][0], cim[mt][0]);
+                    dst[1] = make_double2(cre[mt][1], cim[mt][1]);
+                }
+            }
+        }
+        __syncthreads();
+        if (phase_clk && tid == 0) atomicAdd(&phase_clk[6], (unsigned long long)(clock64() - tC));
+    }
+    const long long t_rotated = phase_clk ? clock64() : 0;
+    if (total_rot == 0) {
+        if (phase_clk && tid == 0) {
+            atomicAdd(&phase_clk[0], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
+            atomicAdd(&phase_clk[3], 1ull);
+        }
+        return;
+    }
+    if (tid == 0) atomicAdd(&rot[mat], total_rot);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int r = 0; r < 8; ++r) {
+            bulk_s2g(X + (size_t)(bI * 8 + r) * ld, rows + (size_t)r * pitch, rowbytes);
+            bulk_s2g(X + (size_t)(bJ * 8 + r) * ld, rows + (size_t)(8 + r) * pitch, rowbytes);
+        }
+        bulk_commit();
+        bulk_wait_all();
+        if (phase_clk) {
+            atomicAdd(&phase_clk[0], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
+            atomicAdd(&phase_clk[2], (unsigned long long)(clock64() - t_rotated));
+            atomicAdd(&phase_clk[3], 1ull);
+        }
+    }
+}
+
 __global__ void sweep_begin_kernel(int* rot, int* done, int* n_active, unsigned long long* rot_total,
                                    unsigned long long* sweep_total, int batch, int reset_done) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { *n_active = 0; *rot_total = 0ull; *sweep_total = 0ull; }
-    if (i < 4) rot_total[16 + i] = 0ull;   // phase_clk lives 128 bytes after rot_total
+    if (i < 8) rot_total[16 + i] = 0ull;   // phase_clk lives 128 bytes after rot_total
     if (i < batch) {
         rot[i] = 0;
         if (reset_done) done[i] = 0;
@@ -558,8 +795,35 @@ int launch_round(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int co
     return 0;
 }
 
+size_t gram_smem_bytes(int ltot_r) {
+    return ((sizeof(GramSmem) + 127) / 128) * 128 + (size_t)GR * (ltot_r + GRAM_PAD) * sizeof(cplx);
+}
+bool use_gram_kernel(const SvdPlan& pl) {
+    static const int enabled = env_int("MPSB_JACOBI_GRAM", 1);
+    return enabled && pl.bsz == 8 && gram_smem_bytes(round_up(pl.ltot, 32)) <= 220 * 1024;
+}
+int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int inner,
+                double tol2, cudaStream_t st) {
+    const int ltot_r = round_up(pl.ltot, 32);
+    const size_t smem = gram_smem_bytes(ltot_r);
+    static size_t configured = 0;
+    if (smem > configured) {
+        MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int nblk = pl.n_pad / 8;
+    dim3 grid(nblk / 2, count);
+    jacobi_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
+                                                        nblk, round, inner, s.rot, s.done, tol2,
+                                                        g_prof.enabled > 1 ? s.phase_clk : nullptr);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
                      int inner, double tol2, double eabs2, cudaStream_t st) {
+    if (use_gram_kernel(pl)) return launch_gram(pl, X, s, mat0, count, round, inner, tol2, st);
     switch (pl.bsz) {
         case 1: return launch_round<1>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
         case 2: return launch_round<2>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
@@ -679,11 +943,13 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         g_prof.rotations = h[0];
         g_prof.problem_sweeps = h[1];
         if (g_prof.enabled > 1) {
-            unsigned long long c[4];
+            unsigned long long c[8];
             MPSB_CHECK_CUDA(cudaMemcpy(c, s.phase_clk, sizeof(c), cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[mpsb] jacobi CTA phases (mean SM clocks): load %.0f rotate %.0f store %.0f over %llu CTAs\n",
-                    (double)c[0] / (double)(c[3] ? c[3] : 1), (double)c[1] / (double)(c[3] ? c[3] : 1),
-                    (double)c[2] / (double)(c[3] ? c[3] : 1), c[3]);
+            const double nc = (double)(c[3] ? c[3] : 1);
+            fprintf(stderr, "[mpsb] jacobi CTA phases (mean SM clocks): load %.0f rotate %.0f store %.0f over %llu CTAs"
+                            " | gram %.0f tournament %.0f update %.0f\n",
+                    (double)c[0] / nc, (double)c[1] / nc, (double)c[2] / nc, c[3], (double)c[4] / nc, (double)c[5] / nc,
+                    (double)c[6] / nc);
         }
     }
     return 0;
