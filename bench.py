@@ -85,6 +85,37 @@ def cpu_leg(per_worker):
                       f"wall {wall:.1f} s"}
 
 
+def idmrg_leg(with_cpu):
+    """Secondary metric of BASELINE.json: time per iDMRG sweep (= one next_LR growth step), TFIM g = J = 1
+    (DMRG/iDMRG.py:64-76) at trunc = 32 (config 1) and 128, device-resident environments; CPU = the oracle's
+    matrix-free restatement with ARPACK on one core (the reference's dense H_eff build takes 9-12 s at chi = 32)."""
+    import torch
+    from dmrg_b200 import iDMRG, _lib as L
+    from dmrg_b200.MPO import MPO
+    W = (-MPO('sx') - MPO('sz') ** 2).tomatrix()
+    out = {"model": "TFIM g=J=1, d=2, w=3, complex128", "unit": "ms per next_LR"}
+    for chi in (32, 128):
+        Ld, Rd, Wd = L.to_device(np.array([[[0, 0, 1]]])), L.to_device(np.array([[[1, 0, 0]]])), L.to_device(W)
+        times, nmv = [], []
+        for i in range(16):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            Ld, Rd, E, _ = iDMRG.next_LR_device(Ld, Rd, Wd, trunc=chi)
+            torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+            nmv.append(iDMRG.last_info["n_matvec"])
+        out[f"chi{chi}"] = {"ms": 1e3 * statistics.mean(times[-6:]), "matvecs": statistics.mean(nmv[-6:]),
+                            "energy_per_site_step16": E / 32}
+    if with_cpu:
+        from oracle import idmrg_oracle as io_
+        Lc, Rc = io_.boundary(3)
+        t = []
+        for i in range(12):
+            t0 = time.perf_counter()
+            Lc, Rc, Ec = io_.next_LR(Lc, Rc, W, trunc=32)
+            t.append(time.perf_counter() - t0)
+        out["cpu_chi32"] = {"ms": 1e3 * statistics.mean(t[-4:]), "kind": "port (matrix-free numpy + ARPACK, 1 process)"}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the box's host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -116,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-updates", type=int, default=24, help="oracle updates per CPU worker in the baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-idmrg", action="store_true", help="skip the secondary metric (time per iDMRG growth step)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -276,6 +308,8 @@ def main():
                     "sweeps_per_update": sweeps / (k_steps * n), "all_ranks_full": ranks_ok},
             "hbm_mandatory_gbs": hbm_bytes / (ms_total * 1e-3) / 1e9,
             "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    if world == 1 and not args.no_idmrg:
+        line["idmrg"] = idmrg_leg(not args.no_cpu)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(args.cpu_updates)
     print(json.dumps(line))

@@ -97,16 +97,31 @@ __global__ void dot_final_kernel(const cplx* __restrict__ part, int nchunk, int 
 
 __global__ void __launch_bounds__(256)
 axpy_multi_kernel(const cplx* __restrict__ V, long long ldv, int m, long long n, const cplx* __restrict__ c,
-                  cplx* __restrict__ w) {
+                  double sign, cplx* __restrict__ w) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     cplx acc = w[i];
     for (int j = 0; j < m; ++j) {
-        const cplx cj = c[j], v = V[(size_t)j * ldv + i];
+        cplx cj = c[j];
+        cj.x *= sign;
+        cj.y *= sign;
+        const cplx v = V[(size_t)j * ldv + i];
         acc.x = fma(cj.x, v.x, fma(-cj.y, v.y, acc.x));
         acc.y = fma(cj.x, v.y, fma(cj.y, v.x, acc.y));
     }
     w[i] = acc;
+}
+
+// w *= 1/sqrt(nrm2[0].x); a vanishing norm (Lanczos breakdown) zeroes the vector instead of producing NaNs
+__global__ void __launch_bounds__(256) normalise_kernel(long long n, const cplx* __restrict__ nrm2, cplx* __restrict__ w) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v2 = nrm2[0].x;
+    const double sc = v2 > 0.0 ? rsqrt(v2) : 0.0;
+    cplx v = w[i];
+    v.x *= sc;
+    v.y *= sc;
+    w[i] = v;
 }
 
 __global__ void __launch_bounds__(256) dscal_kernel(long long n, double alpha, cplx* __restrict__ w) {
@@ -159,9 +174,18 @@ int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w,
     return 0;
 }
 
-int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, cplx* w, cudaStream_t st) {
+int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
+                cudaStream_t st) {
     if (m == 0 || n == 0) return 0;
-    axpy_multi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, ldv, m, n, c, w);
+    axpy_multi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, ldv, m, n, c, sign, w);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st) {
+    if (n == 0) return 0;
+    normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, nrm2, w);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -208,10 +208,14 @@ int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void
 size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
     const size_t n = (size_t)chil * d * d * chir;
     const int nchunk = 64;
-    return heff_bytes(chil, chir, d, w) + al(n * sizeof(cplx)) * (size_t)(krylov + 2) +
-           al((size_t)(krylov + 2) * nchunk * sizeof(cplx)) + al((size_t)(krylov + 2) * sizeof(cplx)) * 3;
+    const size_t kk = (size_t)krylov + 2;
+    return heff_bytes(chil, chir, d, w) + al(n * sizeof(cplx)) * kk + al(kk * nchunk * sizeof(cplx)) +
+           al(kk * kk * sizeof(cplx)) * 2 + al(kk * sizeof(cplx)) * 2;
 }
 
+// One restart cycle runs without any host synchronisation: the Gram-Schmidt coefficients stay on the device
+// (the axpy kernel reads them there), normalisation uses the device-resident norm, and alpha / beta are read
+// back once per cycle.
 int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
                         int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
                         int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
@@ -224,6 +228,7 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     const int nchunk = 64;
     int m = krylov;
     if ((size_t)m > n) m = (int)n;
+    const size_t kk = (size_t)krylov + 2;
     unsigned char* p = static_cast<unsigned char*>(ws);
     Heff h;
     int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
@@ -231,61 +236,61 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     if (rc) return rc;
     p += heff_bytes(chil, chir, d, w);
     const size_t vstride = al(n * sizeof(cplx)) / sizeof(cplx);
-    cplx* V = reinterpret_cast<cplx*>(p);                 p += al(n * sizeof(cplx)) * (size_t)(krylov + 2);
-    cplx* part = reinterpret_cast<cplx*>(p);              p += al((size_t)(krylov + 2) * nchunk * sizeof(cplx));
-    cplx* c1 = reinterpret_cast<cplx*>(p);                p += al((size_t)(krylov + 2) * sizeof(cplx));
-    cplx* c2 = reinterpret_cast<cplx*>(p);                p += al((size_t)(krylov + 2) * sizeof(cplx));
+    cplx* V = reinterpret_cast<cplx*>(p);                 p += al(n * sizeof(cplx)) * kk;
+    cplx* part = reinterpret_cast<cplx*>(p);              p += al(kk * nchunk * sizeof(cplx));
+    cplx* C1 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-1 coefficients, row j
+    cplx* C2 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-2 coefficients
+    cplx* N2 = reinterpret_cast<cplx*>(p);                p += al(kk * sizeof(cplx));        // ||w_j||^2
     cplx* c3 = reinterpret_cast<cplx*>(p);
     cplx* th = static_cast<cplx*>(theta);
-    std::vector<cplx> hc((size_t)krylov + 2);
+    std::vector<cplx> h1(kk * kk), h2(kk * kk), hn(kk), hc(kk);
     std::vector<double> alpha, beta, T, Y;
     int n_mv = 0;
     double E = 0.0, resid = 0.0;
 
     // normalise the start vector into V[0]
-    rc = zdotc_multi(th, 0, 1, (long long)n, th, c1, part, nchunk, st);
+    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, st);
     if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx), cudaMemcpyDeviceToHost, st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-    MPSB_REQUIRE(hc[0].x > 0.0 && std::isfinite(hc[0].x), "lanczos_ground: start vector has norm^2 = %g", hc[0].x);
+    MPSB_REQUIRE(hn[0].x > 0.0 && std::isfinite(hn[0].x), "lanczos_ground: start vector has norm^2 = %g", hn[0].x);
     MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-    rc = zdscal((long long)n, 1.0 / std::sqrt(hc[0].x), V, st);
+    rc = znormalise((long long)n, N2, V, st);
     if (rc) return rc;
 
     for (int restart = 0; restart < max_restarts; ++restart) {
-        alpha.clear();
-        beta.clear();
-        int mm = 0;
         for (int j = 0; j < m; ++j) {
             cplx* wv = V + (size_t)(j + 1) * vstride;
             rc = heff_apply(h, V + (size_t)j * vstride, wv, st);
             if (rc) return rc;
             ++n_mv;
-            // two passes of classical Gram-Schmidt against V[0..j]
+            // two passes of classical Gram-Schmidt against V[0..j]; coefficients never leave the device
             for (int pass = 0; pass < 2; ++pass) {
-                cplx* c = pass == 0 ? c1 : c2;
+                cplx* c = (pass == 0 ? C1 : C2) + (size_t)j * kk;
                 rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, st);
                 if (rc) return rc;
-                MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c, sizeof(cplx) * (j + 1), cudaMemcpyDeviceToHost, st));
-                MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-                if (pass == 0) alpha.push_back(hc[j].x);
-                else alpha.back() += hc[j].x;
-                for (int q = 0; q <= j; ++q) { hc[q].x = -hc[q].x; hc[q].y = -hc[q].y; }
-                MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx) * (j + 1), cudaMemcpyHostToDevice, st));
-                rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c3, wv, st);
+                rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c, -1.0, wv, st);
                 if (rc) return rc;
-                MPSB_CHECK_CUDA(cudaStreamSynchronize(st));   // hc is reused by the next pass
             }
-            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, c1, part, nchunk, st);
+            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, N2 + j, part, nchunk, st);
             if (rc) return rc;
-            MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
-            MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-            const double bj = std::sqrt(hc[0].x > 0.0 ? hc[0].x : 0.0);
-            beta.push_back(bj);
-            mm = j + 1;
-            if (!(bj > 1e-14 * (std::fabs(alpha[0]) + 1e-300))) break;   // invariant subspace reached
-            rc = zdscal((long long)n, 1.0 / bj, wv, st);
+            rc = znormalise((long long)n, N2 + j, wv, st);
             if (rc) return rc;
+        }
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(h1.data(), C1, sizeof(cplx) * kk * m, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(h2.data(), C2, sizeof(cplx) * kk * m, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx) * m, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+        alpha.assign(m, 0.0);
+        beta.assign(m, 0.0);
+        int mm = m;
+        for (int j = 0; j < m; ++j) {
+            alpha[j] = h1[(size_t)j * kk + j].x + h2[(size_t)j * kk + j].x;
+            beta[j] = std::sqrt(hn[j].x > 0.0 ? hn[j].x : 0.0);
+            if (!(beta[j] > 1e-14 * (std::fabs(alpha[0]) + 1e-300)) || !std::isfinite(beta[j])) {   // invariant subspace
+                mm = j + 1;
+                break;
+            }
         }
         // Ritz pair of the mm x mm tridiagonal matrix
         T.assign((size_t)mm * mm, 0.0);
@@ -299,41 +304,35 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
             if (T[(size_t)i * mm + i] < T[(size_t)best * mm + best]) best = i;
         E = T[(size_t)best * mm + best];
         resid = std::fabs(beta[mm - 1] * Y[(size_t)(mm - 1) * mm + best]);
-        // theta = sum_j y_j V[j]
+        // theta = sum_j y_j V[j], renormalised (guards against drift); restart from it
         for (int i = 0; i < mm; ++i) hc[i] = make_double2(Y[(size_t)i * mm + best], 0.0);
         MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx) * mm, cudaMemcpyHostToDevice, st));
         MPSB_CHECK_CUDA(cudaMemsetAsync(th, 0, n * sizeof(cplx), st));
-        rc = zaxpy_multi(V, (long long)vstride, mm, (long long)n, c3, th, st);
+        rc = zaxpy_multi(V, (long long)vstride, mm, (long long)n, c3, 1.0, th, st);
         if (rc) return rc;
-        // renormalise (guards against drift) and restart from it
-        rc = zdotc_multi(th, 0, 1, (long long)n, th, c1, part, nchunk, st);
+        rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, st);
         if (rc) return rc;
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-        rc = zdscal((long long)n, 1.0 / std::sqrt(hc[0].x), th, st);
+        rc = znormalise((long long)n, N2, th, st);
         if (rc) return rc;
         if (resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0) || mm < m) break;
         MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
     }
-    // true residual ||H theta - E theta|| with one more product
+    // Rayleigh quotient and true residual ||H theta - E theta|| of the returned vector, one more product
     cplx* hv = V + (size_t)1 * vstride;
     rc = heff_apply(h, th, hv, st);
     if (rc) return rc;
     ++n_mv;
-    rc = zdotc_multi(th, 0, 1, (long long)n, hv, c1, part, nchunk, st);
+    rc = zdotc_multi(th, 0, 1, (long long)n, hv, C1, part, nchunk, st);
     if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    rc = zaxpy_multi(th, 0, 1, (long long)n, C1, -1.0, hv, st);
+    if (rc) return rc;
+    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, N2, part, nchunk, st);
+    if (rc) return rc;
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), C1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx), cudaMemcpyDeviceToHost, st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-    E = hc[0].x;                                   // Rayleigh quotient of the returned vector
-    hc[0] = make_double2(-E, 0.0);
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx), cudaMemcpyHostToDevice, st));
-    rc = zaxpy_multi(th, 0, 1, (long long)n, c3, hv, st);
-    if (rc) return rc;
-    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, c1, part, nchunk, st);
-    if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), c1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
-    MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-    resid = std::sqrt(hc[0].x > 0.0 ? hc[0].x : 0.0);
+    E = hc[0].x;
+    resid = std::sqrt(hn[0].x > 0.0 ? hn[0].x : 0.0);
     if (energy_host) *energy_host = E;
     if (resid_host) *resid_host = resid;
     if (n_matvec_host) *n_matvec_host = n_mv;

@@ -103,8 +103,11 @@ int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_
 // y[j] = sum_i conj(V[j][i]) w[i]  for j < m (deterministic two-pass reduction); part: m * nchunk scratch
 int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
                 cudaStream_t st);
-// w[i] += sum_j c[j] V[j][i]   (c on device, m entries; sign folded into c by the caller)
-int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, cplx* w, cudaStream_t st);
+// w[i] += sign * sum_j c[j] V[j][i]   (c on device, m entries)
+int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
+                cudaStream_t st);
+// w *= 1/sqrt(nrm2[0].x) with nrm2 on the device (zero vector if the norm vanishes)
+int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st);
 // w[i] = alpha * w[i]  (alpha real, on host)
 int zdscal(long long n, double alpha, cplx* w, cudaStream_t st);
 
