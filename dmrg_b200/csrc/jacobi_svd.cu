@@ -403,6 +403,241 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
     }
 }
 
+// ---- cross round, register-resident (rounds >= 1 of a sweep, rows of <= 256 columns) ------------------
+// The 8 x 8 cross pairs between two blocks of 8 rows.  Warp w owns row p = w of block I in REGISTERS for the whole
+// task (8 complex per lane, loaded straight from global, stored straight back); the rows of block J come through
+// shared memory by TMA bulk copy and circulate: in step s warp w meets row q = (w + s) mod 8.
+// Work per pair and column is cut to the minimum:
+//   * row norms are computed once per task and then updated analytically (a' = a - t|c|, b' = b + t|c|), so only
+//     the cross inner product c (4 FMA) is formed per pair;
+//   * rotations are applied in scaled ("fast Givens") form: with rows X = d * x the update is
+//         x_p' = x_p - tau_p x_q,   x_q' = x_q + sig_q x_p,   d' = cs * d        (8 FMA per column, not 12),
+//     tau_p = tau d_q/d_p, sig_q = conj(tau) d_p/d_q, tau = t c/|c|; the scales are folded back into the rows at
+//     the end of the task (at most 8 rotations per row, so d >= cs_min^8 stays far from underflow).
+// MUFU seeds (about 20 bits) and Newton refinements: each refinement is 2-3 dependent FP64 operations instead
+// of the ~20-instruction IEEE division / square-root sequences.
+__device__ __forceinline__ double rcp_approx(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double rsqrt_approx(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double newton_rcp(double x, double r) { return fma(r, fma(-x, r, 1.0), r); }
+__device__ __forceinline__ double newton_rsqrt(double x, double y) {
+    const double h = 0.5 * x * y;
+    return fma(y, fma(-h, y, 0.5), y);
+}
+
+constexpr int CROSS_THREADS = 128;     // 4 warps, each owning TWO rows of block I in registers
+#ifndef MPSB_CROSS_MINBLOCKS
+#define MPSB_CROSS_MINBLOCKS 3
+#endif
+
+// State of one register-resident row: data x = X / d, true squared norm a, scale d and d^2.
+struct RegRow {
+    cplx x[8];
+    double a, d, e;
+    bool dirty;
+};
+
+// One Jacobi pair between a register row and the streamed row y (scale dq, eq = dq^2, true norm^2 bq).
+// Returns 1 if a rotation was applied.
+__device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, double& eq, double& bq, int ldot,
+                                          double tol2, int lane) {
+    double cr0 = 0.0, ci0 = 0.0, cr1 = 0.0, ci1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        if (lane + 32 * j < ldot) {
+            cr0 = fma(r.x[j].x, y[j].x, fma(r.x[j].y, y[j].y, cr0));
+            ci0 = fma(r.x[j].y, y[j].x, fma(-r.x[j].x, y[j].y, ci0));
+        }
+        if (lane + 32 * (j + 1) < ldot) {
+            cr1 = fma(r.x[j + 1].x, y[j + 1].x, fma(r.x[j + 1].y, y[j + 1].y, cr1));
+            ci1 = fma(r.x[j + 1].y, y[j + 1].x, fma(-r.x[j + 1].x, y[j + 1].y, ci1));
+        }
+    }
+    const double crs = warp_sum(cr0 + cr1), cis = warp_sum(ci0 + ci1);      // scaled inner product x_p . x_q^H
+    const double ac2 = r.e * eq * fma(crs, crs, cis * cis);                  // |c|^2 of the true rows
+    if (!(ac2 > tol2 * r.a * bq)) return 0;
+    // t/|c| = sgn(z) / (|z| + sqrt(z^2 + |c|^2)) from MUFU seeds + one Newton step each; the tangent may be
+    // 1e-12 off without harm because ...
+    const double z = 0.5 * (bq - r.a);
+    const double v1 = fma(z, z, ac2);
+    const double denom = fabs(z) + v1 * newton_rsqrt(v1, rsqrt_approx(v1));
+    const double inv = newton_rcp(denom, rcp_approx(denom));
+    const double k = z >= 0.0 ? inv : -inv;
+    // tau_p = tau d_q/d_p = k d_q^2 c~ ;  sig_q = conj(tau) d_p/d_q = k d_p^2 conj(c~)   (no divisions)
+    const double kq = k * eq, kp = k * r.e;
+    const double tpr = kq * crs, tpi = kq * cis;
+    const double sqr = kp * crs, sqi = -kp * cis;
+    // ... the scale cs is computed from the tangent actually applied, to full precision, so the combined
+    // transformation cs * [[1, -tau], [conj(tau), 1]] stays unitary to rounding
+    const double wv = fma(inv * inv, ac2, 1.0);
+    const double cs = newton_rsqrt(wv, newton_rsqrt(wv, rsqrt_approx(wv)));
+    const double cs2 = cs * cs;
+    const double delta = k * ac2;                                            // t |c|
+    r.d *= cs;
+    r.e *= cs2;
+    r.a -= delta;
+    r.dirty = true;
+    dq *= cs;
+    eq *= cs2;
+    bq += delta;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const cplx xo = r.x[j], yo = y[j];
+        r.x[j].x = fma(-tpr, yo.x, fma(tpi, yo.y, xo.x));
+        r.x[j].y = fma(-tpr, yo.y, fma(-tpi, yo.x, xo.y));
+        y[j].x = fma(sqr, xo.x, fma(-sqi, xo.y, yo.x));
+        y[j].y = fma(sqr, xo.y, fma(sqi, xo.x, yo.y));
+    }
+    return 1;
+}
+
+__global__ void __launch_bounds__(CROSS_THREADS, MPSB_CROSS_MINBLOCKS)
+jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
+                    int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
+                    unsigned long long* __restrict__ phase_clk) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [8][ltot_r]
+    __shared__ double nq[8], dqs[8], eqs[8];                  // true norm^2, scale d and d^2 of the rows of block J
+    __shared__ __align__(8) uint64_t bar;
+
+    const int mat = mat0 + blockIdx.y;
+    if (done[mat]) return;
+    const long long t_start = phase_clk ? clock64() : 0;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int bI, bJ;
+    rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    cplx* X = Xall + (size_t)mat * strideX;
+    const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, rowbytes * 8);
+        for (int r = 0; r < 8; ++r) bulk_g2s(rowsJ + (size_t)r * ltot_r, X + (size_t)(bJ * 8 + r) * ld, rowbytes, &bar);
+    }
+    // rows 2w, 2w+1 of block I: global -> registers (512 contiguous bytes per warp load)
+    cplx* gp0 = X + (size_t)(bI * 8 + 2 * w) * ld;
+    cplx* gp1 = gp0 + ld;
+    RegRow r0, r1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        r0.x[j] = c < ltot_r ? gp0[c] : make_double2(0.0, 0.0);
+        r1.x[j] = c < ltot_r ? gp1[c] : make_double2(0.0, 0.0);
+    }
+    {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane + 32 * j < ldot) {
+                a0 = fma(r0.x[j].x, r0.x[j].x, fma(r0.x[j].y, r0.x[j].y, a0));
+                a1 = fma(r1.x[j].x, r1.x[j].x, fma(r1.x[j].y, r1.x[j].y, a1));
+            }
+        r0.a = warp_sum(a0); r1.a = warp_sum(a1);
+        r0.d = r1.d = r0.e = r1.e = 1.0;
+        r0.dirty = r1.dirty = false;
+    }
+    if (!mbar_wait(&bar, 0)) __trap();
+    for (int rr = w; rr < 8; rr += 4) {   // norms of the rows of block J
+        const cplx* r = rowsJ + (size_t)rr * ltot_r;
+        double b = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < ldot) { const cplx y = r[c]; b = fma(y.x, y.x, fma(y.y, y.y, b)); }
+        }
+        b = warp_sum(b);
+        if (lane == 0) { nq[rr] = b; dqs[rr] = 1.0; eqs[rr] = 1.0; }
+    }
+    __syncthreads();
+    const long long t_loaded = phase_clk ? clock64() : 0;
+
+    int nrot = 0;
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) {
+        const int q = (2 * w + s) & 7;                    // the 4 warps meet 4 distinct rows of block J in every step
+        cplx* rq = rowsJ + (size_t)q * ltot_r;
+        cplx y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            y[j] = c < ltot_r ? rq[c] : make_double2(0.0, 0.0);
+        }
+        double dq = dqs[q], eq = eqs[q], bq = nq[q];
+        const int n0 = cross_pair(r0, y, dq, eq, bq, ldot, tol2, lane);
+        const int n1 = cross_pair(r1, y, dq, eq, bq, ldot, tol2, lane);
+        nrot += n0 + n1;
+        // Even rows of block J are visited in even steps, odd rows in odd steps, so steps 6 and 7 are the last
+        // visits: fold the accumulated scale back into the row there.
+        bool store = (n0 + n1) > 0;
+        if (s >= 6 && dq != 1.0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { y[j].x *= dq; y[j].y *= dq; }
+            dq = 1.0;
+            eq = 1.0;
+            store = true;
+        }
+        if (store) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (c < ltot_r) rq[c] = y[j];
+            }
+            if (lane == 0) { dqs[q] = dq; eqs[q] = eq; nq[q] = bq; }
+        }
+        __syncthreads();
+    }
+    const int any = __syncthreads_or(nrot > 0);
+    const long long t_rotated = phase_clk ? clock64() : 0;
+    if (!any) {
+        if (phase_clk && tid == 0) {
+            atomicAdd(&phase_clk[0], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
+            atomicAdd(&phase_clk[3], 1ull);
+        }
+        return;
+    }
+    if (lane == 0 && nrot > 0) atomicAdd(&rot[mat], nrot);
+    // fold the scales back: register rows on their way to global memory, J rows in shared memory
+    if (r0.dirty) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < ltot_r) gp0[c] = make_double2(r0.x[j].x * r0.d, r0.x[j].y * r0.d);
+        }
+    }
+    if (r1.dirty) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < ltot_r) gp1[c] = make_double2(r1.x[j].x * r1.d, r1.x[j].y * r1.d);
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int r = 0; r < 8; ++r) bulk_s2g(X + (size_t)(bJ * 8 + r) * ld, rowsJ + (size_t)r * ltot_r, rowbytes);
+        bulk_commit();
+        bulk_wait_all();
+        if (phase_clk) {
+            atomicAdd(&phase_clk[0], (unsigned long long)(t_loaded - t_start));
+            atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
+            atomicAdd(&phase_clk[2], (unsigned long long)(clock64() - t_rotated));
+            atomicAdd(&phase_clk[3], 1ull);
+        }
+    }
+}
+
 // ---- Gram-assisted round (block of 16 rows per CTA, FP64 tensor cores) -------------------------------
 // Same outer schedule as jacobi_round_kernel<8>, but the long-row arithmetic runs on DMMA:
 //   A. G = P P^H (16x16 Hermitian) over the first ldot columns            -- DMMA, K split over the 8 warps
@@ -823,6 +1058,25 @@ int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int cou
 
 int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
                      int inner, double tol2, double eabs2, cudaStream_t st) {
+    static const int cross_enabled = env_int("MPSB_JACOBI_CROSS", 1);
+    const int ltot_r = round_up(pl.ltot, 32);
+    if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
+        const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
+        static size_t configured = 0;
+        if (smem > configured) {
+            MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem));
+            configured = smem;
+        }
+        const int nblk = pl.n_pad / 8;
+        dim3 grid(nblk / 2, count);
+        jacobi_cross_kernel<<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot,
+                                                              ltot_r, nblk, round, s.rot, s.done, tol2,
+                                                              g_prof.enabled > 1 ? s.phase_clk : nullptr);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (use_gram_kernel(pl)) return launch_gram(pl, X, s, mat0, count, round, inner, tol2, st);
     switch (pl.bsz) {
         case 1: return launch_round<1>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
