@@ -271,7 +271,12 @@ def main():
     nrow, ncol = CHI * D, D * CHI
     npairs = nrow * (nrow - 1) // 2
     k_steps = args.steps
-    jac_flop = sweeps * npairs * 16.0 * ncol + rot * 24.0 * ncol          # algorithmic flops of the Jacobi phase
+    # Algorithmic flops of the Jacobi phase.  Lean model = what one-sided Jacobi must do per visited
+    # pair with cached row norms and scaled rotations: the cross inner product (4 FMA = 8 flops per column) and,
+    # if the pair is rotated, the 2x2 update of two complex rows in scaled form (8 FMA = 16 flops per column).
+    # The textbook count (three inner products, unscaled rotation: 16 and 24 flops per column) is given beside it.
+    jac_flop = sweeps * npairs * 8.0 * ncol + rot * 16.0 * ncol
+    jac_flop_textbook = sweeps * npairs * 16.0 * ncol + rot * 24.0 * ncol
     jac_s = phases[3] * 1e-3
     gemm_flop = k_steps * n * 8.0 * (nrow * CHI * ncol + nrow * ncol * CHI)
     gemm_s = (phases[0] + phases[5]) * 1e-3
@@ -280,9 +285,19 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    roofline = {"kernel": "jacobi_round_kernel (all sweeps of one step)", "bound": "fp64", "achieved": jac_flop / jac_s / 1e12,
-                "peak": fp64_peak, "unit": "TFLOP/s", "frac": jac_flop / jac_s / 1e12 / fp64_peak, "traffic": None,
-                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+    traffic = None
+    try:   # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except (OSError, ValueError):
+        pass
+    roofline = {"kernel": "jacobi_cross_kernel + jacobi_gram_kernel (all Jacobi sweeps of one step)", "bound": "fp64",
+                "achieved": jac_flop / jac_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": jac_flop / jac_s / 1e12 / fp64_peak,
+                "traffic": traffic,
+                "flop_model": "lean: 8*L per visited pair + 16*L per rotation (L = 256 columns)",
+                "achieved_textbook": jac_flop_textbook / jac_s / 1e12,
+                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); B200 FP64 "
+                               "vector and tensor peaks are nominally equal, so one denominator serves both",
                 "share_of_step": float(phases[3] / phases.sum())}
     roof_gemm = {"kernel": "zgemm_kernel (theta formation + back-projection, DMMA m8n8k4)", "bound": "tensor",
                  "achieved": gemm_flop / gemm_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
