@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
 qr_precond_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, int ltot, int ld, int G,
                   int CW, double* __restrict__ frob2) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    cplx* v = reinterpret_cast<cplx*>(smraw);                      // [n]
-    cplx* wpart = v + align_up(n, 8);                               // [G][ld]
-    double* cn = reinterpret_cast<double*>(wpart + (size_t)G * ld); // [ldot]
+    const size_t nal = align_up(n, 8);
+    cplx* vbuf = reinterpret_cast<cplx*>(smraw);                    // [2][nal]   reflector of this / the pending step
+    cplx* wbuf = vbuf + 2 * nal;                                    // [2][G][ld] partial w = v^H X per row group
+    cplx* wpart = wbuf;                                             // scratch for the column norms below
+    double* cn = reinterpret_cast<double*>(wbuf + (size_t)2 * G * ld);   // [ldot]
     int* order = reinterpret_cast<int*>(cn + align_up(ldot, 8));    // [ldot]
     unsigned char* colDone = reinterpret_cast<unsigned char*>(order + align_up(ldot, 8));  // [ld]
     __shared__ double red[33];
@@ -138,21 +140,52 @@ qr_precond_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
     }
     __syncthreads();
 
+    // Householder steps with the rank-1 update of step k-1 fused into the pass that forms w_k = v_k^H X:
+    // every trailing element is read and written once per step instead of read twice and written once.
+    // Pending reflector: (vbuf[pv], tau_prev, wbuf[pv]) acting on rows >= kprev.
     const int nsteps = n < ldot ? n : ldot;
+    bool have_prev = false;
+    int kprev = 0, pv = 0;
+    double tau_prev = 0.0;
     for (int k = 0; k < nsteps; ++k) {
         const int pc = order[k];
-        for (int i = k + tid; i < n; i += NT) v[i] = X[(size_t)i * ld + pc];
+        const int cu = pv ^ 1;                       // buffers written in this step
+        cplx* vcur = vbuf + (size_t)cu * nal;
+        const cplx* vprev = vbuf + (size_t)pv * nal;
+        const cplx* wprev = wbuf + (size_t)pv * G * ld;
+        cplx* wcur = wbuf + (size_t)cu * G * ld;
+        // A. pivot column with the pending update applied
+        {
+            cplx wp = make_double2(0.0, 0.0);
+            if (have_prev) {
+                for (int g = 0; g < G; ++g) { wp.x += wprev[(size_t)g * ld + pc].x; wp.y += wprev[(size_t)g * ld + pc].y; }
+                wp.x *= tau_prev;
+                wp.y *= tau_prev;
+            }
+            const int lo = have_prev ? kprev : k;
+            for (int i = lo + tid; i < n; i += NT) {
+                cplx x = X[(size_t)i * ld + pc];
+                if (have_prev) {
+                    const cplx vi = vprev[i];
+                    x.x -= vi.x * wp.x - vi.y * wp.y;
+                    x.y -= vi.x * wp.y + vi.y * wp.x;
+                }
+                if (i < k) X[(size_t)i * ld + pc] = x;      // finished entries of R above the diagonal
+                else vcur[i] = x;
+            }
+        }
         __syncthreads();
         double loc = 0.0;
         for (int i = k + 1 + tid; i < n; i += NT) {
-            const cplx x = v[i];
+            const cplx x = vcur[i];
             loc = fma(x.x, x.x, fma(x.y, x.y, loc));
         }
-        const cplx alpha = v[k];
-        const double sigma = block_sum(loc, red);          // contains the barriers that order v[k] reads
+        const cplx alpha = vcur[k];
+        const double sigma = block_sum(loc, red);          // contains the barriers that order vcur[k] reads
         const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
         const double normx2 = a2 + sigma;
-        if (!(normx2 > 0.0)) {                              // zero column: nothing to annihilate
+        if (!(normx2 > 0.0)) {                              // zero column: no reflector, the pending one stays pending
+            for (int i = k + tid; i < n; i += NT) X[(size_t)i * ld + pc] = make_double2(0.0, 0.0);
             if (tid == 0) colDone[pc] = 1;
             __syncthreads();
             continue;
@@ -164,50 +197,81 @@ qr_precond_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
         const cplx vk = make_double2(phase.x * (absa + normx), phase.y * (absa + normx));
         const double vhv = (absa + normx) * (absa + normx) + sigma;
         const double tau = 2.0 / vhv;
-        if (tid == 0) v[k] = vk;
+        if (tid == 0) vcur[k] = vk;
         __syncthreads();
-        // pass 1: partial w_j = sum_i conj(v_i) X[i][j]
+        // C. fused pass: apply the pending reflector, accumulate w_k = sum_{i >= k} conj(v_k[i]) X[i][j]
+        const int lo = have_prev ? kprev : k;
         for (int s = 0; s < nstrips; ++s) {
             const int j = s * CW + cj;
             if (active && j < ltot && j != pc && !(j < ldot && colDone[j])) {
-                double wr = 0.0, wi = 0.0;
-#pragma unroll 4
-                for (int i = k + cg; i < n; i += G) {
-                    const cplx x = X[(size_t)i * ld + j];
-                    const cplx vi = v[i];
-                    wr = fma(vi.x, x.x, fma(vi.y, x.y, wr));
-                    wi = fma(vi.x, x.y, fma(-vi.y, x.x, wi));
+                double pr = 0.0, pi = 0.0;
+                if (have_prev) {
+                    for (int g = 0; g < G; ++g) { pr += wprev[(size_t)g * ld + j].x; pi += wprev[(size_t)g * ld + j].y; }
+                    pr *= tau_prev;
+                    pi *= tau_prev;
                 }
-                wpart[(size_t)cg * ld + j] = make_double2(wr, wi);
+                double wr = 0.0, wi = 0.0;
+                int i = lo + cg;
+                for (; i < k; i += G) {                       // rows finished by the pending reflector only
+                    const cplx vi = vprev[i];
+                    cplx x = X[(size_t)i * ld + j];
+                    x.x -= vi.x * pr - vi.y * pi;
+                    x.y -= vi.x * pi + vi.y * pr;
+                    X[(size_t)i * ld + j] = x;
+                }
+                if (have_prev) {
+#pragma unroll 8
+                    for (; i < n; i += G) {
+                        const cplx vi = vprev[i], vc = vcur[i];
+                        cplx x = X[(size_t)i * ld + j];
+                        x.x -= vi.x * pr - vi.y * pi;
+                        x.y -= vi.x * pi + vi.y * pr;
+                        X[(size_t)i * ld + j] = x;
+                        wr = fma(vc.x, x.x, fma(vc.y, x.y, wr));
+                        wi = fma(vc.x, x.y, fma(-vc.y, x.x, wi));
+                    }
+                } else {
+#pragma unroll 8
+                    for (; i < n; i += G) {
+                        const cplx vc = vcur[i];
+                        const cplx x = X[(size_t)i * ld + j];
+                        wr = fma(vc.x, x.x, fma(vc.y, x.y, wr));
+                        wi = fma(vc.x, x.y, fma(-vc.y, x.x, wi));
+                    }
+                }
+                wcur[(size_t)cg * ld + j] = make_double2(wr, wi);
             }
         }
+        // D. the pivot column itself: beta on the diagonal, zeros below
+        for (int i = k + tid; i < n; i += NT)
+            X[(size_t)i * ld + pc] = (i == k) ? beta : make_double2(0.0, 0.0);
+        if (tid == 0) colDone[pc] = 1;
+        have_prev = true;
+        kprev = k;
+        tau_prev = tau;
+        pv = cu;
         __syncthreads();
-        // pass 2: X[i][j] -= tau v_i w_j
+    }
+    if (have_prev) {   // last pending update
+        const cplx* vprev = vbuf + (size_t)pv * nal;
+        const cplx* wprev = wbuf + (size_t)pv * G * ld;
         for (int s = 0; s < nstrips; ++s) {
             const int j = s * CW + cj;
-            if (active && j < ltot && j != pc && !(j < ldot && colDone[j])) {
-                double wr = 0.0, wi = 0.0;
-                for (int g = 0; g < G; ++g) {
-                    const cplx t = wpart[(size_t)g * ld + j];
-                    wr += t.x;
-                    wi += t.y;
-                }
-                wr *= tau;
-                wi *= tau;
-#pragma unroll 4
-                for (int i = k + cg; i < n; i += G) {
-                    const cplx vi = v[i];
+            if (active && j < ltot && !(j < ldot && colDone[j])) {
+                double pr = 0.0, pi = 0.0;
+                for (int g = 0; g < G; ++g) { pr += wprev[(size_t)g * ld + j].x; pi += wprev[(size_t)g * ld + j].y; }
+                pr *= tau_prev;
+                pi *= tau_prev;
+#pragma unroll 8
+                for (int i = kprev + cg; i < n; i += G) {
+                    const cplx vi = vprev[i];
                     cplx x = X[(size_t)i * ld + j];
-                    x.x -= vi.x * wr - vi.y * wi;
-                    x.y -= vi.x * wi + vi.y * wr;
+                    x.x -= vi.x * pr - vi.y * pi;
+                    x.y -= vi.x * pi + vi.y * pr;
                     X[(size_t)i * ld + j] = x;
                 }
             }
         }
-        for (int i = k + tid; i < n; i += NT)
-            X[(size_t)i * ld + pc] = (i == k) ? beta : make_double2(0.0, 0.0);
-        if (tid == 0) colDone[pc] = 1;
-        __syncthreads();
     }
 }
 
@@ -1140,10 +1204,10 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     {
         int CW = std::min(pl.ld, QR_THREADS);
         int G = QR_THREADS / CW;
-        const size_t wbudget = 96 * 1024;
+        const size_t wbudget = 48 * 1024;       // per w buffer (two are kept)
         G = std::max(1, std::min<int>(G, (int)(wbudget / ((size_t)pl.ld * sizeof(cplx)))));
         G = std::min(G, std::max(1, pl.n));
-        const size_t smem = align_up(pl.n, 8) * sizeof(cplx) + (size_t)G * pl.ld * sizeof(cplx) +
+        const size_t smem = 2 * align_up(pl.n, 8) * sizeof(cplx) + (size_t)2 * G * pl.ld * sizeof(cplx) +
                             align_up(pl.ldot, 8) * sizeof(double) + align_up(pl.ldot, 8) * sizeof(int) + pl.ld + 64;
         MPSB_REQUIRE(smem <= 220 * 1024, "svd: QR scratch %zu B exceeds shared memory", smem);
         static size_t configured = 0;
