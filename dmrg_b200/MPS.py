@@ -428,10 +428,10 @@ class MPS:
         """General multiple sites update (not implemented in the reference either, DMRG/MPS.py:459-461)."""
         raise NotImplementedError
 
-    def iTEBD_double(self, H, t, n):
+    def iTEBD_double(self, H, t, n, order=2):
         """Second-order Suzuki-Trotter evolution exp(-i H t) with n slices for a nearest-neighbour two-site
         Hamiltonian H (DMRG/MPS.py:463-490).  All even (odd) bonds of a half sweep are independent and go to the
-        GPU as one batch."""
+        GPU as one batch.  `order` (new, default = the reference's 2) selects the ST1 / ST2 / ST4 task line."""
         def even_update(k):
             U = _lib.to_device(la.expm(-1j * H * k * t).reshape([self.dim] * 4))
 
@@ -445,7 +445,7 @@ class MPS:
             def _odd_update():
                 self._update_bonds(U, list(range(1, self.L - 1, 2)))
             return _odd_update
-        ST.ST2((even_update, odd_update), n)
+        {1: ST.ST1, 2: ST.ST2, 4: ST.ST4}[order]((even_update, odd_update), n)
 
     def testCanon(self, err=1e-13):
         """Assert both orthonormality relations of the canonical form (DMRG/MPS.py:495-508)."""

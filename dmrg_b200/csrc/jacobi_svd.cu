@@ -1209,17 +1209,21 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         G = std::min(G, std::max(1, pl.n));
         const size_t smem = 2 * align_up(pl.n, 8) * sizeof(cplx) + (size_t)2 * G * pl.ld * sizeof(cplx) +
                             align_up(pl.ldot, 8) * sizeof(double) + align_up(pl.ldot, 8) * sizeof(int) + pl.ld + 64;
-        MPSB_REQUIRE(smem <= 220 * 1024, "svd: QR scratch %zu B exceeds shared memory", smem);
-        static size_t configured = 0;
-        if (smem > configured) {
-            MPSB_CHECK_CUDA(cudaFuncSetAttribute(qr_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem));
-            configured = smem;
+        static const int qr_enabled = env_int("MPSB_SVD_QR", 1);
+        // Very long rows (chi >= 1024 with carried columns) do not leave room for the reflector scratch; the
+        // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
+        if (qr_enabled && smem <= 220 * 1024) {
+            static size_t configured = 0;
+            if (smem > configured) {
+                MPSB_CHECK_CUDA(cudaFuncSetAttribute(qr_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)smem));
+                configured = smem;
+            }
+            qr_precond_kernel<<<pl.batch, QR_THREADS, smem, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, G, CW,
+                                                                 s.frob2);
+            MPSB_COUNT_LAUNCH();
+            MPSB_CHECK_CUDA(cudaGetLastError());
         }
-        qr_precond_kernel<<<pl.batch, QR_THREADS, smem, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, G, CW,
-                                                             s.frob2);
-        MPSB_COUNT_LAUNCH();
-        MPSB_CHECK_CUDA(cudaGetLastError());
     }
 
     prof_mark(3, st);

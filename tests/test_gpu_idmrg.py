@@ -115,3 +115,42 @@ def test_idmrg_heisenberg_real_mpo(lib, golden):
     np.testing.assert_allclose(e, g["heis_e_total"], rtol=1e-6)              # trunc cuts a multiplet: SURVEY App. B1
     ed = [-3, -6.464102, -9.974309, -13.499730, -17.032141, -20.568363]
     np.testing.assert_allclose(e[:6], ed, atol=6e-5)
+
+
+def test_idmrg_aklt_config2(lib):
+    """BASELINE config 2 (reduced chi): spin-1 AKLT chain through the new two-site MPO builder; the energy per
+    added bond is exactly -2/3 and the kept Schmidt spectrum has (numerical) rank 4 = 2 x 2 edge sectors."""
+    from dmrg_b200 import iDMRG, spin
+    from dmrg_b200.MPO import two_site_mpo
+    ss = sum(np.kron(a, a) for a in spin.S(1)[1:])
+    W = two_site_mpo((ss + ss @ ss / 3).real, 3)
+    w = W.shape[0]
+    L, R = np.zeros((1, 1, w)), np.zeros((1, 1, w))
+    L[0, 0, w - 1] = 1; R[0, 0, 0] = 1
+    Eprev = 0.0
+    for i in range(8):
+        L, R, E = iDMRG.next_LR(L, R, W, trunc=16)
+        bond = (E - Eprev) / 2
+        Eprev = E
+        if i >= 2:
+            assert abs(bond + 2 / 3) < 1e-10
+    S = iDMRG.last_info["S"]
+    p = S ** 2 / np.sum(S ** 2)
+    # pairs are degenerate up to the exponentially small finite-size splitting of the 16-site chain
+    assert np.sum(p[:4]) > 1 - 1e-12 and abs(p[0] - p[1]) < 1e-3 and abs(p[2] - p[3]) < 1e-3
+
+
+def test_idmrg_matches_oracle_at_chi24_with_entropy(lib):
+    """TFIM growth at trunc = 24 against the matrix-free oracle: energies to 1e-9, entanglement entropy of the kept
+    spectrum to 1e-8 (both runs truncate the same non-degenerate spectrum)."""
+    from dmrg_b200 import iDMRG
+    W = io_.tfim_mpo(g=0.8)
+    L, R = io_.boundary(3)
+    Lo, Ro = io_.boundary(3)
+    for i in range(10):
+        L, R, E = iDMRG.next_LR(L, R, W, trunc=24)
+        Lo, Ro, Eo, So, _ = io_.next_LR(Lo, Ro, W, trunc=24, return_state=True)
+        assert abs(E - Eo) < 1e-9 * abs(Eo)
+    Sg = iDMRG.last_info["S"]
+    assert abs(io_.entropy_from_S(Sg, 24) - io_.entropy_from_S(So, 24)) < 1e-8
+    np.testing.assert_allclose(Sg[:12], So[:12], rtol=1e-8)
