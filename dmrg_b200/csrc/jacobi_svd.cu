@@ -510,16 +510,18 @@ struct RegRow {
 
 // One Jacobi pair between a register row and the streamed row y (scale dq, eq = dq^2, true norm^2 bq).
 // Returns 1 if a rotation was applied.
+// FULL: all 256 columns take part in the inner product (no per-column predicates in the hot loop).
+template <bool FULL>
 __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, double& eq, double& bq, int ldot,
                                           double tol2, int lane) {
     double cr0 = 0.0, ci0 = 0.0, cr1 = 0.0, ci1 = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-        if (lane + 32 * j < ldot) {
+        if (FULL || lane + 32 * j < ldot) {
             cr0 = fma(r.x[j].x, y[j].x, fma(r.x[j].y, y[j].y, cr0));
             ci0 = fma(r.x[j].y, y[j].x, fma(-r.x[j].x, y[j].y, ci0));
         }
-        if (lane + 32 * (j + 1) < ldot) {
+        if (FULL || lane + 32 * (j + 1) < ldot) {
             cr1 = fma(r.x[j + 1].x, y[j + 1].x, fma(r.x[j + 1].y, y[j + 1].y, cr1));
             ci1 = fma(r.x[j + 1].y, y[j + 1].x, fma(-r.x[j + 1].x, y[j + 1].y, ci1));
         }
@@ -562,6 +564,7 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
     return 1;
 }
 
+template <bool FULL>
 __global__ void __launch_bounds__(CROSS_THREADS, MPSB_CROSS_MINBLOCKS)
 jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                     int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
@@ -596,14 +599,14 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = lane + 32 * j;
-        r0.x[j] = c < ltot_r ? gp0[c] : make_double2(0.0, 0.0);
-        r1.x[j] = c < ltot_r ? gp1[c] : make_double2(0.0, 0.0);
+        r0.x[j] = (FULL || c < ltot_r) ? gp0[c] : make_double2(0.0, 0.0);
+        r1.x[j] = (FULL || c < ltot_r) ? gp1[c] : make_double2(0.0, 0.0);
     }
     {
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (lane + 32 * j < ldot) {
+            if (FULL || lane + 32 * j < ldot) {
                 a0 = fma(r0.x[j].x, r0.x[j].x, fma(r0.x[j].y, r0.x[j].y, a0));
                 a1 = fma(r1.x[j].x, r1.x[j].x, fma(r1.x[j].y, r1.x[j].y, a1));
             }
@@ -618,7 +621,7 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
-            if (c < ldot) { const cplx y = r[c]; b = fma(y.x, y.x, fma(y.y, y.y, b)); }
+            if (FULL || c < ldot) { const cplx y = r[c]; b = fma(y.x, y.x, fma(y.y, y.y, b)); }
         }
         b = warp_sum(b);
         if (lane == 0) { nq[rr] = b; dqs[rr] = 1.0; eqs[rr] = 1.0; }
@@ -635,11 +638,11 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
-            y[j] = c < ltot_r ? rq[c] : make_double2(0.0, 0.0);
+            y[j] = (FULL || c < ltot_r) ? rq[c] : make_double2(0.0, 0.0);
         }
         double dq = dqs[q], eq = eqs[q], bq = nq[q];
-        const int n0 = cross_pair(r0, y, dq, eq, bq, ldot, tol2, lane);
-        const int n1 = cross_pair(r1, y, dq, eq, bq, ldot, tol2, lane);
+        const int n0 = cross_pair<FULL>(r0, y, dq, eq, bq, ldot, tol2, lane);
+        const int n1 = cross_pair<FULL>(r1, y, dq, eq, bq, ldot, tol2, lane);
         nrot += n0 + n1;
         // Even rows of block J are visited in even steps, odd rows in odd steps, so steps 6 and 7 are the last
         // visits: fold the accumulated scale back into the row there.
@@ -655,7 +658,7 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = lane + 32 * j;
-                if (c < ltot_r) rq[c] = y[j];
+                if (FULL || c < ltot_r) rq[c] = y[j];
             }
             if (lane == 0) { dqs[q] = dq; eqs[q] = eq; nq[q] = bq; }
         }
@@ -677,14 +680,14 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
-            if (c < ltot_r) gp0[c] = make_double2(r0.x[j].x * r0.d, r0.x[j].y * r0.d);
+            if (FULL || c < ltot_r) gp0[c] = make_double2(r0.x[j].x * r0.d, r0.x[j].y * r0.d);
         }
     }
     if (r1.dirty) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
-            if (c < ltot_r) gp1[c] = make_double2(r1.x[j].x * r1.d, r1.x[j].y * r1.d);
+            if (FULL || c < ltot_r) gp1[c] = make_double2(r1.x[j].x * r1.d, r1.x[j].y * r1.d);
         }
     }
     fence_async_smem();
@@ -1126,17 +1129,28 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
     const int ltot_r = round_up(pl.ltot, 32);
     if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
         const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
-        static size_t configured = 0;
-        if (smem > configured) {
-            MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem));
-            configured = smem;
+        const bool full = (ltot_r == 256 && pl.ldot == 256);
+        static size_t configured[2] = {0, 0};
+        if (smem > configured[full]) {
+            if (full)
+                MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel<true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else
+                MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel<false>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[full] = smem;
         }
         const int nblk = pl.n_pad / 8;
         dim3 grid(nblk / 2, count);
-        jacobi_cross_kernel<<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot,
-                                                              ltot_r, nblk, round, s.rot, s.done, tol2,
-                                                              g_prof.enabled > 1 ? s.phase_clk : nullptr);
+        unsigned long long* pc = g_prof.enabled > 1 ? s.phase_clk : nullptr;
+        if (full)
+            jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
+                                                                         pl.ldot, ltot_r, nblk, round, s.rot, s.done,
+                                                                         tol2, pc);
+        else
+            jacobi_cross_kernel<false><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
+                                                                          pl.ldot, ltot_r, nblk, round, s.rot, s.done,
+                                                                          tol2, pc);
         MPSB_COUNT_LAUNCH();
         MPSB_CHECK_CUDA(cudaGetLastError());
         return 0;
