@@ -115,6 +115,78 @@ class ChainBatch:
         return _lib.to_host(self.rank).T
 
 
+class HostBondUpdater:
+    """Two-site updates on HOST-resident (pinned) batches: the public entry point for callers whose tensors live
+    in host memory (the reference keeps everything in numpy).  The batch is cut into `pieces` sub-batches; the
+    host->device copy of piece k+1 and the device->host copy of piece k-1 run on a copy stream while piece k is
+    in the kernels, so PCIe time hides behind the SVD.
+
+        upd = HostBondUpdater(n, chi_l, chi, chi_r, d, trun, err)
+        upd(Bi, Bj, Sl, U, Bi_out, Bj_out, Sr_out, rank_out)      # pinned torch CPU tensors, batch first
+    """
+
+    def __init__(self, n, xl, x, xr, d, trun, err, pieces=4):
+        t = _lib.torch()
+        self.n, self.xl, self.x, self.xr, self.d = n, xl, x, xr, d
+        self.trun, self.err = int(trun), float(err)
+        self.kcap = max(1, min(self.trun, d * xl, d * xr))
+        self.pieces = max(1, min(pieces, n))
+        self.bounds = [(n * k) // self.pieces for k in range(self.pieces + 1)]
+        m = max(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))
+        self.m = m
+        self.copy_stream = t.cuda.Stream()
+        self.dev = []
+        for _ in range(2):          # double-buffered device staging
+            self.dev.append(dict(Bi=_lib.empty((m, xl, d, x)), Bj=_lib.empty((m, x, d, xr)), Sl=_lib.empty((m, xl), "f64"),
+                                 U=_lib.empty((m, d, d, d, d)), Bio=_lib.empty((m, xl, d, self.kcap)),
+                                 Bjo=_lib.empty((m, self.kcap, d, xr)), Sro=_lib.empty((m, self.kcap), "f64"),
+                                 rk=_lib.empty((m,), "i32"), up=t.cuda.Event(), done=t.cuda.Event(), down=t.cuda.Event()))
+        lib = _lib.load()
+        self.ws_bytes = int(lib.mpsb_tebd_two_site_workspace(m, xl, x, xr, d))
+
+    def _upload(self, k, Bi, Bj, Sl, U):
+        t = _lib.torch()
+        a, b = self.bounds[k], self.bounds[k + 1]
+        buf = self.dev[k & 1]
+        with t.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(buf["down"])          # the previous occupant of this buffer has been read out
+            buf["Bi"][:b - a].copy_(Bi[a:b], non_blocking=True)
+            buf["Bj"][:b - a].copy_(Bj[a:b], non_blocking=True)
+            buf["Sl"][:b - a].copy_(Sl[a:b], non_blocking=True)
+            buf["U"][:b - a].copy_(U[a:b], non_blocking=True)
+            buf["up"].record(self.copy_stream)
+
+    def __call__(self, Bi, Bj, Sl, U, Bi_out, Bj_out, Sr_out, rank_out):
+        t = _lib.torch()
+        lib = _lib.load()
+        xl, x, xr, d, kcap = self.xl, self.x, self.xr, self.d, self.kcap
+        main = t.cuda.current_stream()
+        ws, wsn = _lib.workspace(self.ws_bytes)
+        for buf in self.dev:
+            buf["down"].record(main)
+        self._upload(0, Bi, Bj, Sl, U)
+        for k in range(self.pieces):
+            a, b = self.bounds[k], self.bounds[k + 1]
+            buf = self.dev[k & 1]
+            if k + 1 < self.pieces:
+                self._upload(k + 1, Bi, Bj, Sl, U)
+            main.wait_event(buf["up"])
+            _lib.check(lib.mpsb_tebd_two_site(b - a, xl, x, xr, d, _lib.ptr(buf["Bi"]), xl * d * x, _lib.ptr(buf["Bj"]),
+                                              x * d * xr, _lib.ptr(buf["Sl"]), xl, _lib.ptr(buf["U"]), d ** 4, self.trun,
+                                              self.err, kcap, _lib.ptr(buf["Bio"]), xl * d * kcap, _lib.ptr(buf["Bjo"]),
+                                              kcap * d * xr, _lib.ptr(buf["Sro"]), kcap, _lib.ptr(buf["rk"]), ws, wsn,
+                                              _lib.stream_ptr()), "mpsb_tebd_two_site")
+            buf["done"].record(main)
+            with t.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(buf["done"])
+                Bi_out[a:b].copy_(buf["Bio"][:b - a], non_blocking=True)
+                Bj_out[a:b].copy_(buf["Bjo"][:b - a], non_blocking=True)
+                Sr_out[a:b].copy_(buf["Sro"][:b - a], non_blocking=True)
+                rank_out[a:b].copy_(buf["rk"][:b - a], non_blocking=True)
+                buf["down"].record(self.copy_stream)
+        main.wait_stream(self.copy_stream)
+
+
 def shard(n_total, rank, world):
     """Contiguous block of chain indices owned by `rank`."""
     per, rem = divmod(n_total, world)
