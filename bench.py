@@ -185,7 +185,7 @@ def main():
                                        L.ptr(rk), ws, wsn, L.stream_ptr()), "mpsb_tebd_two_site")
 
     from dmrg_b200.batched import HostBondUpdater
-    host_update = HostBondUpdater(n, CHI, CHI, CHI, D, TRUN, ERR, pieces=4)
+    host_update = HostBondUpdater(n, CHI, CHI, CHI, D, TRUN, ERR, pieces=int(os.environ.get("MPSB_E2E_PIECES", "2")))
 
     def e2e_step():
         """Host buffers in, host buffers out, through the package's host-side entry point (H2D and D2H copies of

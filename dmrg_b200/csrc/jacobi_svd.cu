@@ -1190,7 +1190,7 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
     p.bsz = b;
     p.n_pad = round_up(n, 2 * b);
     const size_t matbytes = (size_t)p.n_pad * rowbytes;
-    const size_t l2_budget = (size_t)env_int("MPSB_SVD_L2_MB", 80) * 1024 * 1024;
+    const size_t l2_budget = (size_t)env_int("MPSB_SVD_L2_MB", 1 << 20) * 1024 * 1024;
     int chunk = (int)std::max<size_t>(1, l2_budget / matbytes);
     chunk = env_int("MPSB_SVD_CHUNK", chunk);
     if (chunk < 1) chunk = 1;
