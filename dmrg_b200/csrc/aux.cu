@@ -59,12 +59,16 @@ transpose_kernel(const cplx* __restrict__ in, int ldi, int rows, int cols, cplx*
 }
 
 constexpr int DOT_THREADS = 256;
-// part[j][chunk] = sum over the chunk of conj(V[j][i]) w[i]
+// y[j] = sum_i conj(V[j][i]) w[i]: every block reduces one chunk of one vector into part[j][chunk]; the block that
+// draws the last ticket of vector j adds the partials in a fixed order (deterministic) and re-arms the ticket.
+// `part` holds m * nchunk partial sums followed by m ticket counters (zero on entry, zero again on exit).
 __global__ void __launch_bounds__(DOT_THREADS)
-dot_partial_kernel(const cplx* __restrict__ V, long long ldv, long long n, const cplx* __restrict__ w,
-                   cplx* __restrict__ part, int nchunk) {
+dot_fused_kernel(const cplx* __restrict__ V, long long ldv, long long n, const cplx* __restrict__ w,
+                 cplx* __restrict__ part, int nchunk, int m_cap, cplx* __restrict__ y) {
     __shared__ double sr[DOT_THREADS / 32], si[DOT_THREADS / 32];
+    __shared__ int is_last;
     const int j = blockIdx.y, ch = blockIdx.x;
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(part + (size_t)m_cap * nchunk);
     const long long per = (n + nchunk - 1) / nchunk;
     const long long lo = (long long)ch * per, hi = lo + per < n ? lo + per : n;
     const cplx* v = V + (size_t)j * ldv;
@@ -85,14 +89,27 @@ dot_partial_kernel(const cplx* __restrict__ V, long long ldv, long long n, const
         double a = 0.0, b = 0.0;
         for (int q = 0; q < DOT_THREADS / 32; ++q) { a += sr[q]; b += si[q]; }
         part[(size_t)j * nchunk + ch] = make_double2(a, b);
+        __threadfence();
+        is_last = (atomicAdd(&tickets[j], 1u) == (unsigned)(nchunk - 1));
     }
-}
-__global__ void dot_final_kernel(const cplx* __restrict__ part, int nchunk, int m, cplx* __restrict__ y) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    double a = 0.0, b = 0.0;
-    for (int q = 0; q < nchunk; ++q) { a += part[(size_t)j * nchunk + q].x; b += part[(size_t)j * nchunk + q].y; }
-    y[j] = make_double2(a, b);
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        double a = 0.0, b = 0.0;
+        for (int q = threadIdx.x; q < nchunk; q += 32) {
+            const cplx t = __ldcg(&part[(size_t)j * nchunk + q]);
+            a += t.x;
+            b += t.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (threadIdx.x == 0) {
+            y[j] = make_double2(a, b);
+            tickets[j] = 0u;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -162,13 +179,11 @@ int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_
 }
 
 int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
-                cudaStream_t st) {
+                int m_cap, cudaStream_t st) {
     if (m == 0) return 0;
-    MPSB_REQUIRE(m <= 65535 && nchunk >= 1, "zdotc_multi: bad m=%d nchunk=%d", m, nchunk);
+    MPSB_REQUIRE(m <= 65535 && m <= m_cap && nchunk >= 1, "zdotc_multi: bad m=%d (cap %d) nchunk=%d", m, m_cap, nchunk);
     dim3 grid(nchunk, m);
-    dot_partial_kernel<<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk);
-    MPSB_COUNT_LAUNCH();
-    dot_final_kernel<<<(m + 63) / 64, 64, 0, st>>>(part, nchunk, m, y);
+    dot_fused_kernel<<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk, m_cap, y);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;

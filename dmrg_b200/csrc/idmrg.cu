@@ -6,7 +6,11 @@
 //   mpsb_env_left/right   environment growth as GEMM -> W kernel -> GEMM                    (replaces :59-60)
 // Index conventions: L[A,a,i] (bra, ket, mpo), R[D,d,k], W[i,j,B,b] (mpo-row, mpo-col, bra, ket),
 // theta[a,b,c,d] (left bond, phys1, phys2, right bond).
+#include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../include/mpsb.h"
@@ -156,11 +160,11 @@ void sym_eig_host(int m, std::vector<double>& a, std::vector<double>& v) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j) (i == j ? diag : off) += a[(size_t)i * m + j] * a[(size_t)i * m + j];
-        if (off <= 1e-34 * (diag + off)) break;
+        if (off <= 1e-29 * (diag + off)) break;      // off-norm / norm <= 3e-15: quadratically convergent from here
         for (int p = 0; p < m - 1; ++p)
             for (int q = p + 1; q < m; ++q) {
                 const double apq = a[(size_t)p * m + q];
-                if (apq == 0.0) continue;
+                if (std::fabs(apq) <= 1e-17 * std::sqrt(std::fabs(a[(size_t)p * m + p] * a[(size_t)q * m + q])) ) continue;
                 const double tau = (a[(size_t)q * m + q] - a[(size_t)p * m + p]) / (2.0 * apq);
                 const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
                 const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
@@ -205,17 +209,24 @@ int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void
     return heff_apply(h, static_cast<const cplx*>(theta), static_cast<cplx*>(out), st);
 }
 
+constexpr int LANCZOS_KEEP = 8;        // Ritz vectors carried across a (thick) restart
+
 size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
     const size_t n = (size_t)chil * d * d * chir;
     const int nchunk = 64;
     const size_t kk = (size_t)krylov + 2;
-    return heff_bytes(chil, chir, d, w) + al(n * sizeof(cplx)) * kk + al(kk * nchunk * sizeof(cplx)) +
-           al(kk * kk * sizeof(cplx)) * 2 + al(kk * sizeof(cplx)) * 2;
+    return heff_bytes(chil, chir, d, w) + al(n * sizeof(cplx)) * (kk + LANCZOS_KEEP) + al(kk * (nchunk + 1) * sizeof(cplx)) +
+           al(kk * kk * sizeof(cplx)) * 2 + al(kk * sizeof(cplx)) * 2 + al(kk * LANCZOS_KEEP * sizeof(cplx));
 }
 
-// One restart cycle runs without any host synchronisation: the Gram-Schmidt coefficients stay on the device
-// (the axpy kernel reads them there), normalisation uses the device-resident norm, and alpha / beta are read
-// back once per cycle.
+// Thick-restart Lanczos with full (twice-applied) reorthogonalisation.
+//  * A cycle extends the orthonormal basis V[0..m] one product at a time; the Gram-Schmidt coefficients stay on the
+//    device (the axpy kernel reads them there) and the new vector is normalised from the device-resident norm, so a
+//    cycle runs without host synchronisation; coefficients are read back once per cycle.
+//  * The projected matrix Hp = V^H H V is assembled from those coefficients (column j: h_ij = c1_i + c2_i, i <= j,
+//    and the norm beta_j below the diagonal).  After a restart its leading block is diag(theta) of the kept Ritz
+//    vectors and the couplings to the continued Lanczos vector are measured by the same Gram-Schmidt pass.
+//  * Restart: keep the LANCZOS_KEEP lowest Ritz vectors (V Y) plus the residual vector v_{m}.
 int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
                         int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
                         int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
@@ -237,19 +248,22 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     p += heff_bytes(chil, chir, d, w);
     const size_t vstride = al(n * sizeof(cplx)) / sizeof(cplx);
     cplx* V = reinterpret_cast<cplx*>(p);                 p += al(n * sizeof(cplx)) * kk;
-    cplx* part = reinterpret_cast<cplx*>(p);              p += al(kk * nchunk * sizeof(cplx));
+    cplx* Vk = reinterpret_cast<cplx*>(p);                p += al(n * sizeof(cplx)) * LANCZOS_KEEP;   // Ritz vectors
+    cplx* part = reinterpret_cast<cplx*>(p);              p += al(kk * (nchunk + 1) * sizeof(cplx));   // partials + tickets
     cplx* C1 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-1 coefficients, row j
     cplx* C2 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-2 coefficients
     cplx* N2 = reinterpret_cast<cplx*>(p);                p += al(kk * sizeof(cplx));        // ||w_j||^2
-    cplx* c3 = reinterpret_cast<cplx*>(p);
+    cplx* c3 = reinterpret_cast<cplx*>(p);                p += al(kk * sizeof(cplx));
+    cplx* Yd = reinterpret_cast<cplx*>(p);                                                     // [keep][kk] Ritz coefficients
     cplx* th = static_cast<cplx*>(theta);
-    std::vector<cplx> h1(kk * kk), h2(kk * kk), hn(kk), hc(kk);
-    std::vector<double> alpha, beta, T, Y;
+    std::vector<cplx> h1(kk * kk), h2(kk * kk), hn(kk), hc(kk * LANCZOS_KEEP);
+    std::vector<double> Hp((size_t)m * m, 0.0), T, Y;
     int n_mv = 0;
     double E = 0.0, resid = 0.0;
 
+    MPSB_CHECK_CUDA(cudaMemsetAsync(part, 0, al(kk * (nchunk + 1) * sizeof(cplx)), st));
     // normalise the start vector into V[0]
-    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, st);
+    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st);
     if (rc) return rc;
     MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx), cudaMemcpyDeviceToHost, st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -258,75 +272,100 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     rc = znormalise((long long)n, N2, V, st);
     if (rc) return rc;
 
-    for (int restart = 0; restart < max_restarts; ++restart) {
-        for (int j = 0; j < m; ++j) {
+    int j0 = 0;                 // first basis index whose product has not been formed yet
+    bool converged = false;
+    const bool dbg = getenv("MPSB_LANCZOS_DEBUG") != nullptr;
+    double t_enq = 0.0, t_wait = 0.0, t_host = 0.0;
+    auto now = [] { return std::chrono::high_resolution_clock::now(); };
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    for (int restart = 0; restart < max_restarts && !converged; ++restart) {
+        auto ta = now();
+        for (int j = j0; j < m; ++j) {
             cplx* wv = V + (size_t)(j + 1) * vstride;
             rc = heff_apply(h, V + (size_t)j * vstride, wv, st);
             if (rc) return rc;
             ++n_mv;
-            // two passes of classical Gram-Schmidt against V[0..j]; coefficients never leave the device
             for (int pass = 0; pass < 2; ++pass) {
                 cplx* c = (pass == 0 ? C1 : C2) + (size_t)j * kk;
-                rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, st);
+                rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, (int)kk, st);
                 if (rc) return rc;
                 rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c, -1.0, wv, st);
                 if (rc) return rc;
             }
-            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, N2 + j, part, nchunk, st);
+            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, N2 + j, part, nchunk, (int)kk, st);
             if (rc) return rc;
             rc = znormalise((long long)n, N2 + j, wv, st);
             if (rc) return rc;
         }
         MPSB_CHECK_CUDA(cudaMemcpyAsync(h1.data(), C1, sizeof(cplx) * kk * m, cudaMemcpyDeviceToHost, st));
         MPSB_CHECK_CUDA(cudaMemcpyAsync(h2.data(), C2, sizeof(cplx) * kk * m, cudaMemcpyDeviceToHost, st));
+        auto tb = now();
         MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx) * m, cudaMemcpyDeviceToHost, st));
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-        alpha.assign(m, 0.0);
-        beta.assign(m, 0.0);
+        auto tc = now();
+        t_enq += us(ta, tb);
+        t_wait += us(tb, tc);
+        // assemble the new columns of the projected matrix; stop at an invariant subspace
         int mm = m;
-        for (int j = 0; j < m; ++j) {
-            alpha[j] = h1[(size_t)j * kk + j].x + h2[(size_t)j * kk + j].x;
-            beta[j] = std::sqrt(hn[j].x > 0.0 ? hn[j].x : 0.0);
-            if (!(beta[j] > 1e-14 * (std::fabs(alpha[0]) + 1e-300)) || !std::isfinite(beta[j])) {   // invariant subspace
-                mm = j + 1;
-                break;
+        double beta_last = 0.0;
+        for (int j = j0; j < m; ++j) {
+            for (int i = 0; i <= j; ++i) {
+                const double v = h1[(size_t)j * kk + i].x + h2[(size_t)j * kk + i].x;
+                Hp[(size_t)i * m + j] = v;
+                Hp[(size_t)j * m + i] = v;
             }
+            const double bj = std::sqrt(hn[j].x > 0.0 ? hn[j].x : 0.0);
+            beta_last = bj;
+            if (j + 1 < m) { Hp[(size_t)(j + 1) * m + j] = bj; Hp[(size_t)j * m + j + 1] = bj; }
+            if (!(bj > 1e-14 * (std::fabs(Hp[0]) + 1e-300)) || !std::isfinite(bj)) { mm = j + 1; break; }
         }
-        // Ritz pair of the mm x mm tridiagonal matrix
         T.assign((size_t)mm * mm, 0.0);
-        for (int i = 0; i < mm; ++i) {
-            T[(size_t)i * mm + i] = alpha[i];
-            if (i + 1 < mm) T[(size_t)i * mm + i + 1] = T[(size_t)(i + 1) * mm + i] = beta[i];
-        }
+        for (int i = 0; i < mm; ++i)
+            for (int q = 0; q < mm; ++q) T[(size_t)i * mm + q] = Hp[(size_t)i * m + q];
         sym_eig_host(mm, T, Y);
-        int best = 0;
-        for (int i = 1; i < mm; ++i)
-            if (T[(size_t)i * mm + i] < T[(size_t)best * mm + best]) best = i;
+        std::vector<int> idx(mm);
+        for (int i = 0; i < mm; ++i) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return T[(size_t)a * mm + a] < T[(size_t)b * mm + b]; });
+        const int best = idx[0];
         E = T[(size_t)best * mm + best];
-        resid = std::fabs(beta[mm - 1] * Y[(size_t)(mm - 1) * mm + best]);
-        // theta = sum_j y_j V[j], renormalised (guards against drift); restart from it
-        for (int i = 0; i < mm; ++i) hc[i] = make_double2(Y[(size_t)i * mm + best], 0.0);
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(c3, hc.data(), sizeof(cplx) * mm, cudaMemcpyHostToDevice, st));
-        MPSB_CHECK_CUDA(cudaMemsetAsync(th, 0, n * sizeof(cplx), st));
-        rc = zaxpy_multi(V, (long long)vstride, mm, (long long)n, c3, 1.0, th, st);
-        if (rc) return rc;
-        rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, st);
-        if (rc) return rc;
-        rc = znormalise((long long)n, N2, th, st);
-        if (rc) return rc;
-        if (resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0) || mm < m) break;
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+        resid = std::fabs(beta_last * Y[(size_t)(mm - 1) * mm + best]);
+        converged = resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0) || mm < m || restart + 1 == max_restarts;
+        const int keep = converged ? 1 : std::min(LANCZOS_KEEP, mm - 1);
+        // Ritz vectors Vk[i] = sum_q Y[q][idx[i]] V[q]
+        for (int i = 0; i < keep; ++i)
+            for (int q = 0; q < mm; ++q) hc[(size_t)i * kk + q] = make_double2(Y[(size_t)q * mm + idx[i]], 0.0);
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(cplx) * kk * keep, cudaMemcpyHostToDevice, st));
+        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, al(n * sizeof(cplx)) * keep, st));
+        for (int i = 0; i < keep; ++i) {
+            rc = zaxpy_multi(V, (long long)vstride, mm, (long long)n, Yd + (size_t)i * kk, 1.0, Vk + (size_t)i * vstride, st);
+            if (rc) return rc;
+        }
+        t_host += us(tc, now());
+        if (converged) break;
+        // new basis: kept Ritz vectors, then the residual direction v_m (already orthogonal to all of them)
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(V + (size_t)keep * vstride, V + (size_t)m * vstride, n * sizeof(cplx),
+                                        cudaMemcpyDeviceToDevice, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(V, Vk, al(n * sizeof(cplx)) * keep, cudaMemcpyDeviceToDevice, st));
+        std::fill(Hp.begin(), Hp.end(), 0.0);
+        for (int i = 0; i < keep; ++i) Hp[(size_t)i * m + i] = T[(size_t)idx[i] * mm + idx[i]];
+        j0 = keep;
     }
-    // Rayleigh quotient and true residual ||H theta - E theta|| of the returned vector, one more product
+    if (dbg) fprintf(stderr, "[mpsb] lanczos: %d matvecs, enqueue %.0f us, wait %.0f us, host ritz %.0f us\n", n_mv, t_enq, t_wait, t_host);
+    // returned vector: lowest Ritz vector, renormalised; Rayleigh quotient and true residual with one more product
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(th, Vk, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st);
+    if (rc) return rc;
+    rc = znormalise((long long)n, N2, th, st);
+    if (rc) return rc;
     cplx* hv = V + (size_t)1 * vstride;
     rc = heff_apply(h, th, hv, st);
     if (rc) return rc;
     ++n_mv;
-    rc = zdotc_multi(th, 0, 1, (long long)n, hv, C1, part, nchunk, st);
+    rc = zdotc_multi(th, 0, 1, (long long)n, hv, C1, part, nchunk, (int)kk, st);
     if (rc) return rc;
     rc = zaxpy_multi(th, 0, 1, (long long)n, C1, -1.0, hv, st);
     if (rc) return rc;
-    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, N2, part, nchunk, st);
+    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, N2, part, nchunk, (int)kk, st);
     if (rc) return rc;
     MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), C1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
     MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx), cudaMemcpyDeviceToHost, st));

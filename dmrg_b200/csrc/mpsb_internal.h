@@ -100,9 +100,10 @@ int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int l
 // out[c][a][b] = in[a][b][c]  (n_ab = a*b merged)   and the inverse
 int perm_last_to_first(const cplx* in, int n_ab, int n_c, cplx* out, cudaStream_t st);
 int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_t st);
-// y[j] = sum_i conj(V[j][i]) w[i]  for j < m (deterministic two-pass reduction); part: m * nchunk scratch
+// y[j] = sum_i conj(V[j][i]) w[i]  for j < m (deterministic, single launch).  part: m_cap * nchunk partial sums
+// followed by m_cap ticket counters (unsigned int) that must be zero on entry; they are zero again on exit.
 int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
-                cudaStream_t st);
+                int m_cap, cudaStream_t st);
 // w[i] += sign * sum_j c[j] V[j][i]   (c on device, m entries)
 int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
                 cudaStream_t st);

@@ -50,6 +50,23 @@ def halve(psi, sh, trunc=10):
     return U, s_all, V
 
 
+def _halve_split(theta, sh, trunc):
+    """U and V of the two-site tensor from two independent row-orthogonalisations (of psi and of psi^H) instead of
+    one with carried identity columns: rows stay half as long, which keeps chi <= 128 on the register-resident
+    Jacobi kernel.  U and V then carry unrelated phases per singular vector - harmless for `next_LR`, whose two
+    environment updates use them separately (DMRG/iDMRG.py:59-60)."""
+    lsize, rsize = sh[0] * sh[1], sh[2] * sh[3]
+    A = theta.reshape(lsize, rsize)
+    _, s_all, vh, k = _device_svd(A, lsize, rsize, trunc, 0.0, want_u=False, normalise=0)
+    _, _, uh, k2 = _device_svd(_lib.conj_transpose(A), rsize, lsize, trunc, 0.0, want_u=False, normalise=0)
+    assert k == k2
+    U = _lib.conj_transpose(uh)
+    return U.reshape(sh[0], sh[1], k), s_all, vh.reshape(k, sh[2], sh[3])
+
+
+_halve_public = halve
+
+
 def _heff_apply(L, M, R, theta):
     lib = _lib.load()
     xl, xr, w, d = L.shape[0], R.shape[0], M.shape[0], M.shape[2]
@@ -86,9 +103,12 @@ def ground_state(Ld, Md, Rd, seed=0, theta0=None):
     """Lowest eigenpair of H_eff on device tensors: (E, theta) with theta normalised."""
     lib = _lib.load()
     xl, xr, w, d = Ld.shape[0], Rd.shape[0], Md.shape[0], Md.shape[2]
-    if theta0 is None:
-        rs = np.random.RandomState(seed)
-        theta0 = _lib.to_device(rs.randn(xl, d, d, xr) + 1j * rs.randn(xl, d, d, xr))
+    if theta0 is None:      # seeded start vector, generated on the device (the reference's ARPACK start is random too)
+        t = _lib.torch()
+        gen = t.Generator(device=_lib.device())
+        gen.manual_seed(int(seed))
+        theta0 = t.randn((xl, d, d, xr, 2), dtype=t.float64, device=_lib.device(), generator=gen)
+        theta0 = t.view_as_complex(theta0)
     theta = theta0.clone()
     import ctypes
     E, resid, nmv = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
@@ -117,7 +137,12 @@ def next_LR_device(Ld, Rd, Md, trunc=None, swap_conj=False, seed=0):
     """`next_LR` on device-resident tensors (no host round trip): returns (L', R', E, S_all)."""
     E, theta = ground_state(Ld, Md, Rd, seed=seed)
     sh = tuple(theta.shape)
-    U, S, V = halve(theta, sh) if trunc is None else halve(theta, sh, trunc)
+    if trunc is None and halve is not _halve_public:       # somebody rebound the module-level halve (reference idiom)
+        U, S, V = halve(theta, sh)
+    elif sh[0] * sh[1] <= 256:                             # carried-identity SVD is faster while rows stay short
+        U, S, V = halve(theta, sh, 10 if trunc is None else trunc)
+    else:
+        U, S, V = _halve_split(theta, sh, 10 if trunc is None else trunc)
     Ln = _env(True, Ld, U.contiguous(), Md, swap_conj)
     Rn = _env(False, Rd, V.contiguous(), Md, swap_conj)
     last_info["S"] = _lib.to_host(S)
