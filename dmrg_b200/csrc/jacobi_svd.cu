@@ -1516,7 +1516,8 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
 
     prof_mark(3, st);
     const double eps = 2.220446049250313e-16;
-    const double tol = sqrt((double)pl.ldot) * eps;
+    static const double tol_factor = (double)env_int("MPSB_SVD_TOL_X10", 10) / 10.0;
+    const double tol = tol_factor * sqrt((double)pl.ldot) * eps;
     const double eabs = 0.0;   // purely relative criterion: kept right singular vectors must be orthonormal to ~tol
     const double tol2 = tol * tol, eabs2 = eabs * eabs;
     const int nblk = pl.n_pad / pl.bsz;
