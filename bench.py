@@ -251,6 +251,15 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in (Bi_p, Bj_p, Sl_p, U_p))
     d2h = sum(t.numel() * t.element_size() for t in (Bio_p, Bjo_p, Sro_p, rk_p))
 
+    # per-chain observables of the last step (entanglement entropy of the new bond, kept rank), gathered over the
+    # ranks with the path's one collective (outside the timed region)
+    from dmrg_b200.batched import gather_observables
+    p2 = Sro * Sro
+    ent = -(torch.where(p2 > 0, p2 * torch.log(p2.clamp_min(1e-300)), torch.zeros_like(p2))).sum(dim=1)
+    obs = gather_observables(torch.stack([ent, rk.to(torch.float64)], dim=1))
+    obs_summary = {"chains": int(obs.shape[0]), "mean_entropy": float(obs[:, 0].mean().item()),
+                   "mean_rank": float(obs[:, 1].mean().item())}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -323,6 +332,7 @@ def main():
                 ["theta_gemm", "gate", "qr", "jacobi", "finalise", "backproj_gemm"], phases)},
             "svd": {"sweeps_slowest_problem": int(sv_sweeps), "rotations_per_update": rot / (k_steps * n),
                     "sweeps_per_update": sweeps / (k_steps * n), "all_ranks_full": ranks_ok},
+            "observables": obs_summary,
             "hbm_mandatory_gbs": hbm_bytes / (ms_total * 1e-3) / 1e9,
             "hbm_peak_gbs": peaks.get("hbm_gbs")}
     if world == 1 and not args.no_idmrg:
