@@ -117,74 +117,86 @@ class ChainBatch:
 
 class HostBondUpdater:
     """Two-site updates on HOST-resident (pinned) batches: the public entry point for callers whose tensors live
-    in host memory (the reference keeps everything in numpy).  The batch is cut into `pieces` sub-batches; the
-    host->device copy of piece k+1 and the device->host copy of piece k-1 run on a copy stream while piece k is
-    in the kernels, so PCIe time hides behind the SVD.
+    in host memory (the reference keeps everything in numpy).  Device staging is double-buffered and all copies run
+    on a private copy stream, so a caller that streams batches through
 
         upd = HostBondUpdater(n, chi_l, chi, chi_r, d, trun, err)
-        upd(Bi, Bj, Sl, U, Bi_out, Bj_out, Sr_out, rank_out)      # pinned torch CPU tensors, batch first
-    """
+        upd.stage(Bi, Bj, Sl, U)                      # host -> device of batch 0 (asynchronous)
+        for each batch k:
+            upd.stage(<inputs of batch k+1>)          # overlaps the kernels of batch k
+            upd.run(Bi_out, Bj_out, Sr_out, rank_out) # kernels of batch k, then device -> host (asynchronous)
+        upd.finish()                                  # outputs of the last batch are in the host buffers
 
-    def __init__(self, n, xl, x, xr, d, trun, err, pieces=4):
+    hides the PCIe time behind the SVD.  `upd(Bi, Bj, Sl, U, Bi_out, Bj_out, Sr_out, rank_out)` is the plain
+    synchronous form (stage + run + finish).  All host tensors are pinned torch CPU tensors, batch first."""
+
+    def __init__(self, n, xl, x, xr, d, trun, err):
         t = _lib.torch()
         self.n, self.xl, self.x, self.xr, self.d = n, xl, x, xr, d
         self.trun, self.err = int(trun), float(err)
         self.kcap = max(1, min(self.trun, d * xl, d * xr))
-        self.pieces = max(1, min(pieces, n))
-        self.bounds = [(n * k) // self.pieces for k in range(self.pieces + 1)]
-        m = max(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))
-        self.m = m
         self.copy_stream = t.cuda.Stream()
-        self.dev = []
-        for _ in range(2):          # double-buffered device staging
-            self.dev.append(dict(Bi=_lib.empty((m, xl, d, x)), Bj=_lib.empty((m, x, d, xr)), Sl=_lib.empty((m, xl), "f64"),
-                                 U=_lib.empty((m, d, d, d, d)), Bio=_lib.empty((m, xl, d, self.kcap)),
-                                 Bjo=_lib.empty((m, self.kcap, d, xr)), Sro=_lib.empty((m, self.kcap), "f64"),
-                                 rk=_lib.empty((m,), "i32"), up=t.cuda.Event(), done=t.cuda.Event(), down=t.cuda.Event()))
-        lib = _lib.load()
-        self.ws_bytes = int(lib.mpsb_tebd_two_site_workspace(m, xl, x, xr, d))
+        self.bufs = []
+        for _ in range(2):
+            self.bufs.append(dict(Bi=_lib.empty((n, xl, d, x)), Bj=_lib.empty((n, x, d, xr)), Sl=_lib.empty((n, xl), "f64"),
+                                  U=_lib.empty((n, d, d, d, d)), Bio=_lib.empty((n, xl, d, self.kcap)),
+                                  Bjo=_lib.empty((n, self.kcap, d, xr)), Sro=_lib.empty((n, self.kcap), "f64"),
+                                  rk=_lib.empty((n,), "i32"), up=t.cuda.Event(), computed=t.cuda.Event(),
+                                  down=t.cuda.Event()))
+        self.ws_bytes = int(_lib.load().mpsb_tebd_two_site_workspace(n, xl, x, xr, d))
+        self.staged = []          # buffer indices uploaded and not yet run
+        self.next_buf = 0
+        main = t.cuda.current_stream()
+        for b in self.bufs:
+            b["computed"].record(main)
+            b["down"].record(main)
 
-    def _upload(self, k, Bi, Bj, Sl, U):
+    def stage(self, Bi, Bj, Sl, U):
         t = _lib.torch()
-        a, b = self.bounds[k], self.bounds[k + 1]
-        buf = self.dev[k & 1]
+        assert len(self.staged) < 2, "two batches are already staged"
+        k = self.next_buf
+        self.next_buf ^= 1
+        buf = self.bufs[k]
         with t.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(buf["down"])          # the previous occupant of this buffer has been read out
-            buf["Bi"][:b - a].copy_(Bi[a:b], non_blocking=True)
-            buf["Bj"][:b - a].copy_(Bj[a:b], non_blocking=True)
-            buf["Sl"][:b - a].copy_(Sl[a:b], non_blocking=True)
-            buf["U"][:b - a].copy_(U[a:b], non_blocking=True)
+            self.copy_stream.wait_event(buf["computed"])       # the kernels that read these inputs have finished
+            buf["Bi"].copy_(Bi, non_blocking=True)
+            buf["Bj"].copy_(Bj, non_blocking=True)
+            buf["Sl"].copy_(Sl, non_blocking=True)
+            buf["U"].copy_(U, non_blocking=True)
             buf["up"].record(self.copy_stream)
+        self.staged.append(k)
 
-    def __call__(self, Bi, Bj, Sl, U, Bi_out, Bj_out, Sr_out, rank_out):
+    def run(self, Bi_out, Bj_out, Sr_out, rank_out):
         t = _lib.torch()
         lib = _lib.load()
-        xl, x, xr, d, kcap = self.xl, self.x, self.xr, self.d, self.kcap
+        assert self.staged, "nothing staged"
+        buf = self.bufs[self.staged.pop(0)]
+        xl, x, xr, d, kcap, n = self.xl, self.x, self.xr, self.d, self.kcap, self.n
         main = t.cuda.current_stream()
         ws, wsn = _lib.workspace(self.ws_bytes)
-        for buf in self.dev:
-            buf["down"].record(main)
-        self._upload(0, Bi, Bj, Sl, U)
-        for k in range(self.pieces):
-            a, b = self.bounds[k], self.bounds[k + 1]
-            buf = self.dev[k & 1]
-            if k + 1 < self.pieces:
-                self._upload(k + 1, Bi, Bj, Sl, U)
-            main.wait_event(buf["up"])
-            _lib.check(lib.mpsb_tebd_two_site(b - a, xl, x, xr, d, _lib.ptr(buf["Bi"]), xl * d * x, _lib.ptr(buf["Bj"]),
-                                              x * d * xr, _lib.ptr(buf["Sl"]), xl, _lib.ptr(buf["U"]), d ** 4, self.trun,
-                                              self.err, kcap, _lib.ptr(buf["Bio"]), xl * d * kcap, _lib.ptr(buf["Bjo"]),
-                                              kcap * d * xr, _lib.ptr(buf["Sro"]), kcap, _lib.ptr(buf["rk"]), ws, wsn,
-                                              _lib.stream_ptr()), "mpsb_tebd_two_site")
-            buf["done"].record(main)
-            with t.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(buf["done"])
-                Bi_out[a:b].copy_(buf["Bio"][:b - a], non_blocking=True)
-                Bj_out[a:b].copy_(buf["Bjo"][:b - a], non_blocking=True)
-                Sr_out[a:b].copy_(buf["Sro"][:b - a], non_blocking=True)
-                rank_out[a:b].copy_(buf["rk"][:b - a], non_blocking=True)
-                buf["down"].record(self.copy_stream)
-        main.wait_stream(self.copy_stream)
+        main.wait_event(buf["up"])
+        main.wait_event(buf["down"])                             # previous outputs of this buffer have left the device
+        _lib.check(lib.mpsb_tebd_two_site(n, xl, x, xr, d, _lib.ptr(buf["Bi"]), xl * d * x, _lib.ptr(buf["Bj"]), x * d * xr,
+                                          _lib.ptr(buf["Sl"]), xl, _lib.ptr(buf["U"]), d ** 4, self.trun, self.err, kcap,
+                                          _lib.ptr(buf["Bio"]), xl * d * kcap, _lib.ptr(buf["Bjo"]), kcap * d * xr,
+                                          _lib.ptr(buf["Sro"]), kcap, _lib.ptr(buf["rk"]), ws, wsn, _lib.stream_ptr()),
+                   "mpsb_tebd_two_site")
+        buf["computed"].record(main)
+        with t.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(buf["computed"])
+            Bi_out.copy_(buf["Bio"], non_blocking=True)
+            Bj_out.copy_(buf["Bjo"], non_blocking=True)
+            Sr_out.copy_(buf["Sro"], non_blocking=True)
+            rank_out.copy_(buf["rk"], non_blocking=True)
+            buf["down"].record(self.copy_stream)
+
+    def finish(self):
+        _lib.torch().cuda.current_stream().wait_stream(self.copy_stream)
+
+    def __call__(self, Bi, Bj, Sl, U, Bi_out, Bj_out, Sr_out, rank_out):
+        self.stage(Bi, Bj, Sl, U)
+        self.run(Bi_out, Bj_out, Sr_out, rank_out)
+        self.finish()
 
 
 def shard(n_total, rank, world):

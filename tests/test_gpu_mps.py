@@ -256,13 +256,22 @@ def test_host_bond_updater_matches_direct_call(lib):
     Sl = np.abs(rs.randn(n, xl)) + 0.1
     U = np.stack([la.expm(-0.1j * (h + h.conj().T)).reshape([d] * 4) for h in rs.randn(n, 4, 4) + 1j * rs.randn(n, 4, 4)])
     trun, err = 8, 1e-12
-    upd = HostBondUpdater(n, xl, x, xr, d, trun, err, pieces=3)
+    upd = HostBondUpdater(n, xl, x, xr, d, trun, err)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     k = upd.kcap
     Bio, Bjo = torch.empty((n, xl, d, k), dtype=torch.complex128).pin_memory(), torch.empty((n, k, d, xr), dtype=torch.complex128).pin_memory()
     Sro, rk = torch.empty((n, k), dtype=torch.float64).pin_memory(), torch.empty((n,), dtype=torch.int32).pin_memory()
-    upd(pin(Bi), pin(Bj), pin(Sl), pin(U), Bio, Bjo, Sro, rk)
+    ins = (pin(Bi), pin(Bj), pin(Sl), pin(U))
+    upd(*ins, Bio, Bjo, Sro, rk)
     torch.cuda.synchronize()
+    first = (Bio.clone(), Sro.clone())
+    upd.stage(*ins)                       # streamed form: two batches in flight
+    upd.stage(*ins)
+    upd.run(Bio, Bjo, Sro, rk)
+    upd.run(Bio, Bjo, Sro, rk)
+    upd.finish()
+    torch.cuda.synchronize()
+    assert torch.equal(first[0], Bio) and torch.equal(first[1], Sro)
     for c in range(n):
         o = OracleMPS([Bi[c], Bj[c]], trun=trun, err=err)
         o.s[0] = Sl[c]
