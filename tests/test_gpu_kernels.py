@@ -200,3 +200,53 @@ def test_transfer_step(lib):
     np.testing.assert_allclose(lib.to_host(out), np.einsum('kl,kio,ij,ljr->or', E, A.conj(), Op, B), atol=1e-12)
     out = MPS._transfer(lib.to_device(E), lib.to_device(A), lib.to_device(B), None)
     np.testing.assert_allclose(lib.to_host(out), np.einsum('kl,kio,lir->or', E, A.conj(), B), atol=1e-12)
+
+
+def test_svd_fuzz_shapes(lib):
+    """40 random shapes (1..90 rows/cols, tall, wide, tiny) through every Jacobi kernel variant and padding path."""
+    from dmrg_b200.MPS import svd_truncate
+    rs = np.random.RandomState(2024)
+    for trial in range(40):
+        rows, cols = int(rs.randint(1, 91)), int(rs.randint(1, 91))
+        m = crand(rs, rows, cols)
+        if trial % 5 == 0:                          # rank deficient
+            r = max(1, min(rows, cols) // 2)
+            m = crand(rs, rows, r) @ crand(rs, r, cols)
+        trun = int(rs.choice([3, 17, 1000]))
+        err = float(rs.choice([1e-13, 1e-6]))
+        u, s, vh = svd_truncate(m, trun=trun, err=err)
+        uo, so, vo = oracle_svd_truncate(m, trun=trun, err=err)
+        assert len(s) == len(so), (rows, cols, trun, err, len(s), len(so))
+        if len(s) == 0:
+            continue
+        np.testing.assert_allclose(s, so, rtol=1e-10, atol=1e-14, err_msg=str((rows, cols, trun, err)))
+        k = len(s)
+        s_raw = la.svd(m, compute_uv=False)[:k]
+        np.testing.assert_allclose(u.conj().T @ u, np.eye(k), atol=1e-11)
+        np.testing.assert_allclose(vh @ vh.conj().T, np.eye(k), atol=1e-11)
+        # u s vh is the best rank-k approximation: same as LAPACK's up to the gauge of degenerate values
+        np.testing.assert_allclose((u * s_raw) @ vh, (uo * s_raw) @ vo, atol=1e-9 * s_raw[0])
+
+
+def test_tebd_fuzz_shapes(lib):
+    """Random (chi_l, chi, chi_r, d) two-site updates, batch 3, against the oracle."""
+    rs = np.random.RandomState(77)
+    for trial in range(16):
+        d = int(rs.choice([2, 2, 3, 4]))
+        xl, x, xr = (int(v) for v in rs.randint(1, 24, size=3))
+        b = 3
+        Bi, Bj = crand(rs, b, xl, d, x), crand(rs, b, x, d, xr)
+        Sl = np.abs(rs.randn(b, xl)) + 0.05
+        h = crand(rs, d * d, d * d)
+        U = la.expm(-0.15j * (h + h.conj().T)).reshape([d] * 4)
+        trun, err = int(rs.choice([4, 12, 64])), 1e-11
+        kcap = max(1, min(trun, d * xl, d * xr))
+        bio, bjo, sro, rank = _tebd_call(lib, Bi, Bj, Sl, U, trun, err, kcap)
+        for c in range(b):
+            Mi, Mj, s = _oracle_update(Bi[c], Bj[c], Sl[c], U, trun, err)
+            k = len(s)
+            assert rank[c] == k, (xl, x, xr, d, trun)
+            np.testing.assert_allclose(sro[c, :k], s, rtol=1e-9, atol=1e-14)
+            th_g = np.tensordot(bio[c, :, :, :k], bjo[c, :k], axes=([2], [0]))
+            th_o = np.tensordot(Mi, Mj, axes=([2], [0]))
+            np.testing.assert_allclose(th_g, th_o, atol=1e-8 * max(1.0, np.abs(th_o).max()))
