@@ -114,8 +114,8 @@ class OracleMPS:
         """DMRG/MPS.py:423."""
         self.M[i] = np.tensordot(self.M[i], U, axes=([1], [1])).transpose(0, 2, 1)
 
-    def update_double(self, U, i):
-        """DMRG/MPS.py:445-455."""
+    def update_double(self, U, i, unitary=True):
+        """DMRG/MPS.py:445-457."""
         Bi, Bj = self.M[i], self.M[i + 1]
         xl, d, _ = Bi.shape
         xr = Bj.shape[2]
@@ -129,6 +129,8 @@ class OracleMPS:
         self.s[i + 1] = s
         self.M[i] = (thetaB.reshape(xl * d, d * xr) @ vh.conj().T).reshape(xl, d, k)
         self.M[i + 1] = vh.reshape(k, d, xr)
+        if not unitary:
+            self.ortho_left_site(i + 1)
 
     def half_sweep(self, U, parity):
         """Body of `_even_update` / `_odd_update`, DMRG/MPS.py:479-480, 487-488."""

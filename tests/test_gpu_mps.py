@@ -282,3 +282,30 @@ def test_host_bond_updater_matches_direct_call(lib):
         th_g = np.tensordot(Bio[c, :, :, :kk].numpy(), Bjo[c, :kk].numpy(), axes=([2], [0]))
         th_o = np.tensordot(o.M[0], o.M[1], axes=([2], [0]))
         np.testing.assert_allclose(th_g, th_o, atol=1e-10 * max(1.0, np.abs(th_o).max()))
+
+
+def test_non_unitary_update_branch(lib):
+    """`unitary=False` (imaginary-time gates, DMRG/MPS.py:424-425, 456-457 — present but untested in the reference):
+    a left-to-right sweep of exp(-tau H) gates followed by canon(), GPU vs oracle."""
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200.spin import sigma
+    L = 6
+    Z, X, I2 = sigma[3], sigma[1], np.eye(2)
+    Hb = -np.kron(Z, Z) - 0.5 * 1.1 * (np.kron(X, I2) + np.kron(I2, X))
+    G = la.expm(-0.2 * Hb).reshape(2, 2, 2, 2)
+    rs = np.random.RandomState(3)
+    chis = [1, 2, 4, 4, 4, 2, 1]
+    Ms = [rs.randn(chis[i], 2, chis[i + 1]) + 1j * rs.randn(chis[i], 2, chis[i + 1]) for i in range(L)]
+    s = MPS([m.copy() for m in Ms], 2, trun=8, err=1e-12)
+    o = OracleMPS([m.copy() for m in Ms], trun=8, err=1e-12)
+    s.canon(); o.canon()
+    for sweep in range(3):
+        for i in range(L - 1):
+            s.update_double(G, i, unitary=False)
+            o.update_double(G, i, unitary=False)
+        s.canon(); o.canon()
+    for b in range(L + 1):
+        np.testing.assert_allclose(np.asarray(s.s[b], dtype=float), o.s[b], rtol=1e-9, atol=1e-13)
+    e_gpu = sum(s.measure(i, Hb) for i in range(L - 1))
+    e_ora = sum(o.measure(i, Hb) for i in range(L - 1))
+    assert abs(e_gpu - e_ora) < 1e-10
