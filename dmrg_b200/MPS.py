@@ -383,44 +383,61 @@ class MPS:
         if not unitary:
             self.ortho_left_site(i + 1)
 
+    @staticmethod
+    def _bucket(v):
+        """Bond dimensions are padded up to a few size classes so that bonds of similar size share one launch
+        sequence (zero padding is exact: it only adds zero singular values, which `truncate` drops)."""
+        if v <= 4:
+            return v
+        step = 8 if v <= 64 else 32
+        return (v + step - 1) // step * step
+
     def _update_bonds(self, U_dev, bonds):
-        """Apply the same gate to disjoint bonds.  Bonds with identical shapes share one batched call."""
+        """Apply the same gate to disjoint bonds; bonds in the same padded size class share one batched call."""
         self._flush()
         lib = _lib.load()
-        t = _lib.torch()
         d = self.dim
         groups = {}
         for i in bonds:
-            key = (int(self.x[i]), int(self.x[i + 1]), int(self.x[i + 2]))
+            key = (self._bucket(int(self.x[i])), self._bucket(int(self.x[i + 1])), self._bucket(int(self.x[i + 2])))
             groups.setdefault(key, []).append(i)
         pending = []
-        for (xl, x, xr), idx in groups.items():
+        for (PL, PX, PR), idx in groups.items():
             nb = len(idx)
-            kcap = max(1, min(xl * d, d * xr, max(int(self.trun), 1)))
-            if nb == 1:
+            kcap = max(1, min(PL * d, d * PR, max(int(self.trun), 1)))
+            exact = all((int(self.x[i]), int(self.x[i + 1]), int(self.x[i + 2])) == (PL, PX, PR) for i in idx)
+            if nb == 1 and exact:
                 bi, bj = self._dev[idx[0]], self._dev[idx[0] + 1]
                 sl = self._schmidt(idx[0])
             else:
-                bi = t.stack([self._dev[i] for i in idx])
-                bj = t.stack([self._dev[i + 1] for i in idx])
-                sl = _lib.to_device(np.stack([np.asarray(self.s[i], dtype=float) * np.ones(xl) for i in idx]), np.float64)
-            bio = _lib.empty((nb, xl, d, kcap))
-            bjo = _lib.empty((nb, kcap, d, xr))
+                bi = _lib.zeros((nb, PL, d, PX))
+                bj = _lib.zeros((nb, PX, d, PR))
+                slh = np.zeros((nb, PL))
+                for b, i in enumerate(idx):
+                    xl, x, xr = int(self.x[i]), int(self.x[i + 1]), int(self.x[i + 2])
+                    bi[b, :xl, :, :x].copy_(self._dev[i])
+                    bj[b, :x, :, :xr].copy_(self._dev[i + 1])
+                    slh[b, :xl] = np.asarray(self.s[i], dtype=float) * np.ones(xl)
+                sl = _lib.to_device(slh, np.float64)
+            bio = _lib.empty((nb, PL, d, kcap))
+            bjo = _lib.empty((nb, kcap, d, PR))
             sro = _lib.empty((nb, kcap), "f64")
             rank = _lib.empty((nb,), "i32")
-            ws, wsn = _lib.workspace(lib.mpsb_tebd_two_site_workspace(nb, xl, x, xr, d))
-            _lib.check(lib.mpsb_tebd_two_site(nb, xl, x, xr, d, _lib.ptr(bi), xl * d * x, _lib.ptr(bj), x * d * xr,
-                                              _lib.ptr(sl), xl, _lib.ptr(U_dev), 0, int(self.trun), float(self.err), kcap,
-                                              _lib.ptr(bio), xl * d * kcap, _lib.ptr(bjo), kcap * d * xr, _lib.ptr(sro),
+            ws, wsn = _lib.workspace(lib.mpsb_tebd_two_site_workspace(nb, PL, PX, PR, d))
+            _lib.check(lib.mpsb_tebd_two_site(nb, PL, PX, PR, d, _lib.ptr(bi), PL * d * PX, _lib.ptr(bj), PX * d * PR,
+                                              _lib.ptr(sl), PL, _lib.ptr(U_dev), 0, int(self.trun), float(self.err), kcap,
+                                              _lib.ptr(bio), PL * d * kcap, _lib.ptr(bjo), kcap * d * PR, _lib.ptr(sro),
                                               kcap, _lib.ptr(rank), ws, wsn, _lib.stream_ptr()), "mpsb_tebd_two_site")
-            pending.append((idx, kcap, bio, bjo, sro, rank))
-        for idx, kcap, bio, bjo, sro, rank in pending:
+            pending.append((idx, kcap, bio, bjo, sro, rank, (PL, PR)))
+        for idx, kcap, bio, bjo, sro, rank, (PL, PR) in pending:
             ranks = _lib.to_host(rank)
             sr = _lib.to_host(sro)
             for b, i in enumerate(idx):
                 k = int(ranks[b])
-                self._dev[i] = bio[b] if k == kcap else bio[b, :, :, :k].contiguous()
-                self._dev[i + 1] = bjo[b] if k == kcap else bjo[b, :k].contiguous()
+                xl, xr = int(self.x[i]), int(self.x[i + 2])
+                whole = (k == kcap and xl == PL and xr == PR)
+                self._dev[i] = bio[b] if whole else bio[b, :xl, :, :k].contiguous()
+                self._dev[i + 1] = bjo[b] if whole else bjo[b, :k, :, :xr].contiguous()
                 self.xr[i] = k
                 self.Sr[i] = sr[b, :k].copy()
 
