@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <utility>
 #include "../../include/mpsb.h"
 #include "common.cuh"
 #include "mpsb_internal.h"
@@ -22,6 +24,18 @@ void prof_mark(int idx, cudaStream_t st) {
         g_prof.have_events = 1;
     }
     cudaEventRecord(g_prof.ev[idx], st);
+}
+
+int ensure_dynamic_smem(const void* func, size_t bytes) {
+    static thread_local std::map<std::pair<const void*, int>, size_t> granted;
+    int dev = 0;
+    MPSB_CHECK_CUDA(cudaGetDevice(&dev));
+    size_t& have = granted[std::make_pair(func, dev)];
+    if (bytes > have) {
+        MPSB_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return 0;
 }
 
 void set_error(const char* fmt, ...) {

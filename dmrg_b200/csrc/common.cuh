@@ -41,6 +41,10 @@ extern unsigned long long g_launch_count;
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Raises cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the CURRENT device when a launch needs more than
+// was granted so far (the attribute is per device, so the cache is keyed by (function, device)).  Returns 0 / 2.
+int ensure_dynamic_smem(const void* func, size_t bytes);
+
 // ---- device helpers --------------------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -1342,12 +1342,7 @@ int launch_round(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int co
                  int inner, double tol2, double eabs2, cudaStream_t st) {
     const int ltot_r = round_up(pl.ltot, 32);
     const size_t smem = (size_t)2 * B * ltot_r * sizeof(cplx);
-    static size_t configured = 0;
-    if (smem > configured) {
-        MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_round_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_round_kernel<B>), smem)) return rc;
     const int nblk = pl.n_pad / pl.bsz;
     dim3 grid(nblk / 2, count);
     jacobi_round_kernel<B><<<grid, 32 * B, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
@@ -1369,11 +1364,7 @@ int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int cou
                 double tol2, cudaStream_t st) {
     const int ltot_r = round_up(pl.ltot, 32);
     const size_t smem = gram_smem_bytes(ltot_r);
-    static size_t configured = 0;
-    if (smem > configured) {
-        MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_gram_kernel), smem)) return rc;
     const int nblk = pl.n_pad / 8;
     dim3 grid(nblk / 2, count);
     jacobi_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
@@ -1391,16 +1382,9 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
     if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
         const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
         const bool full = (ltot_r == 256 && pl.ldot == 256);
-        static size_t configured[2] = {0, 0};
-        if (smem > configured[full]) {
-            if (full)
-                MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel<true>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else
-                MPSB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel<false>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[full] = smem;
-        }
+        if (int rc = ensure_dynamic_smem(full ? reinterpret_cast<const void*>(jacobi_cross_kernel<true>)
+                                              : reinterpret_cast<const void*>(jacobi_cross_kernel<false>), smem))
+            return rc;
         const int nblk = pl.n_pad / 8;
         dim3 grid(nblk / 2, count);
         unsigned long long* pc = g_prof.enabled > 1 ? s.phase_clk : nullptr;
@@ -1491,22 +1475,12 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         // Very long rows (chi >= 1024 with carried columns) do not leave room for the reflector scratch; the
         // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
         if (qr_enabled && qr_blocked && smem_b <= 200 * 1024) {
-            static size_t configured_b = 0;
-            if (smem_b > configured_b) {
-                MPSB_CHECK_CUDA(cudaFuncSetAttribute(qr_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)smem_b));
-                configured_b = smem_b;
-            }
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_blocked_kernel), smem_b)) return rc;
             qr_blocked_kernel<<<pl.batch, QB_THREADS, smem_b, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, s.frob2);
             MPSB_COUNT_LAUNCH();
             MPSB_CHECK_CUDA(cudaGetLastError());
         } else if (qr_enabled && smem <= 220 * 1024) {
-            static size_t configured = 0;
-            if (smem > configured) {
-                MPSB_CHECK_CUDA(cudaFuncSetAttribute(qr_precond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)smem));
-                configured = smem;
-            }
+            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_precond_kernel), smem)) return rc;
             qr_precond_kernel<<<pl.batch, QR_THREADS, smem, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, G, CW,
                                                                  s.frob2);
             MPSB_COUNT_LAUNCH();
@@ -1573,11 +1547,8 @@ int svd_finalise(const SvdPlan& pl, const cplx* X, void* state, const SvdOutputs
     while (npow2 < pl.n_pad) npow2 <<= 1;
     const size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
     MPSB_REQUIRE(smem <= 200 * 1024, "svd_finalise: %d rows exceed the sort buffer", pl.n_pad);
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        MPSB_CHECK_CUDA(cudaFuncSetAttribute(finalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024)
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(finalise_kernel), smem)) return rc;
     finalise_kernel<<<pl.batch, FIN_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, pl.n, pl.n_pad, npow2,
                                                         pl.ldot, pl.ltot, pl.ld, out);
     MPSB_COUNT_LAUNCH();

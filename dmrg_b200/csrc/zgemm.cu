@@ -139,12 +139,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) zgemm_kernel(GemmArgs p) {
 
 template <bool TA, bool CA, bool TB, bool CB>
 int launch(const GemmArgs& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        MPSB_CHECK_CUDA(cudaFuncSetAttribute(zgemm_kernel<TA, CA, TB, CB>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        configured = true;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(zgemm_kernel<TA, CA, TB, CB>), GEMM_SMEM)) return rc;
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batch1 * p.batch2);
     zgemm_kernel<TA, CA, TB, CB><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
     MPSB_COUNT_LAUNCH();
