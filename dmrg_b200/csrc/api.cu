@@ -59,7 +59,6 @@ struct Arena {
         used += al(bytes);
         return r;
     }
-    bool ok() const { return used <= size; }
 };
 
 struct TebdLayout {
