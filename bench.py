@@ -132,8 +132,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": f"TEBD two-site update, chi={CHI}, d={D}, complex128, saturated bonds",
-                       "chains_per_step": cb["cores"] * args.cpu_updates},
+            "config": {"workload": f"config 4 shard: {args.chains} independent chains/GPU, one saturated chi={CHI} d={D} complex128 "
+                                   f"two-site update each per step (trun={TRUN}, err={ERR})",
+                       "chains_per_gpu": args.chains, "chi": CHI, "d": D,
+                       "inputs": "right-isometric B tensors, Gaussian Schmidt spectrum, per-chain GUE gate dt=0.05",
+                       "sample_per_step": f"{cb['cores'] * args.cpu_updates} of the {args.chains} updates (bounded CPU sample)",
+                       "parallelism": "one worker process per host core"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "updates/s", "h2d_bytes_per_step": 0,
                                         "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
