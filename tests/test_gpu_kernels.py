@@ -250,3 +250,24 @@ def test_tebd_fuzz_shapes(lib):
             th_g = np.tensordot(bio[c, :, :, :k], bjo[c, :k], axes=([2], [0]))
             th_o = np.tensordot(Mi, Mj, axes=([2], [0]))
             np.testing.assert_allclose(th_g, th_o, atol=1e-8 * max(1.0, np.abs(th_o).max()))
+
+
+def test_large_local_dimension_d10(lib):
+    """Boson-chain sized local space (transmit/bhopping.py uses d = 10): two-site update and one-site gate at d = 10."""
+    rs = np.random.RandomState(10)
+    d, xl, x, xr, b = 10, 4, 6, 5, 2
+    Bi, Bj = crand(rs, b, xl, d, x), crand(rs, b, x, d, xr)
+    Sl = np.abs(rs.randn(b, xl)) + 0.1
+    h = crand(rs, d * d, d * d)
+    U = la.expm(-0.05j * (h + h.conj().T)).reshape([d] * 4)
+    trun, err = d, 1e-10                                  # BMPS uses trun = dim (transmit/bhopping.py:37)
+    kcap = max(1, min(trun, d * xl, d * xr))
+    bio, bjo, sro, rank = _tebd_call(lib, Bi, Bj, Sl, U, trun, err, kcap)
+    for c in range(b):
+        Mi, Mj, s = _oracle_update(Bi[c], Bj[c], Sl[c], U, trun, err)
+        k = len(s)
+        assert rank[c] == k
+        np.testing.assert_allclose(sro[c, :k], s, rtol=1e-10)
+        th_g = np.tensordot(bio[c, :, :, :k], bjo[c, :k], axes=([2], [0]))
+        th_o = np.tensordot(Mi, Mj, axes=([2], [0]))
+        np.testing.assert_allclose(th_g, th_o, atol=1e-9 * np.abs(th_o).max())
