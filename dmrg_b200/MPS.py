@@ -53,6 +53,7 @@ def _device_svd(a_dev, rows, cols, trun, err, want_u, normalise=1):
                                   _lib.ptr(vh), _lib.ptr(uh), _lib.ptr(s), _lib.ptr(sraw), _lib.ptr(rank), ws, wsn,
                                   _lib.stream_ptr()), "mpsb_svd_trunc")
     k = int(rank.item())
+    _lib.warn_if_unconverged("svd_truncate")
     u = None
     if want_u:
         u = _lib.conj_transpose(uh[:k]) if k else _lib.empty((rows, 0))
@@ -431,6 +432,7 @@ class MPS:
             pending.append((idx, kcap, bio, bjo, sro, rank, (PL, PR)))
         for idx, kcap, bio, bjo, sro, rank, (PL, PR) in pending:
             ranks = _lib.to_host(rank)
+            _lib.warn_if_unconverged("update_double")
             sr = _lib.to_host(sro)
             for b, i in enumerate(idx):
                 k = int(ranks[b])

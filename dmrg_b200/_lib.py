@@ -191,3 +191,10 @@ def conj_transpose(A, conj=True):
     if rows and cols:
         check(load().mpsb_transpose(rows, cols, ptr(A), cols, ptr(out), rows, int(conj), stream_ptr()), "mpsb_transpose")
     return out
+
+
+def warn_if_unconverged(where):
+    """The Jacobi iteration stops after MPSB_SVD_MAX_SWEEPS (40) sweeps; say so instead of staying silent."""
+    if int(load().mpsb_last_svd_sweeps()) >= int(os.environ.get("MPSB_SVD_MAX_SWEEPS", "40")):
+        import warnings
+        warnings.warn(f"{where}: Jacobi SVD stopped at the sweep limit; results may be less accurate than 1e-10")
