@@ -253,7 +253,7 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     cplx* C1 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-1 coefficients, row j
     cplx* C2 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-2 coefficients
     cplx* N2 = reinterpret_cast<cplx*>(p);                p += al(kk * sizeof(cplx));        // ||w_j||^2
-    cplx* c3 = reinterpret_cast<cplx*>(p);                p += al(kk * sizeof(cplx));
+    p += al(kk * sizeof(cplx));                                                              // (spare slot kept so workspace sizes stay stable)
     cplx* Yd = reinterpret_cast<cplx*>(p);                                                     // [keep][kk] Ritz coefficients
     cplx* th = static_cast<cplx*>(theta);
     std::vector<cplx> h1(kk * kk), h2(kk * kk), hn(kk), hc(kk * LANCZOS_KEEP);
