@@ -41,13 +41,23 @@ struct SvdState {           // device scratch, carved out of the caller's worksp
     unsigned long long* rot_total;      // [1] rotations applied over the whole call
     unsigned long long* sweep_total;    // [1] sum over problems of sweeps executed
     unsigned long long* phase_clk;      // [4] debug: summed SM clocks of load / rotate / store phases + CTA count
+    int* stamps;            // [batch][stamp_stride] change stamps of the row blocks, then "verified clean" stamps of
+    int stamp_stride;       //  the (round, slot) block pairs; 0 ints per problem when the plan does not use them
 };
+
+// A block pair that was found clean (no rotation needed) after the last change of either block is still clean:
+// its CTA can leave before loading a single row.  Stamps are launch numbers (monotone within one SVD call).
+__host__ __device__ inline int stamp_ints(int n_pad, int bsz) {
+    const int nblk = n_pad / bsz;
+    return (bsz == 8 && nblk >= 4 && nblk <= 128) ? nblk + (nblk - 1) * (nblk / 2) : 0;
+}
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-SvdState carve_state(void* state, int batch) {
+SvdState carve_state(void* state, int batch, int stamp_stride) {
     unsigned char* p = static_cast<unsigned char*>(state);
     SvdState s;
+    s.stamp_stride = stamp_stride;
     s.rot = reinterpret_cast<int*>(p);            p += align_up(sizeof(int) * batch, 256);
     s.done = reinterpret_cast<int*>(p);           p += align_up(sizeof(int) * batch, 256);
     s.frob2 = reinterpret_cast<double*>(p);       p += align_up(sizeof(double) * batch, 256);
@@ -55,6 +65,7 @@ SvdState carve_state(void* state, int batch) {
     s.rot_total = reinterpret_cast<unsigned long long*>(p + 64);
     s.sweep_total = reinterpret_cast<unsigned long long*>(p + 128);
     s.phase_clk = reinterpret_cast<unsigned long long*>(p + 192);
+    s.stamps = stamp_stride ? reinterpret_cast<int*>(p + 256) : nullptr;
     return s;
 }
 
@@ -829,7 +840,8 @@ template <bool FULL>
 __global__ void __launch_bounds__(CROSS_THREADS, MPSB_CROSS_MINBLOCKS)
 jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                     int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
-                    unsigned long long* __restrict__ phase_clk) {
+                    unsigned long long* __restrict__ phase_clk, int* __restrict__ stamps, int stamp_stride,
+                    int launch_id) {
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [8][ltot_r]
     __shared__ double nq[8], dqs[8], eqs[8];                  // true norm^2, scale d and d^2 of the rows of block J
@@ -841,6 +853,12 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int bI, bJ;
     rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
+    const int chk_idx = nblk + round * (nblk >> 1) + blockIdx.x;
+    if (stp) {                                               // verified clean since both blocks last changed
+        const int chk = stp[chk_idx];
+        if (chk > stp[bI] && chk > stp[bJ]) return;
+    }
     cplx* X = Xall + (size_t)mat * strideX;
     const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
 
@@ -933,9 +951,11 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
             atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
             atomicAdd(&phase_clk[3], 1ull);
         }
+        if (stp && tid == 0) stp[chk_idx] = launch_id;      // verified clean at this launch
         return;
     }
     if (lane == 0 && nrot > 0) atomicAdd(&rot[mat], nrot);
+    if (stp && tid == 0) { stp[bI] = launch_id; stp[bJ] = launch_id; }
     // fold the scales back: register rows on their way to global memory, J rows in shared memory
     if (r0.dirty) {
 #pragma unroll
@@ -1003,7 +1023,8 @@ __device__ __forceinline__ void jacobi_angle_fast(double a, double b, double cr,
 __global__ void __launch_bounds__(GRAM_THREADS, 3)
 jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                    int round, int inner_sweeps, int* __restrict__ rot, const int* __restrict__ done, double tol2,
-                   unsigned long long* __restrict__ phase_clk) {
+                   unsigned long long* __restrict__ phase_clk, int* __restrict__ stamps, int stamp_stride,
+                   int launch_id) {
     extern __shared__ __align__(128) unsigned char smraw[];
     GramSmem& sm = *reinterpret_cast<GramSmem*>(smraw);
     cplx* rows = reinterpret_cast<cplx*>(smraw + ((sizeof(GramSmem) + 127) / 128) * 128);   // [GR][pitch]
@@ -1016,6 +1037,12 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
     const int g = lane >> 2, t = lane & 3;
     int bI, bJ;
     rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
+    const int chk_idx = nblk + round * (nblk >> 1) + blockIdx.x;
+    if (stp) {                                               // verified clean since both blocks last changed
+        const int chk = stp[chk_idx];
+        if (chk > stp[bI] && chk > stp[bJ]) return;
+    }
     cplx* X = Xall + (size_t)mat * strideX;
     const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
 
@@ -1182,9 +1209,11 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
             atomicAdd(&phase_clk[1], (unsigned long long)(t_rotated - t_loaded));
             atomicAdd(&phase_clk[3], 1ull);
         }
+        if (stp && tid == 0) stp[chk_idx] = launch_id;
         return;
     }
     if (tid == 0) atomicAdd(&rot[mat], total_rot);
+    if (stp && tid == 0) { stp[bI] = launch_id; stp[bJ] = launch_id; }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -1361,7 +1390,7 @@ bool use_gram_kernel(const SvdPlan& pl) {
     return enabled && pl.bsz == 8 && gram_smem_bytes(round_up(pl.ltot, 32)) <= 220 * 1024;
 }
 int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int inner,
-                double tol2, cudaStream_t st) {
+                double tol2, int launch_id, cudaStream_t st) {
     const int ltot_r = round_up(pl.ltot, 32);
     const size_t smem = gram_smem_bytes(ltot_r);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_gram_kernel), smem)) return rc;
@@ -1369,14 +1398,16 @@ int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int cou
     dim3 grid(nblk / 2, count);
     jacobi_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
                                                         nblk, round, inner, s.rot, s.done, tol2,
-                                                        g_prof.enabled > 1 ? s.phase_clk : nullptr);
+                                                        g_prof.enabled > 1 ? s.phase_clk : nullptr,
+                                                        nblk == pl.n_pad / pl.bsz ? s.stamps : nullptr, s.stamp_stride,
+                                                        launch_id);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
-                     int inner, double tol2, double eabs2, cudaStream_t st) {
+                     int inner, double tol2, double eabs2, int launch_id, cudaStream_t st) {
     static const int cross_enabled = env_int("MPSB_JACOBI_CROSS", 1);
     const int ltot_r = round_up(pl.ltot, 32);
     if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
@@ -1391,16 +1422,16 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
         if (full)
             jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
                                                                          pl.ldot, ltot_r, nblk, round, s.rot, s.done,
-                                                                         tol2, pc);
+                                                                         tol2, pc, s.stamps, s.stamp_stride, launch_id);
         else
             jacobi_cross_kernel<false><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
                                                                           pl.ldot, ltot_r, nblk, round, s.rot, s.done,
-                                                                          tol2, pc);
+                                                                          tol2, pc, s.stamps, s.stamp_stride, launch_id);
         MPSB_COUNT_LAUNCH();
         MPSB_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
-    if (use_gram_kernel(pl)) return launch_gram(pl, X, s, mat0, count, round, inner, tol2, st);
+    if (use_gram_kernel(pl)) return launch_gram(pl, X, s, mat0, count, round, inner, tol2, launch_id, st);
     switch (pl.bsz) {
         case 1: return launch_round<1>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
         case 2: return launch_round<2>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
@@ -1448,12 +1479,14 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
 }
 
 size_t svd_state_bytes(const SvdPlan& plan) {
-    return align_up(sizeof(int) * plan.batch, 256) * 2 + align_up(sizeof(double) * plan.batch, 256) + 256;
+    return align_up(sizeof(int) * plan.batch, 256) * 2 + align_up(sizeof(double) * plan.batch, 256) + 256 +
+           align_up(sizeof(int) * (size_t)plan.batch * stamp_ints(plan.n_pad, plan.bsz), 256);
 }
 
 int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, int* sweeps_out) {
-    const SvdState s = carve_state(state, pl.batch);
+    const SvdState s = carve_state(state, pl.batch, stamp_ints(pl.n_pad, pl.bsz));
     const long long strideX = (long long)pl.n_pad * pl.ld;
+    if (s.stamps) MPSB_CHECK_CUDA(cudaMemsetAsync(s.stamps, 0, sizeof(int) * (size_t)pl.batch * s.stamp_stride, st));
     sweep_begin_kernel<<<(pl.batch + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, s.rot_total, s.sweep_total,
                                                                pl.batch, 1);
     MPSB_COUNT_LAUNCH();
@@ -1498,12 +1531,13 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     const int rounds = nblk - 1;
     const int inner = (nblk == 2) ? pl.max_sweeps : 1;
     int max_sweeps_seen = 0;
+    int launch_id = 1;
     for (int mat0 = 0; mat0 < pl.batch; mat0 += pl.chunk) {
         const int count = std::min(pl.chunk, pl.batch - mat0);
         int sweep = 0;
         for (; sweep < pl.max_sweeps; ++sweep) {
             for (int r = 0; r < rounds; ++r) {
-                int rc = launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, st);
+                int rc = launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
                 if (rc) return rc;
             }
             MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
