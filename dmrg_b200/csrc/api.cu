@@ -247,6 +247,13 @@ int mpsb_one_site(int batch, int chil, int chir, int d, const void* M, long long
                     static_cast<cplx*>(M_out), sMo, static_cast<cudaStream_t>(stream));
 }
 
+int mpsb_mpo_site(int batch, int chil, int chir, int d, int wl, int wr, const void* M, long long sM, const void* W,
+                  long long sW, void* out, long long sOut, void* stream) {
+    MPSB_REQUIRE(M && W && out && M != out, "mpo_site: null or aliased buffers");
+    return mpo_site(batch, chil, chir, d, wl, wr, static_cast<const cplx*>(M), sM, static_cast<const cplx*>(W), sW,
+                    static_cast<cplx*>(out), sOut, static_cast<cudaStream_t>(stream));
+}
+
 // ---- canon: gauge steps ------------------------------------------------------------------------------------
 // Left step: work matrix X = [ (Sl M_i)^H | M_next ], rows = right bond r (chir of them).  After the row
 // orthogonalisation  X = [ diag(s) U^H | Vh M_next ]  (DMRG/MPS.py:257-264).

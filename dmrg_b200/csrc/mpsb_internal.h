@@ -81,6 +81,9 @@ int gate_scale(int batch, int chil, int chir, int d, const cplx* theta0, long lo
 int one_site(int batch, int chil, int chir, int d, const cplx* M, long long sM, const cplx* U, long long sU,
              cplx* Mo, long long sMo, cudaStream_t st);
 
+int mpo_site(int batch, int chil, int chir, int d, int wl, int wr, const cplx* M, long long sM, const cplx* W,
+             long long sW, cplx* out, long long sOut, cudaStream_t st);
+
 // ---- layout helpers (aux.cu) ---------------------------------------------------------------------
 // Describes how an (i, j) element of a logical matrix is fetched from memory:
 //   value = conj?( src[i * rs + j * cs] ) * (scale ? scale[(j / sdiv) % smod] : 1)

@@ -69,7 +69,50 @@ one_site_kernel(int chil, int chir, int d, const cplx* __restrict__ M, long long
     }
 }
 
+// Site tensor times MPO tensor (BMPS.update_MPO, transmit/bhopping.py:94-104):
+//   out[(i,l), o, (k,m)] = sum_j M[i,j,k] W[l,m,j,o].
+// One thread per output element, (k,m) fastest so stores coalesce; M[i,:,k] is shared by the wl*wr*d threads
+// around it and W is small, so both operands come from L1/L2.  HBM-bound on the store (16 B per element).
+__global__ void __launch_bounds__(256)
+mpo_site_kernel(int chil, int chir, int d, int wl, int wr, const cplx* __restrict__ M, long long sM,
+                const cplx* __restrict__ W, long long sW, cplx* __restrict__ out, long long sOut) {
+    const int b = blockIdx.y;
+    const long long total = (long long)chil * wl * d * chir * wr;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int m = (int)(e % wr);
+    long long r = e / wr;
+    const int k = (int)(r % chir); r /= chir;
+    const int o = (int)(r % d); r /= d;
+    const int l = (int)(r % wl);
+    const int i = (int)(r / wl);
+    const cplx* src = M + (size_t)b * sM + (size_t)i * d * chir + k;
+    const cplx* w = W + (size_t)b * sW + ((size_t)(l * wr + m) * d) * d + o;
+    double re = 0.0, im = 0.0;
+    for (int j = 0; j < d; ++j) {
+        const cplx x = src[(size_t)j * chir];
+        const cplx g = __ldg(w + (size_t)j * d);
+        re = fma(g.x, x.x, fma(-g.y, x.y, re));
+        im = fma(g.x, x.y, fma(g.y, x.x, im));
+    }
+    out[(size_t)b * sOut + e] = make_double2(re, im);
+}
+
 }  // namespace
+
+int mpo_site(int batch, int chil, int chir, int d, int wl, int wr, const cplx* M, long long sM, const cplx* W,
+             long long sW, cplx* out, long long sOut, cudaStream_t st) {
+    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && wl >= 1 && wr >= 1, "mpo_site: bad dims");
+    MPSB_REQUIRE(batch <= 65535, "mpo_site: batch %d exceeds grid.y", batch);
+    if (batch == 0) return 0;
+    const long long total = (long long)chil * wl * d * chir * wr;
+    MPSB_REQUIRE((total + 255) / 256 <= 2147483647LL, "mpo_site: output too large for one launch");
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    mpo_site_kernel<<<grid, 256, 0, st>>>(chil, chir, d, wl, wr, M, sM, W, sW, out, sOut);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int gate_scale(int batch, int chil, int chir, int d, const cplx* theta0, long long s_theta0, const cplx* U,
                long long s_U, const double* Sl, long long s_Sl, cplx* thetaB, long long s_thetaB, cplx* X,

@@ -74,6 +74,14 @@ int mpsb_tebd_two_site(int batch, int chil, int chi, int chir, int d, const void
 int mpsb_one_site(int batch, int chil, int chir, int d, const void* M, long long sM, const void* U, long long sU,
                   void* M_out, long long sMo, void* stream);
 
+/* Matrix product operator applied to one site tensor (BMPS.update_MPO, transmit/bhopping.py:94-104, the einsum
+ * "ijk,lmjo->ilokm" followed by the reshape to (chil*wl, d, chir*wr)):
+ *     out[(i,l), o, (k,m)] = sum_j M[i,j,k] W[l,m,j,o]
+ * M [chil][d][chir], W [wl][wr][d][d] (left MPO bond, right MPO bond, input leg, output leg), out
+ * [chil*wl][d][chir*wr]; strides in elements between batch items (sW = 0 shares one W).  out must not alias M. */
+int mpsb_mpo_site(int batch, int chil, int chir, int d, int wl, int wr, const void* M, long long sM, const void* W,
+                  long long sW, void* out, long long sOut, void* stream);
+
 /* Gauge steps of MPS.canon (DMRG/MPS.py:246-284).  Left step on site i:
  *     m = (Sl * M_i) as (chil*d) x chir;  u, s, vh = svd_truncate(m);  M_i <- u;  Sr <- s;  M_next <- vh . M_next
  * Right step on site i:

@@ -289,15 +289,87 @@ def case_idmrg():
     np.savez(os.path.join(GOLD, "idmrg_energies.npz"), **out)
 
 
+def import_reference_transmit():
+    """`transmit/` imports three things this image no longer has (`scipy.misc.imresize`, `matplotlib`, and
+    `joblib.Memory(cachedir=...)`); none is used by `BMPS`.  Stub exactly those and import the package unmodified."""
+    import types
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Memory:
+        def __init__(self, *a, **k):
+            pass
+
+        def cache(self, f):
+            return f
+    stub("joblib", Memory=_Memory)
+    stub("matplotlib")
+    stub("matplotlib.pyplot")
+    stub("matplotlib.colors", Normalize=object)
+    scipy.misc = stub("scipy.misc", imresize=None, imsave=None)
+    from transmit import bhopping, cat
+    return bhopping, cat
+
+
+BMPS_CASES = {
+    "d6": dict(dim=6, l=6, para={"omega0": 0.3, "g": 1.0, "u": 0.7, "h": 0.4, "K": 0.5},
+               pack={"dk": 0.5, "center": 3, "k_c": -np.pi / 2, "trun": True, "alpha": 1.2}, t=0.3, n=4, tail=True),
+    "d10": dict(dim=10, l=5, para={"omega0": 0, "g": 1.0, "u": 0, "h": 0, "K": 1.0},
+                pack={"dk": 0.5, "center": 2, "k_c": -np.pi / 2, "trun": True, "alpha": 1.5}, t=0.4, n=5, tail=True),
+    "d5_notail": dict(dim=5, l=7, para={"omega0": 0.2, "g": 0.8, "u": 0.5, "h": 0.6, "K": 0.0},
+                      pack={"dk": 0.4, "center": 3, "k_c": np.pi / 3, "trun": False, "alpha": 0.9}, t=0.5, n=3,
+                      tail=False),
+}
+
+
+def case_bmps():
+    """the reference's d >> 2 caller (transmit/bhopping.py), MPO application included."""
+    bh, cat = import_reference_transmit()
+    from oracle.bmps_oracle import OracleBMPS, coherent
+    for al in (0.0, 0.4 - 0.3j, 1.7j):
+        close(cat.coherent(al, 12), coherent(al, 12), 1e-15, "coherent state")
+    out = {}
+    for name, c in BMPS_CASES.items():
+        ref = quiet(bh.BMPS, c["dim"], c["l"], c["para"], c["pack"])
+        orc = OracleBMPS(c["dim"], c["l"], c["para"], c["pack"])
+        occ0 = np.array([ref.measure(i, ref.N) for i in range(ref.L)])
+        close(occ0, orc.occupations(), 1e-13, name + " initial occupations")
+        quiet(ref.evolve, c["t"], c["n"], c["tail"])
+        orc.evolve(c["t"], c["n"], c["tail"])
+        x_raw = np.array(ref.x)
+        assert list(ref.x) == list(orc.x), name + ": bond dimensions after evolve"
+        ref.canon()
+        orc.canon()
+        assert list(ref.x) == list(orc.x), name + ": bond dimensions after canon"
+        occ = np.array([ref.measure(i, ref.N) for i in range(ref.L)])
+        close(occ, orc.occupations(), 1e-12, name + " occupations")
+        for b in range(ref.L + 1):
+            close(ref.s[b], orc.s[b], 1e-12, name + " Schmidt values bond %d" % b)
+        nn = np.kron(ref.N, ref.N)
+        corr = np.array([ref.measure(i, nn) for i in range(ref.l - 1)])
+        close(corr, [orc.measure(i, nn) for i in range(ref.l - 1)], 1e-12, name + " <N N>")
+        wig = quiet(ref.wigner, 0.3)
+        out[name + "_occ0"], out[name + "_occ"], out[name + "_nn"] = occ0, occ, corr
+        out[name + "_x_raw"], out[name + "_x"] = x_raw, np.array(ref.x)
+        out[name + "_c_n"], out[name + "_wigner"] = np.array(ref.c_n), wig
+        for b in range(ref.L + 1):
+            out[name + "_s%d" % b] = np.asarray(ref.s[b], dtype=float)
+        print("BMPS %s: oracle == reference; bonds %s, <N> = %s" % (name, [int(v) for v in ref.x], np.round(occ, 5)))
+    np.savez(os.path.join(GOLD, "bmps.npz"), cases=json.dumps({k: {**v, "pack": {**v["pack"]}} for k, v in BMPS_CASES.items()}),
+             **out)
+
+
 if __name__ == "__main__":
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    case_canon_testcanon()
-    case_two_body()
-    case_update_double()
-    case_aklt()
-    case_tfim_quench()
-    case_chi128_bond()
-    case_idmrg()
+    cases = {"canon": case_canon_testcanon, "two_body": case_two_body, "update_double": case_update_double,
+             "aklt": case_aklt, "tfim": case_tfim_quench, "chi128": case_chi128_bond, "idmrg": case_idmrg,
+             "bmps": case_bmps}
+    for name in (sys.argv[1:] or list(cases)):          # `python oracle/validate_against_reference.py bmps` runs one
+        cases[name]()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump({"generator": "oracle/validate_against_reference.py", "reference": "/root/reference (peijunz-archive/DMRG, unmodified)",
                    "numpy": np.__version__, "scipy": scipy.__version__, "python": sys.version.split()[0]}, f, indent=1)

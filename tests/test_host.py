@@ -139,3 +139,33 @@ def test_no_cpu_fallback_without_gpu(lib):
     from dmrg_b200.MPS import MPS
     with pytest.raises(lib.MpsbError):
         MPS((1, 2, 1))
+
+
+# ---- transmit/cat helpers (transmit/cat_test.py ported) ---------------------------------------------------
+def test_cat_exp_an():                                   # transmit/cat_test.py:6-18
+    import scipy.linalg as la
+    from dmrg_b200.transmit import cat
+    for n in [1, 2, 4, 8]:
+        for r in np.linspace(0, 1, 7):
+            for theta in np.linspace(0, 2 * np.pi, 13):
+                alpha = r * np.exp(1j * theta)
+                np.testing.assert_allclose(cat.exp_an(alpha, n), la.expm(alpha * cat.a_n(n)), atol=1e-13)
+                np.testing.assert_allclose(cat.exp_ap(alpha, n), la.expm(alpha * cat.a_p(n)), atol=1e-13)
+
+
+def test_cat_coherent_wigner_displace():                 # transmit/cat_test.py:20-47
+    from dmrg_b200.transmit import cat
+    s1 = cat.coherent(1, 20)
+    s30 = cat.coherent(1, 30)
+    for r in np.linspace(0, 2, 11):
+        for theta in np.linspace(0, 2 * np.pi, 7):
+            z = r * np.exp(1j * theta)
+            assert abs(cat.husimi(z, s1) - np.exp(-abs(z - 1) ** 2)) < 1e-6, "Q function test fail"
+            assert abs(cat.wigner(z, s30) - np.exp(-2 * abs(z - 1) ** 2)) < 1e-6, "Wigner function test fail"
+            s2 = cat.displace(z - 1, 30) @ s30
+            assert abs(cat.husimi(z, s2) - 1) < 1e-6, "Displacement function test fail"
+    rho = np.outer(s1, s1.conj())
+    W = cat.wigner_matrix(0.3 - 0.2j, 20)
+    assert abs(cat.expect(W, rho) - cat.expect(W, s1)) < 1e-12
+    assert cat.fock(3, 7)[3] == 1 and cat.fock(3, 7).sum() == 1
+    np.testing.assert_allclose(abs(cat.kerr(0.3, 2, 10)), abs(cat.coherent(2, 10)))

@@ -118,3 +118,43 @@ def test_idmrg_tfim_energies_golden(golden):
         np.testing.assert_allclose(e, g[f"tfim_e_trunc{trunc}"][:steps], rtol=2e-10)
     assert abs(g["tfim_e_trunc10"][0] + 1.1180339887499) < 1e-12
     assert abs(g["tfim_e_trunc10"][39] + 1.2687174555821) < 1e-9
+
+
+def _bmps_cases(golden):
+    import json
+    g = golden("bmps.npz")
+    return g, json.loads(str(g["cases"]))
+
+
+def test_bmps_oracle_golden(golden):
+    """the oracle's bosonic hopping chain against the reference's `transmit/bhopping.py` run."""
+    from oracle.bmps_oracle import OracleBMPS
+    g, cases = _bmps_cases(golden)
+    for name, c in cases.items():
+        o = OracleBMPS(c["dim"], c["l"], c["para"], c["pack"])
+        np.testing.assert_allclose(o.occupations(), g[name + "_occ0"], atol=1e-13)
+        o.evolve(c["t"], c["n"], c["tail"])
+        assert list(o.x) == list(g[name + "_x_raw"])
+        o.canon()
+        assert list(o.x) == list(g[name + "_x"])
+        np.testing.assert_allclose(o.occupations(), g[name + "_occ"], atol=1e-12)
+        for b in range(o.L + 1):
+            np.testing.assert_allclose(o.s[b], g[name + "_s%d" % b], atol=1e-12)
+        nn = np.kron(o.N, o.N)
+        np.testing.assert_allclose([o.measure(i, nn) for i in range(o.l - 1)], g[name + "_nn"], atol=1e-12)
+        np.testing.assert_allclose(o.c_n, g[name + "_c_n"], atol=1e-13)
+
+
+def test_bmps_free_hopping_keeps_coherent_product():
+    """Known answer independent of the reference: under pure hopping a product of coherent states stays one, with
+    amplitudes c(t) = exp(-i g A t) c(0) (A = open-chain adjacency) -> <N_i> = |c_i(t)|^2 up to Fock-cutoff error."""
+    from oracle.bmps_oracle import OracleBMPS
+    para = {"omega0": 0, "g": 1.0, "u": 0, "h": 0, "K": 0}
+    pack = {"dk": 0.6, "center": 3, "k_c": np.pi / 2, "trun": False, "alpha": 0.6}
+    o = OracleBMPS(9, 6, para, pack)
+    c0 = o.c_n.copy()
+    o.evolve(0.4, 20)
+    o.canon()
+    A = np.diag(np.ones(5), 1) + np.diag(np.ones(5), -1)
+    ct = la.expm(-1j * 0.4 * A) @ c0
+    np.testing.assert_allclose(o.occupations()[:6], abs(ct) ** 2, atol=2e-5)     # Trotter error O(dt^2) + cutoff
