@@ -402,6 +402,12 @@ class MPS:
         for i in bonds:
             key = (self._bucket(int(self.x[i])), self._bucket(int(self.x[i + 1])), self._bucket(int(self.x[i + 2])))
             groups.setdefault(key, []).append(i)
+        if len(groups) > 1:
+            # Small bonds are bound by launch latency, not by work: one call padded to the largest size class beats
+            # one call per class (a d = 10 chain with bonds 1,5,10,...,10,8,5,4,3,1 has five classes per half sweep).
+            top = tuple(max(int(self.x[i + j]) for i in bonds) for j in range(3))
+            if top[0] * d <= 128 and d * top[2] <= 128:
+                groups = {top: list(bonds)}
         pending = []
         for (PL, PX, PR), idx in groups.items():
             nb = len(idx)

@@ -1232,6 +1232,107 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
     }
 }
 
+// ---- resident iteration: one CTA keeps the whole work matrix in shared memory ----------------------------
+// For matrices up to ~220 KB (100 x 100 with pitch 128, 64 x 64 with carried columns, ...) the multi-launch
+// iteration above is bound by launch latency and the per-sweep convergence poll: ~15 launches per sweep for a few
+// microseconds of work.  Here a single launch runs every sweep of a problem: the matrix comes in by TMA bulk copies,
+// one warp rotates one row pair per step of the round-robin tournament over all n_pad rows (inner products by warp
+// shuffles, both rows in registers, NJ = row length / 32 columns per lane), the CTA synchronises between steps and
+// stops after the first sweep that applied no rotation.
+template <int NJ>
+__device__ __forceinline__ int rotate_rows(cplx* __restrict__ P, cplx* __restrict__ Q, int ldot, double tol2, int lane) {
+    cplx x[NJ], y[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { x[j] = P[lane + 32 * j]; y[j] = Q[lane + 32 * j]; }     // pitch padding is zero
+    double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (lane + 32 * j < ldot) {
+            a = fma(x[j].x, x[j].x, fma(x[j].y, x[j].y, a));
+            b = fma(y[j].x, y[j].x, fma(y[j].y, y[j].y, b));
+            cr = fma(x[j].x, y[j].x, fma(x[j].y, y[j].y, cr));
+            ci = fma(x[j].y, y[j].x, fma(-x[j].x, y[j].y, ci));
+        }
+    }
+    a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
+    const double ac2 = cr * cr + ci * ci;
+    if (!(ac2 > tol2 * a * b)) return 0;
+    double cs, gr, gi;
+    jacobi_angle(a, b, cr, ci, ac2, cs, gr, gi);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        cplx xn, yn;
+        xn.x = fma(cs, x[j].x, fma(gi, y[j].y, -gr * y[j].x));
+        xn.y = fma(cs, x[j].y, -fma(gr, y[j].y, gi * y[j].x));
+        yn.x = fma(cs, y[j].x, fma(gr, x[j].x, gi * x[j].y));
+        yn.y = fma(cs, y[j].y, fma(gr, x[j].y, -gi * x[j].x));
+        P[lane + 32 * j] = xn;
+        Q[lane + 32 * j] = yn;
+    }
+    return 1;
+}
+
+template <int NJ>      // 1..8: columns per lane; 0: rows of any length, streamed from shared memory
+__global__ void __launch_bounds__((NJ >= 1 && NJ <= 4) ? 1024 : 512, 1)
+jacobi_resident_kernel(cplx* __restrict__ Xall, long long strideX, int n_pad, int ld, int ldot, int max_sweeps,
+                       double tol2, unsigned long long* __restrict__ rot_total,
+                       unsigned long long* __restrict__ sweep_total, int* __restrict__ max_sweeps_seen) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    cplx* rows = reinterpret_cast<cplx*>(smraw);            // [n_pad][ld]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned long long s_rot;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    cplx* X = Xall + (size_t)blockIdx.x * strideX;
+    const uint32_t rowbytes = (uint32_t)ld * sizeof(cplx);
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        s_rot = 0ull;
+    }
+    __syncthreads();
+    if (w == 0) {
+        if (lane == 0) mbar_expect_tx(&bar, rowbytes * (uint32_t)n_pad);
+        __syncwarp();
+        for (int r = lane; r < n_pad; r += 32) bulk_g2s(rows + (size_t)r * ld, X + (size_t)r * ld, rowbytes, &bar);
+    }
+    if (!mbar_wait(&bar, 0)) __trap();
+
+    const int half = n_pad >> 1, steps = n_pad - 1;
+    int sweeps = 0;
+    unsigned long long my_rot = 0ull;
+    while (sweeps < max_sweeps) {
+        int nrot = 0;
+        for (int s = 0; s < steps; ++s) {
+            for (int slot = w; slot < half; slot += nw) {
+                int p, q;
+                rr_pair(n_pad, s, slot, p, q);
+                cplx* P = rows + (size_t)p * ld;
+                cplx* Q = rows + (size_t)q * ld;
+                if (NJ > 0) nrot += rotate_rows<(NJ > 0 ? NJ : 1)>(P, Q, ldot, tol2, lane);
+                else nrot += rotate_pair(P, Q, ldot, ld, 0.0, tol2, 0.0, lane);
+            }
+            __syncthreads();
+        }
+        ++sweeps;
+        my_rot += (unsigned long long)nrot;
+        if (!__syncthreads_or(nrot > 0)) break;
+    }
+    if (lane == 0 && my_rot) atomicAdd(&s_rot, my_rot);
+    fence_async_smem();
+    __syncthreads();
+    if (w == 0) {
+        for (int r = lane; r < n_pad; r += 32) bulk_s2g(X + (size_t)r * ld, rows + (size_t)r * ld, rowbytes);
+        bulk_commit();
+        bulk_wait_all();
+    }
+    if (tid == 0) {
+        atomicAdd(rot_total, s_rot);
+        atomicAdd(sweep_total, (unsigned long long)sweeps);
+        atomicMax(max_sweeps_seen, sweeps);
+    }
+}
+
 __global__ void sweep_begin_kernel(int* rot, int* done, int* n_active, unsigned long long* rot_total,
                                    unsigned long long* sweep_total, int batch, int reset_done) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1443,6 +1544,36 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
     return 1;
 }
 
+size_t resident_smem_bytes(int n_pad, int ld) { return (size_t)n_pad * ld * sizeof(cplx); }
+
+template <int NJ>
+int launch_resident_t(const SvdPlan& pl, cplx* X, const SvdState& s, double tol2, cudaStream_t st) {
+    const size_t smem = resident_smem_bytes(pl.n_pad, pl.ld);
+    const void* fn = reinterpret_cast<const void*>(jacobi_resident_kernel<NJ>);
+    if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
+    const int cap = (NJ >= 1 && NJ <= 4) ? 32 : 16;
+    const int nw = std::max(1, std::min(cap, pl.n_pad / 2));
+    jacobi_resident_kernel<NJ><<<pl.batch, 32 * nw, smem, st>>>(X, (long long)pl.n_pad * pl.ld, pl.n_pad, pl.ld, pl.ldot,
+                                                               pl.max_sweeps, tol2, s.rot_total, s.sweep_total,
+                                                               s.n_active);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_resident(const SvdPlan& pl, cplx* X, const SvdState& s, double tol2, cudaStream_t st) {
+    switch (pl.ld <= 256 ? pl.ld / 32 : 0) {
+        case 1: return launch_resident_t<1>(pl, X, s, tol2, st);
+        case 2: return launch_resident_t<2>(pl, X, s, tol2, st);
+        case 3: return launch_resident_t<3>(pl, X, s, tol2, st);
+        case 4: return launch_resident_t<4>(pl, X, s, tol2, st);
+        case 5: return launch_resident_t<5>(pl, X, s, tol2, st);
+        case 6: return launch_resident_t<6>(pl, X, s, tol2, st);
+        case 7: return launch_resident_t<7>(pl, X, s, tol2, st);
+        case 8: return launch_resident_t<8>(pl, X, s, tol2, st);
+    }
+    return launch_resident_t<0>(pl, X, s, tol2, st);
+}
+
 }  // namespace
 
 int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
@@ -1465,6 +1596,19 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
     while (b * 2 <= bcap && 2 * (b * 2) <= rows_fit && b < (n + 1) / 2) b *= 2;
     p.bsz = b;
     p.n_pad = round_up(n, 2 * b);
+    // Tiny problems in small batches: one launch per SVD with the matrix resident in one CTA's shared memory.  One SM
+    // has 1/148 of the FP64 throughput, so this only wins while the multi-launch path is bound by launch latency
+    // (measured cross-over near 64 x 64: tools/svd_small_probe.py).
+    static const int resident_max_batch = env_int("MPSB_SVD_RESIDENT_BATCH", 296);
+    static const int resident_max_work = env_int("MPSB_SVD_RESIDENT_WORK", 160000);
+    const int n_even = round_up(n, 2);
+    p.resident = 0;
+    if (batch <= resident_max_batch && (long long)n_even * n_even * p.ld <= resident_max_work &&
+        resident_smem_bytes(n_even, p.ld) <= 216 * 1024) {
+        p.resident = 1;
+        p.bsz = 1;
+        p.n_pad = n_even;
+    }
     const size_t matbytes = (size_t)p.n_pad * rowbytes;
     const size_t l2_budget = (size_t)env_int("MPSB_SVD_L2_MB", 1 << 20) * 1024 * 1024;
     int chunk = (int)std::max<size_t>(1, l2_budget / matbytes);
@@ -1507,7 +1651,10 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
                               pl.ld + 64;
         // Very long rows (chi >= 1024 with carried columns) do not leave room for the reflector scratch; the
         // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
-        if (qr_enabled && qr_blocked && smem_b <= 200 * 1024) {
+        // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
+        // to itself the 1024-thread fused kernel has half the latency (tools/tebd_small_probe.py).
+        const bool latency_mode = pl.batch <= 148 && smem <= 220 * 1024;
+        if (qr_enabled && qr_blocked && !latency_mode && smem_b <= 200 * 1024) {
             if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_blocked_kernel), smem_b)) return rc;
             qr_blocked_kernel<<<pl.batch, QB_THREADS, smem_b, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, s.frob2);
             MPSB_COUNT_LAUNCH();
@@ -1532,7 +1679,12 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     const int inner = (nblk == 2) ? pl.max_sweeps : 1;
     int max_sweeps_seen = 0;
     int launch_id = 1;
-    for (int mat0 = 0; mat0 < pl.batch; mat0 += pl.chunk) {
+    if (pl.resident) {
+        if (int rc = launch_resident(pl, X, s, tol2, st)) return rc;
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(&max_sweeps_seen, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int mat0 = 0; mat0 < pl.batch && !pl.resident; mat0 += pl.chunk) {
         const int count = std::min(pl.chunk, pl.batch - mat0);
         int sweep = 0;
         for (; sweep < pl.max_sweeps; ++sweep) {

@@ -51,6 +51,7 @@ struct SvdPlan {
     int bsz;         // rows per Jacobi block (power of two, 1..16)
     int chunk;       // problems swept together (L2 residency)
     int max_sweeps;
+    int resident;    // 1: the whole work matrix of a problem lives in one CTA's shared memory (single launch)
 };
 int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan);
 size_t svd_state_bytes(const SvdPlan& plan);   // per-call scratch besides X (flags, counters, order)
