@@ -24,6 +24,7 @@ void prof_mark(int idx, cudaStream_t st) {
         g_prof.have_events = 1;
     }
     cudaEventRecord(g_prof.ev[idx], st);
+    g_prof.recorded |= 1u << idx;
 }
 
 int ensure_dynamic_smem(const void* func, size_t bytes) {
@@ -104,12 +105,19 @@ const char* mpsb_last_error(void) { return g_error; }
 unsigned long long mpsb_launch_count(void) { return g_launch_count; }
 int mpsb_last_svd_sweeps(void) { return g_last_sweeps; }
 
-void mpsb_profile_enable(int on) { g_prof.enabled = on; }
+void mpsb_profile_enable(int on) {
+    g_prof.enabled = on;
+    g_prof.recorded = 0u;
+}
 int mpsb_profile_read(double* phase_ms, unsigned long long* rotations, unsigned long long* problem_sweeps) {
     MPSB_REQUIRE(g_prof.enabled && g_prof.have_events, "profile_read: profiling was not enabled for the last call");
-    MPSB_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[6]));
+    // Calls other than the two-site update only pass some of the marks (an SVD alone: 3 and 4); phases without both
+    // ends read as -1.
     for (int i = 0; i < 6; ++i) {
+        phase_ms[i] = -1.0;
+        if ((g_prof.recorded >> i & 3u) != 3u) continue;
         float ms = 0.f;
+        MPSB_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[i + 1]));
         MPSB_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
         phase_ms[i] = ms;
     }

@@ -120,6 +120,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 }
+// all committed bulk stores have finished READING their shared-memory source (the buffers may be refilled)
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
 // make generic-proxy smem writes visible to the async proxy (before bulk_s2g)
 __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

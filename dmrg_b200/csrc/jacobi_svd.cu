@@ -49,7 +49,7 @@ struct SvdState {           // device scratch, carved out of the caller's worksp
 // its CTA can leave before loading a single row.  Stamps are launch numbers (monotone within one SVD call).
 __host__ __device__ inline int stamp_ints(int n_pad, int bsz) {
     const int nblk = n_pad / bsz;
-    return (bsz == 8 && nblk >= 4 && nblk <= 128) ? nblk + (nblk - 1) * (nblk / 2) : 0;
+    return (bsz == 8 && nblk >= 4 && nblk <= 512) ? nblk + (nblk - 1) * (nblk / 2) : 0;
 }
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -275,6 +275,239 @@ qr_precond_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
                 pi *= tau_prev;
 #pragma unroll 8
                 for (int i = kprev + cg; i < n; i += G) {
+                    const cplx vi = vprev[i];
+                    cplx x = X[(size_t)i * ld + j];
+                    x.x -= vi.x * pr - vi.y * pi;
+                    x.y -= vi.x * pi + vi.y * pr;
+                    X[(size_t)i * ld + j] = x;
+                }
+            }
+        }
+    }
+}
+
+// ---- Householder QR of ONE large problem spread over the whole GPU (cooperative launch) -------------------------
+// The single-CTA kernels above take 0.2 s (1024 x 1024) to 1.3 s (2048 x 2048) when only one problem is in flight
+// (iDMRG at chi >= 256): every reflector makes one SM stream the whole trailing matrix.  Here the COLUMNS of the
+// problem are dealt out to up to 148 CTAs.  Per step the CTA that owns the pivot column finishes that column, forms
+// the reflector and publishes it in global memory; after a grid barrier every CTA applies the previous (pending)
+// reflector to its own columns and accumulates w = v^H x for the new one in the same pass, exactly like
+// qr_precond_kernel, so the only inter-CTA traffic is one vector and one barrier per step.  Same pivot order
+// (descending column norm, ties by index) and the same reflectors as the single-CTA kernels.
+constexpr int QG_THREADS = 512;
+struct QrGridMeta { double tau; int valid; int pad; };
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned seen = 0, it = 0;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen < target && ++it > (1u << 27)) __trap();      // a lost CTA must fail loudly, not hang the GPU
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// grid = (ncta, batch), launched cooperatively.  scratch per problem: counter (256 B) | meta[2] | colnorm[ld] | v[2][nal]
+__global__ void __launch_bounds__(QG_THREADS, 1)
+qr_grid_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, int ltot, int ld, int Lc, int TC,
+               double* __restrict__ frob2, unsigned char* __restrict__ scratch, size_t scratch_stride) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int nal = (int)align_up(n, 8);
+    cplx* vbuf = reinterpret_cast<cplx*>(smraw);                              // [2][nal]
+    cplx* wbuf = vbuf + 2 * (size_t)nal;                                      // [2][Lc]   w of the pending / new reflector
+    cplx* wpart = wbuf + 2 * (size_t)Lc;                                      // [RG][Lc]
+    const int RG = QG_THREADS / TC;
+    double* cn = reinterpret_cast<double*>(wpart + (size_t)RG * Lc);          // [ldot]
+    int* order = reinterpret_cast<int*>(cn + align_up(ldot, 8));              // [ldot]
+    unsigned char* colDone = reinterpret_cast<unsigned char*>(order + align_up(ldot, 8));   // [Lc] own columns only
+    __shared__ double red[33];
+
+    const int tid = threadIdx.x, prob = blockIdx.y, ncta = gridDim.x;
+    cplx* X = Xall + (size_t)prob * strideX;
+    unsigned char* sc = scratch + (size_t)prob * scratch_stride;
+    unsigned* counter = reinterpret_cast<unsigned*>(sc);
+    QrGridMeta* meta = reinterpret_cast<QrGridMeta*>(sc + 256);
+    double* colnorm = reinterpret_cast<double*>(sc + 512);
+    cplx* vglob = reinterpret_cast<cplx*>(sc + 512 + align_up((size_t)ld * sizeof(double), 256));   // [2][nal]
+    unsigned epoch = 0;
+
+    const int c_lo = blockIdx.x * Lc, c_hi = min(ltot, c_lo + Lc);
+    const int rg = tid / TC, cj = tid % TC;
+
+    // column norms of the own dot columns, Frobenius norm, pivot order (identical in every CTA)
+    for (int jj = cj; c_lo + jj < c_hi; jj += TC) {
+        const int j = c_lo + jj;
+        double acc = 0.0;
+        if (j < ldot)
+            for (int i = rg; i < n; i += RG) {
+                const cplx x = X[(size_t)i * ld + j];
+                acc = fma(x.x, x.x, fma(x.y, x.y, acc));
+            }
+        reinterpret_cast<double*>(wpart)[rg * Lc + jj] = acc;
+    }
+    for (int jj = tid; jj < Lc; jj += QG_THREADS) colDone[jj] = 0;
+    __syncthreads();
+    for (int jj = tid; c_lo + jj < c_hi; jj += QG_THREADS) {
+        double acc = 0.0;
+        for (int g = 0; g < RG; ++g) acc += reinterpret_cast<double*>(wpart)[g * Lc + jj];
+        if (c_lo + jj < ldot) colnorm[c_lo + jj] = acc;
+    }
+    grid_barrier(counter, ++epoch * ncta);
+    double fl = 0.0;
+    for (int j = tid; j < ldot; j += QG_THREADS) {
+        double v;
+        asm volatile("ld.relaxed.gpu.f64 %0, [%1];" : "=d"(v) : "l"(colnorm + j) : "memory");
+        cn[j] = v;
+        fl += v;
+    }
+    const double F2 = block_sum(fl, red);
+    if (blockIdx.x == 0 && tid == 0) frob2[prob] = F2;
+    for (int j = tid; j < ldot; j += QG_THREADS) {
+        const double me = cn[j];
+        int r = 0;
+        for (int q = 0; q < ldot; ++q) {
+            const double o = cn[q];
+            r += (o > me) || (o == me && q < j);
+        }
+        order[r] = j;
+    }
+    __syncthreads();
+
+    const int nsteps = n < ldot ? n : ldot;
+    bool have_prev = false;
+    int kprev = 0, pv = 0;
+    double tau_prev = 0.0;
+    for (int k = 0; k < nsteps; ++k) {
+        const int pc = order[k];
+        const int cu = pv ^ 1;
+        cplx* vcur = vbuf + (size_t)cu * nal;
+        const cplx* vprev = vbuf + (size_t)pv * nal;
+        const cplx* wprev = wbuf + (size_t)pv * Lc;
+        cplx* wcur = wbuf + (size_t)cu * Lc;
+        cplx* vg = vglob + (size_t)cu * nal;
+        const bool owner = pc >= c_lo && pc < c_hi;
+        if (owner) {
+            // A. pivot column with the pending update applied
+            cplx wp = make_double2(0.0, 0.0);
+            if (have_prev) { wp = wprev[pc - c_lo]; wp.x *= tau_prev; wp.y *= tau_prev; }
+            const int lo = have_prev ? kprev : k;
+            for (int i = lo + tid; i < n; i += QG_THREADS) {
+                cplx x = X[(size_t)i * ld + pc];
+                if (have_prev) {
+                    const cplx vi = vprev[i];
+                    x.x -= vi.x * wp.x - vi.y * wp.y;
+                    x.y -= vi.x * wp.y + vi.y * wp.x;
+                }
+                if (i < k) X[(size_t)i * ld + pc] = x;
+                else vcur[i] = x;
+            }
+            __syncthreads();
+            double loc = 0.0;
+            for (int i = k + 1 + tid; i < n; i += QG_THREADS) {
+                const cplx x = vcur[i];
+                loc = fma(x.x, x.x, fma(x.y, x.y, loc));
+            }
+            const cplx alpha = vcur[k];
+            const double sigma = block_sum(loc, red);
+            const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+            const double normx2 = a2 + sigma;
+            if (!(normx2 > 0.0)) {
+                for (int i = k + tid; i < n; i += QG_THREADS) X[(size_t)i * ld + pc] = make_double2(0.0, 0.0);
+                if (tid == 0) { meta[cu].tau = 0.0; meta[cu].valid = 0; colDone[pc - c_lo] = 1; }
+            } else {
+                const double normx = sqrt(normx2), absa = sqrt(a2);
+                cplx phase = make_double2(1.0, 0.0);
+                if (absa > 0.0) phase = make_double2(alpha.x / absa, alpha.y / absa);
+                const cplx beta = make_double2(-phase.x * normx, -phase.y * normx);
+                const cplx vk = make_double2(phase.x * (absa + normx), phase.y * (absa + normx));
+                const double vhv = (absa + normx) * (absa + normx) + sigma;
+                if (tid == 0) { vcur[k] = vk; meta[cu].tau = 2.0 / vhv; meta[cu].valid = 1; colDone[pc - c_lo] = 1; }
+                __syncthreads();
+                for (int i = k + tid; i < n; i += QG_THREADS) {
+                    vg[i] = vcur[i];
+                    X[(size_t)i * ld + pc] = (i == k) ? beta : make_double2(0.0, 0.0);
+                }
+            }
+        }
+        grid_barrier(counter, ++epoch * ncta);
+        double tau;
+        int valid;
+        asm volatile("ld.relaxed.gpu.f64 %0, [%1];" : "=d"(tau) : "l"(&meta[cu].tau) : "memory");
+        asm volatile("ld.relaxed.gpu.s32 %0, [%1];" : "=r"(valid) : "l"(&meta[cu].valid) : "memory");
+        if (!valid) continue;                               // zero column: the pending reflector stays pending
+        if (!owner) {
+            for (int i = k + tid; i < n; i += QG_THREADS) {
+                cplx v;
+                asm volatile("ld.relaxed.gpu.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(vg + i) : "memory");
+                vcur[i] = v;
+            }
+        }
+        __syncthreads();
+        // C. fused pass over the own columns
+        const int lo = have_prev ? kprev : k;
+        for (int jj = cj; jj < Lc; jj += TC) {
+            const int j = c_lo + jj;
+            double wr = 0.0, wi = 0.0;
+            if (j < c_hi && j != pc && !(j < ldot && colDone[jj])) {
+                double pr = 0.0, pi = 0.0;
+                if (have_prev) { pr = wprev[jj].x * tau_prev; pi = wprev[jj].y * tau_prev; }
+                int i = lo + rg;
+                for (; i < k; i += RG) {
+                    const cplx vi = vprev[i];
+                    cplx x = X[(size_t)i * ld + j];
+                    x.x -= vi.x * pr - vi.y * pi;
+                    x.y -= vi.x * pi + vi.y * pr;
+                    X[(size_t)i * ld + j] = x;
+                }
+                if (have_prev) {
+#pragma unroll 4
+                    for (; i < n; i += RG) {
+                        const cplx vi = vprev[i], vc = vcur[i];
+                        cplx x = X[(size_t)i * ld + j];
+                        x.x -= vi.x * pr - vi.y * pi;
+                        x.y -= vi.x * pi + vi.y * pr;
+                        X[(size_t)i * ld + j] = x;
+                        wr = fma(vc.x, x.x, fma(vc.y, x.y, wr));
+                        wi = fma(vc.x, x.y, fma(-vc.y, x.x, wi));
+                    }
+                } else {
+#pragma unroll 4
+                    for (; i < n; i += RG) {
+                        const cplx vc = vcur[i];
+                        const cplx x = X[(size_t)i * ld + j];
+                        wr = fma(vc.x, x.x, fma(vc.y, x.y, wr));
+                        wi = fma(vc.x, x.y, fma(-vc.y, x.x, wi));
+                    }
+                }
+            }
+            wpart[(size_t)rg * Lc + jj] = make_double2(wr, wi);
+        }
+        __syncthreads();
+        for (int jj = tid; jj < Lc; jj += QG_THREADS) {
+            double sr = 0.0, si = 0.0;
+            for (int g = 0; g < RG; ++g) { sr += wpart[(size_t)g * Lc + jj].x; si += wpart[(size_t)g * Lc + jj].y; }
+            wcur[jj] = make_double2(sr, si);
+        }
+        have_prev = true;
+        kprev = k;
+        tau_prev = tau;
+        pv = cu;
+        __syncthreads();
+    }
+    if (have_prev) {   // last pending update
+        const cplx* vprev = vbuf + (size_t)pv * nal;
+        const cplx* wprev = wbuf + (size_t)pv * Lc;
+        for (int jj = cj; jj < Lc; jj += TC) {
+            const int j = c_lo + jj;
+            if (j < c_hi && !(j < ldot && colDone[jj])) {
+                const double pr = wprev[jj].x * tau_prev, pi = wprev[jj].y * tau_prev;
+#pragma unroll 4
+                for (int i = kprev + rg; i < n; i += RG) {
                     const cplx vi = vprev[i];
                     cplx x = X[(size_t)i * ld + j];
                     x.x -= vi.x * pr - vi.y * pi;
@@ -1006,6 +1239,7 @@ struct GramSmem {
     int partner[GR], role[GR], rix[GR];
     int nrot;
     uint64_t bar;
+    uint64_t tile_bar[2];              // tiled kernel: one barrier per tile buffer
 };
 
 // Division-free rotation parameters (see jacobi_angle): f = +-1/sqrt(denom^2 + |c|^2), cs = denom * |f|.
@@ -1018,6 +1252,66 @@ __device__ __forceinline__ void jacobi_angle_fast(double a, double b, double cr,
     const double f = z >= 0.0 ? h : -h;
     gr = f * cr;
     gi = f * ci;
+}
+
+// Phase B of the Gram kernels: tournament of two-sided rotations on the 16 x 16 Gram block sm.G (nsteps = 15: all
+// pairs; nsteps = 8: the cross pairs between rows 0-7 and 8-15), accumulated into sm.Q.  Thread (ei, ej) owns one
+// element of G and Q.  Returns the number of rotations applied (same value in every thread).
+__device__ __forceinline__ int gram_tournament(GramSmem& sm, int nsteps, double tol2, int tid, int ei, int ej) {
+    int my_rot = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        if (tid < 8) {
+            int p, q;
+            if (nsteps == GR - 1) rr_pair(GR, s, tid, p, q);
+            else { p = tid; q = 8 + ((tid + s) & 7); }
+            const double a = sm.G[p][p].x, b = sm.G[q][q].x;
+            const cplx c = sm.G[p][q];
+            const double ac2 = c.x * c.x + c.y * c.y;
+            double cs = 1.0, gr = 0.0, gi = 0.0;
+            if (ac2 > tol2 * a * b) {
+                jacobi_angle_fast(a, b, c.x, c.y, ac2, cs, gr, gi);
+                ++my_rot;
+            }
+            sm.cs[tid] = cs; sm.gr[tid] = gr; sm.gi[tid] = gi;
+            sm.partner[p] = q; sm.role[p] = 0; sm.rix[p] = tid;
+            sm.partner[q] = p; sm.role[q] = 1; sm.rix[q] = tid;
+        }
+        __syncthreads();
+        cplx gn, qn;
+        {
+            const int ip = sm.partner[ei], jp = sm.partner[ej];
+            const int ri = sm.rix[ei], rj = sm.rix[ej];
+            const double csi = sm.cs[ri], csj = sm.cs[rj];
+            // rows:    P' = cs P - g Q,  Q' = conj(g) P + cs Q   -> partner coefficient w_i = -g | conj(g)
+            // columns: Hermitian conjugate of the row transform     -> partner coefficient conj(w_j)
+            const double wri = sm.role[ei] == 0 ? -sm.gr[ri] : sm.gr[ri];
+            const double wii = -sm.gi[ri];
+            const double wrj = sm.role[ej] == 0 ? -sm.gr[rj] : sm.gr[rj];
+            const double wij = sm.gi[rj];
+            const cplx g00 = sm.G[ei][ej], g10 = sm.G[ip][ej], g01 = sm.G[ei][jp], g11 = sm.G[ip][jp];
+            cplx Tj, Tjp;
+            Tj.x = fma(csi, g00.x, fma(wri, g10.x, -wii * g10.y));
+            Tj.y = fma(csi, g00.y, fma(wri, g10.y, wii * g10.x));
+            Tjp.x = fma(csi, g01.x, fma(wri, g11.x, -wii * g11.y));
+            Tjp.y = fma(csi, g01.y, fma(wri, g11.y, wii * g11.x));
+            gn.x = fma(csj, Tj.x, fma(wrj, Tjp.x, -wij * Tjp.y));
+            gn.y = fma(csj, Tj.y, fma(wrj, Tjp.y, wij * Tjp.x));
+            if (ei == ej) gn.y = 0.0;
+            const cplx q0 = sm.Q[ei][ej], q1 = sm.Q[ei][jp];
+            qn.x = fma(csj, q0.x, fma(wrj, q1.x, -wij * q1.y));
+            qn.y = fma(csj, q0.y, fma(wrj, q1.y, wij * q1.x));
+        }
+        __syncthreads();
+        sm.G[ei][ej] = gn;
+        sm.Q[ei][ej] = qn;
+        __syncthreads();
+    }
+    if (tid < 8 && my_rot > 0) atomicAdd(&sm.nrot, my_rot);
+    __syncthreads();
+    const int nrot = sm.nrot;
+    __syncthreads();
+    if (tid == 0) sm.nrot = 0;
+    return nrot;
 }
 
 __global__ void __launch_bounds__(GRAM_THREADS, 3)
@@ -1102,59 +1396,7 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
         __syncthreads();
         // ---- B. tournament on G ------------------------------------------------------------------------
         const long long tB = phase_clk ? clock64() : 0;
-        int my_rot = 0;
-        for (int s = 0; s < nsteps; ++s) {
-            if (tid < 8) {
-                int p, q;
-                if (nsteps == GR - 1) rr_pair(GR, s, tid, p, q);
-                else { p = tid; q = 8 + ((tid + s) & 7); }
-                const double a = sm.G[p][p].x, b = sm.G[q][q].x;
-                const cplx c = sm.G[p][q];
-                const double ac2 = c.x * c.x + c.y * c.y;
-                double cs = 1.0, gr = 0.0, gi = 0.0;
-                if (ac2 > tol2 * a * b) {
-                    jacobi_angle_fast(a, b, c.x, c.y, ac2, cs, gr, gi);
-                    ++my_rot;
-                }
-                sm.cs[tid] = cs; sm.gr[tid] = gr; sm.gi[tid] = gi;
-                sm.partner[p] = q; sm.role[p] = 0; sm.rix[p] = tid;
-                sm.partner[q] = p; sm.role[q] = 1; sm.rix[q] = tid;
-            }
-            __syncthreads();
-            cplx gn, qn;
-            {
-                const int ip = sm.partner[ei], jp = sm.partner[ej];
-                const int ri = sm.rix[ei], rj = sm.rix[ej];
-                const double csi = sm.cs[ri], csj = sm.cs[rj];
-                // rows:    P' = cs P - g Q,  Q' = conj(g) P + cs Q   -> partner coefficient w_i = -g | conj(g)
-                // columns: Hermitian conjugate of the row transform     -> partner coefficient conj(w_j)
-                const double wri = sm.role[ei] == 0 ? -sm.gr[ri] : sm.gr[ri];
-                const double wii = -sm.gi[ri];
-                const double wrj = sm.role[ej] == 0 ? -sm.gr[rj] : sm.gr[rj];
-                const double wij = sm.gi[rj];
-                const cplx g00 = sm.G[ei][ej], g10 = sm.G[ip][ej], g01 = sm.G[ei][jp], g11 = sm.G[ip][jp];
-                cplx Tj, Tjp;
-                Tj.x = fma(csi, g00.x, fma(wri, g10.x, -wii * g10.y));
-                Tj.y = fma(csi, g00.y, fma(wri, g10.y, wii * g10.x));
-                Tjp.x = fma(csi, g01.x, fma(wri, g11.x, -wii * g11.y));
-                Tjp.y = fma(csi, g01.y, fma(wri, g11.y, wii * g11.x));
-                gn.x = fma(csj, Tj.x, fma(wrj, Tjp.x, -wij * Tjp.y));
-                gn.y = fma(csj, Tj.y, fma(wrj, Tjp.y, wij * Tjp.x));
-                if (ei == ej) gn.y = 0.0;
-                const cplx q0 = sm.Q[ei][ej], q1 = sm.Q[ei][jp];
-                qn.x = fma(csj, q0.x, fma(wrj, q1.x, -wij * q1.y));
-                qn.y = fma(csj, q0.y, fma(wrj, q1.y, wij * q1.x));
-            }
-            __syncthreads();
-            sm.G[ei][ej] = gn;
-            sm.Q[ei][ej] = qn;
-            __syncthreads();
-        }
-        if (tid < 8 && my_rot > 0) atomicAdd(&sm.nrot, my_rot);
-        __syncthreads();
-        const int nrot = sm.nrot;
-        __syncthreads();
-        if (tid == 0) sm.nrot = 0;
+        const int nrot = gram_tournament(sm, nsteps, tol2, tid, ei, ej);
         const long long tC = phase_clk ? clock64() : 0;
         if (phase_clk && tid == 0) {
             atomicAdd(&phase_clk[4], (unsigned long long)(tB - tA));
@@ -1229,6 +1471,171 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
             atomicAdd(&phase_clk[2], (unsigned long long)(clock64() - t_rotated));
             atomicAdd(&phase_clk[3], 1ull);
         }
+    }
+}
+
+// ---- Gram rounds for rows that do not fit shared memory (chi = 1024: 2048 x 4096 work matrices) -------------------
+// Same three phases as jacobi_gram_kernel, but the 16 rows stream through two 256-column tile buffers: phase A
+// accumulates G over the tiles of the dot columns (next tile in flight while the current one feeds the DMMAs), phase C
+// re-reads every tile, applies Q^H and writes it back with an asynchronous bulk store that overlaps the next tile.
+// Traffic per CTA and round: 16 rows x (ldot + 2 ltot) x 16 B; one CTA per SM (140 KB of shared memory).
+constexpr int TILE_W = 256;
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
+                         int round, int inner_sweeps, int* __restrict__ rot, const int* __restrict__ done, double tol2,
+                         int* __restrict__ stamps, int stamp_stride, int launch_id) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    GramSmem& sm = *reinterpret_cast<GramSmem*>(smraw);
+    cplx* tiles = reinterpret_cast<cplx*>(smraw + ((sizeof(GramSmem) + 127) / 128) * 128);   // [2][GR][pitch]
+    constexpr int pitch = TILE_W + GRAM_PAD;
+
+    const int mat = mat0 + blockIdx.y;
+    if (done[mat]) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int bI, bJ;
+    rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
+    const int chk_idx = nblk + round * (nblk >> 1) + blockIdx.x;
+    if (stp) {
+        const int chk = stp[chk_idx];
+        if (chk > stp[bI] && chk > stp[bJ]) return;
+    }
+    cplx* X = Xall + (size_t)mat * strideX;
+    if (tid == 0) {
+        mbar_init(&sm.tile_bar[0], 1);
+        mbar_init(&sm.tile_bar[1], 1);
+        mbar_fence_init();
+        sm.nrot = 0;
+    }
+    __syncthreads();
+    uint32_t uses[2] = {0u, 0u};                          // completed phases of each tile barrier (uniform)
+    auto row_ptr = [&](int r) { return X + (size_t)(r < 8 ? bI * 8 + r : bJ * 8 + r - 8) * ld; };
+    auto tile_ptr = [&](int buf) { return tiles + (size_t)buf * GR * pitch; };
+    auto issue_load = [&](int buf, int c0) {              // thread 0: columns [c0, c0 + width) of the 16 rows
+        const int width = min(TILE_W, ltot_r - c0);
+        const uint32_t bytes = (uint32_t)width * sizeof(cplx);
+        mbar_expect_tx(&sm.tile_bar[buf], bytes * GR);
+        for (int r = 0; r < GR; ++r) bulk_g2s(tile_ptr(buf) + (size_t)r * pitch, row_ptr(r) + c0, bytes, &sm.tile_bar[buf]);
+    };
+    auto wait_tile = [&](int buf) {
+        if (!mbar_wait(&sm.tile_bar[buf], uses[buf] & 1u)) __trap();
+        ++uses[buf];
+    };
+
+    const int nsteps = (round == 0 || nblk == 2) ? GR - 1 : 8;
+    const int ei = tid >> 4, ej = tid & 15;
+    const int ntA = (ldot + TILE_W - 1) / TILE_W, ntC = (ltot_r + TILE_W - 1) / TILE_W;
+    int total_rot = 0;
+    for (int sw = 0; sw < inner_sweeps; ++sw) {
+        // ---- A. Gram matrix over the tiles of the dot columns ------------------------------------------------
+        {
+            const int qd = w & 3, khalf = w >> 2;
+            const int ti = qd >> 1, tj = qd & 1;
+            double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+            if (tid == 0) issue_load(0, 0);
+            for (int k = 0; k < ntA; ++k) {
+                const int buf = k & 1, c0 = k * TILE_W;
+                if (tid == 0 && k + 1 < ntA) issue_load(buf ^ 1, c0 + TILE_W);
+                wait_tile(buf);
+                const int lim = min(TILE_W, ldot - c0);
+                const int ksteps = (lim + 3) >> 2;
+                const cplx* ra = tile_ptr(buf) + (size_t)(8 * ti + g) * pitch + t;
+                const cplx* rb = tile_ptr(buf) + (size_t)(8 * tj + g) * pitch + t;
+#pragma unroll 4
+                for (int ks = khalf; ks < ksteps; ks += 2) {
+                    cplx a = ra[4 * ks], b = rb[4 * ks];
+                    if (4 * ks + t >= lim) { a = make_double2(0.0, 0.0); b = make_double2(0.0, 0.0); }
+                    dmma884(re0, re1, a.x, b.x);
+                    dmma884(re0, re1, a.y, b.y);
+                    dmma884(im0, im1, a.y, b.x);
+                    dmma884(im0, im1, -a.x, b.y);
+                }
+                __syncthreads();                          // buffer free for the load issued two tiles ahead
+            }
+            cplx* dst = khalf == 0 ? &sm.G[8 * ti + g][8 * tj + 2 * t] : &sm.Q[8 * ti + g][8 * tj + 2 * t];
+            dst[0] = make_double2(re0, im0);
+            dst[1] = make_double2(re1, im1);
+        }
+        __syncthreads();
+        {
+            cplx v = sm.G[ei][ej];
+            const cplx u = sm.Q[ei][ej];
+            v.x += u.x;
+            v.y = (ei == ej) ? 0.0 : v.y + u.y;
+            sm.G[ei][ej] = v;
+            sm.Q[ei][ej] = make_double2(ei == ej ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+        // ---- B. tournament on G ------------------------------------------------------------------------------
+        const int nrot = gram_tournament(sm, nsteps, tol2, tid, ei, ej);
+        if (nrot == 0) break;
+        total_rot += nrot;
+        // ---- C. P <- Q^H P, tile by tile ------------------------------------------------------------------------
+        {
+            cplx af[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const cplx v = sm.Q[4 * ks + t][8 * mt + g];
+                    af[mt][ks] = make_double2(v.x, -v.y);
+                }
+            if (tid == 0) issue_load(0, 0);
+            for (int k = 0; k < ntC; ++k) {
+                const int buf = k & 1, c0 = k * TILE_W;
+                const int width = min(TILE_W, ltot_r - c0);
+                if (tid == 0 && k + 1 < ntC) {
+                    bulk_wait_read_all();                 // the store of tile k-1 has finished reading that buffer
+                    issue_load(buf ^ 1, c0 + TILE_W);
+                }
+                wait_tile(buf);
+                cplx* rows = tile_ptr(buf);
+                const int ntiles = width >> 3;
+                for (int nt = w; nt < ntiles; nt += 8) {
+                    const int n0 = nt * 8;
+                    cplx bf[4];
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) bf[ks] = rows[(size_t)(4 * ks + t) * pitch + n0 + g];
+                    double cre[2][2], cim[2][2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) { cre[mt][0] = cre[mt][1] = cim[mt][0] = cim[mt][1] = 0.0; }
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            dmma884(cre[mt][0], cre[mt][1], af[mt][ks].x, bf[ks].x);
+                            dmma884(cre[mt][0], cre[mt][1], -af[mt][ks].y, bf[ks].y);
+                            dmma884(cim[mt][0], cim[mt][1], af[mt][ks].x, bf[ks].y);
+                            dmma884(cim[mt][0], cim[mt][1], af[mt][ks].y, bf[ks].x);
+                        }
+                    __syncwarp();
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        cplx* dst = rows + (size_t)(8 * mt + g) * pitch + n0 + 2 * t;
+                        dst[0] = make_double2(cre[mt][0], cim[mt][0]);
+                        dst[1] = make_double2(cre[mt][1], cim[mt][1]);
+                    }
+                }
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t bytes = (uint32_t)width * sizeof(cplx);
+                    for (int r = 0; r < GR; ++r) bulk_s2g(row_ptr(r) + c0, rows + (size_t)r * pitch, bytes);
+                    bulk_commit();
+                }
+            }
+            if (tid == 0) bulk_wait_all();                // rows are back in global memory before they are read again
+            __syncthreads();
+        }
+    }
+    if (total_rot == 0) {
+        if (stp && tid == 0) stp[chk_idx] = launch_id;
+        return;
+    }
+    if (tid == 0) {
+        atomicAdd(&rot[mat], total_rot);
+        if (stp) { stp[bI] = launch_id; stp[bJ] = launch_id; }
     }
 }
 
@@ -1483,6 +1890,41 @@ int launch_round(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int co
     return 0;
 }
 
+size_t qr_grid_scratch_bytes(const SvdPlan& pl) {      // per problem
+    return align_up(512 + align_up((size_t)pl.ld * sizeof(double), 256) + 2 * align_up(pl.n, 8) * sizeof(cplx), 256);
+}
+// Returns 0 when the cooperative kernel ran, -1 when it cannot be used here (the caller falls back), > 0 on errors.
+int launch_qr_grid(const SvdPlan& pl, cplx* X, double* frob2, unsigned char* scratch, cudaStream_t st) {
+    int dev = 0, sms = 0, coop = 0;
+    MPSB_CHECK_CUDA(cudaGetDevice(&dev));
+    MPSB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MPSB_CHECK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop || sms < 1) return -1;
+    const int per_problem = std::max(1, sms / pl.batch);
+    int Lc = round_up((pl.ltot + per_problem - 1) / per_problem, 2);
+    int TC = 1;
+    while (TC < Lc && TC < 32) TC <<= 1;
+    const int ncta = (pl.ltot + Lc - 1) / Lc;
+    const int RG = QG_THREADS / TC;
+    const size_t smem = 2 * align_up(pl.n, 8) * sizeof(cplx) + (size_t)(2 + RG) * Lc * sizeof(cplx) +
+                        align_up(pl.ldot, 8) * (sizeof(double) + sizeof(int)) + Lc + 64;
+    if (smem > 200 * 1024) return -1;
+    const void* fn = reinterpret_cast<const void*>(qr_grid_kernel);
+    if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
+    int per_sm = 0;
+    MPSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_grid_kernel, QG_THREADS, smem));
+    if ((long long)per_sm * sms < (long long)ncta * pl.batch) return -1;
+    const size_t stride = qr_grid_scratch_bytes(pl);
+    MPSB_CHECK_CUDA(cudaMemsetAsync(scratch, 0, stride * pl.batch, st));
+    long long strideX = (long long)pl.n_pad * pl.ld;
+    int n = pl.n, ldot = pl.ldot, ltot = pl.ltot, ld = pl.ld;
+    size_t stride_arg = stride;
+    void* args[] = {&X, &strideX, &n, &ldot, &ltot, &ld, &Lc, &TC, &frob2, &scratch, &stride_arg};
+    MPSB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ncta, pl.batch), dim3(QG_THREADS), args, smem, st));
+    MPSB_COUNT_LAUNCH();
+    return 0;
+}
+
 size_t gram_smem_bytes(int ltot_r) {
     return ((sizeof(GramSmem) + 127) / 128) * 128 + (size_t)GR * (ltot_r + GRAM_PAD) * sizeof(cplx);
 }
@@ -1502,6 +1944,24 @@ int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int cou
                                                         g_prof.enabled > 1 ? s.phase_clk : nullptr,
                                                         nblk == pl.n_pad / pl.bsz ? s.stamps : nullptr, s.stamp_stride,
                                                         launch_id);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t gram_tiled_smem_bytes() {
+    return ((sizeof(GramSmem) + 127) / 128) * 128 + (size_t)2 * GR * (TILE_W + GRAM_PAD) * sizeof(cplx);
+}
+int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int inner,
+                      double tol2, int launch_id, cudaStream_t st) {
+    const int ltot_r = round_up(pl.ltot, 32);
+    const size_t smem = gram_tiled_smem_bytes();
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_gram_tiled_kernel), smem)) return rc;
+    const int nblk = pl.n_pad / 8;
+    dim3 grid(nblk / 2, count);
+    jacobi_gram_tiled_kernel<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot,
+                                                              ltot_r, nblk, round, inner, s.rot, s.done, tol2, s.stamps,
+                                                              s.stamp_stride, launch_id);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1533,6 +1993,7 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
         return 0;
     }
     if (use_gram_kernel(pl)) return launch_gram(pl, X, s, mat0, count, round, inner, tol2, launch_id, st);
+    if (pl.tiled) return launch_gram_tiled(pl, X, s, mat0, count, round, inner, tol2, launch_id, st);
     switch (pl.bsz) {
         case 1: return launch_round<1>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
         case 2: return launch_round<2>(pl, X, s, mat0, count, round, full, inner, tol2, eabs2, st);
@@ -1588,12 +2049,19 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
     const size_t rowbytes = (size_t)p.ld * sizeof(cplx);
     const size_t smem_budget = 200 * 1024;
     const int rows_fit = (int)(smem_budget / rowbytes);
-    MPSB_REQUIRE(rows_fit >= 2, "svd: row of %d elements does not fit shared memory", p.ld);
     int bcap = env_int("MPSB_JACOBI_BSZ", 8);
     if (bcap < 1) bcap = 1;
     if (bcap > 16) bcap = 16;
     int b = 1;
-    while (b * 2 <= bcap && 2 * (b * 2) <= rows_fit && b < (n + 1) / 2) b *= 2;
+    while (b * 2 <= bcap && b < (n + 1) / 2) b *= 2;
+    // Rows too long for 16 of them to sit in shared memory stream through the tiled Gram kernel (8-row blocks);
+    // other block sizes fall back to however many whole rows fit.
+    static const int tiled_enabled = env_int("MPSB_JACOBI_TILED", 1);
+    p.tiled = (tiled_enabled && b == 8 && gram_smem_bytes(p.ld) > 220 * 1024) ? 1 : 0;
+    if (!p.tiled) {
+        MPSB_REQUIRE(rows_fit >= 2, "svd: row of %d elements does not fit shared memory", p.ld);
+        while (b > 1 && 2 * b > rows_fit) b /= 2;
+    }
     p.bsz = b;
     p.n_pad = round_up(n, 2 * b);
     // Tiny problems in small batches: one launch per SVD with the matrix resident in one CTA's shared memory.  One SM
@@ -1618,13 +2086,17 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
     if (chunk > 65535) chunk = 65535;
     p.chunk = chunk;
     p.max_sweeps = env_int("MPSB_SVD_MAX_SWEEPS", 40);
+    static const int qr_grid_enabled = env_int("MPSB_SVD_QR_GRID", 1);
+    static const int qr_grid_min = env_int("MPSB_SVD_QR_GRID_MIN", 160);
+    p.qr_grid = (qr_grid_enabled && batch <= 4 && std::min(n, ldot) >= qr_grid_min) ? 1 : 0;
     *plan = p;
     return 0;
 }
 
 size_t svd_state_bytes(const SvdPlan& plan) {
     return align_up(sizeof(int) * plan.batch, 256) * 2 + align_up(sizeof(double) * plan.batch, 256) + 256 +
-           align_up(sizeof(int) * (size_t)plan.batch * stamp_ints(plan.n_pad, plan.bsz), 256);
+           align_up(sizeof(int) * (size_t)plan.batch * stamp_ints(plan.n_pad, plan.bsz), 256) +
+           (plan.qr_grid ? qr_grid_scratch_bytes(plan) * plan.batch : 0);
 }
 
 int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, int* sweeps_out) {
@@ -1654,7 +2126,16 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
         // to itself the 1024-thread fused kernel has half the latency (tools/tebd_small_probe.py).
         const bool latency_mode = pl.batch <= 148 && smem <= 220 * 1024;
-        if (qr_enabled && qr_blocked && !latency_mode && smem_b <= 200 * 1024) {
+        int grid_rc = -1;
+        if (qr_enabled && pl.qr_grid) {
+            SvdPlan base = pl;
+            base.qr_grid = 0;
+            unsigned char* scratch = static_cast<unsigned char*>(state) + svd_state_bytes(base);
+            grid_rc = launch_qr_grid(pl, X, s.frob2, scratch, st);
+            if (grid_rc > 0) return grid_rc;
+        }
+        if (grid_rc == 0) {
+        } else if (qr_enabled && qr_blocked && !latency_mode && smem_b <= 200 * 1024) {
             if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_blocked_kernel), smem_b)) return rc;
             qr_blocked_kernel<<<pl.batch, QB_THREADS, smem_b, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, s.frob2);
             MPSB_COUNT_LAUNCH();

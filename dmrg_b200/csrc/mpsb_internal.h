@@ -14,6 +14,7 @@ struct Profile {
     int enabled;
     cudaEvent_t ev[8];
     int have_events;
+    unsigned recorded;                  // bit i: event i was recorded since profiling was switched on
     unsigned long long rotations;       // Jacobi rotations applied in the last SVD
     unsigned long long problem_sweeps;  // sum over problems of sweeps executed in the last SVD
 };
@@ -51,6 +52,8 @@ struct SvdPlan {
     int bsz;         // rows per Jacobi block (power of two, 1..16)
     int chunk;       // problems swept together (L2 residency)
     int max_sweeps;
+    int qr_grid;     // 1: few large problems - the QR of each is spread over many CTAs (cooperative launch)
+    int tiled;       // 1: rows longer than shared memory allows stream through the tiled Gram kernel
     int resident;    // 1: the whole work matrix of a problem lives in one CTA's shared memory (single launch)
 };
 int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan);

@@ -139,7 +139,8 @@ int mpsb_last_svd_sweeps(void);
 /* Phase timing of mpsb_tebd_two_site for the roofline report (bench.py).  When enabled, CUDA events are
  * recorded on the caller's stream at the phase boundaries; mpsb_profile_read returns the 6 phase
  * durations in ms (theta GEMM, gate, QR, Jacobi sweeps, finalise, back-projection GEMM) of the last
- * call plus the Jacobi work counters of its SVD. */
+ * call plus the Jacobi work counters of its SVD; a phase the last call did not run reads -1 (an SVD-only call
+ * reports just the Jacobi sweeps). */
 void mpsb_profile_enable(int on);
 int mpsb_profile_read(double* phase_ms, unsigned long long* rotations, unsigned long long* problem_sweeps);
 
