@@ -271,3 +271,78 @@ def test_large_local_dimension_d10(lib):
         th_g = np.tensordot(bio[c, :, :, :k], bjo[c, :k], axes=([2], [0]))
         th_o = np.tensordot(Mi, Mj, axes=([2], [0]))
         np.testing.assert_allclose(th_g, th_o, atol=1e-9 * np.abs(th_o).max())
+
+
+@pytest.mark.parametrize("shape", [(200, 300), (330, 170), (520, 520), (24, 1500), (700, 40)])
+def test_svd_large_single_problem(lib, shape):
+    """One big problem: cooperative multi-CTA QR (min(rows, cols) >= 160) and, once the carried identity makes the rows
+    longer than shared memory holds (520 + 520 columns, 1500 columns), the column-tiled Gram Jacobi kernel."""
+    from dmrg_b200.MPS import svd_truncate
+    rows, cols = shape
+    rs = np.random.RandomState(rows + 7 * cols)
+    k0 = min(rows, cols)
+    qu, _ = np.linalg.qr(crand(rs, rows, k0))
+    qv, _ = np.linalg.qr(crand(rs, cols, k0))
+    sv = np.exp(-np.arange(k0) * 20.0 / k0)                     # Schmidt-like decay over 9 decades
+    sv[k0 // 2] = sv[k0 // 2 + 1]                               # one exactly degenerate pair
+    m = (qu * sv) @ qv.conj().T
+    u, s, vh = svd_truncate(m, trun=10 ** 6, err=1e-7)
+    uo, so, vo = oracle_svd_truncate(m, trun=10 ** 6, err=1e-7)
+    assert len(s) == len(so)
+    k = len(s)
+    np.testing.assert_allclose(s, so, rtol=1e-10, atol=1e-15)
+    np.testing.assert_allclose(u.conj().T @ u, np.eye(k), atol=1e-11)
+    np.testing.assert_allclose(vh @ vh.conj().T, np.eye(k), atol=1e-11)
+    s_raw = la.svd(m, compute_uv=False)[:k]
+    np.testing.assert_allclose((u * s_raw) @ vh, (uo * s_raw) @ vo, atol=1e-9)
+    assert lib.load().mpsb_last_svd_sweeps() <= 20
+
+
+def test_svd_grid_qr_small_batch_and_zero_columns(lib):
+    """Batch of 3 problems sharing the GPU in the cooperative QR; one has zero columns (reflector skipped), one is
+    all zeros."""
+    rs = np.random.RandomState(99)
+    n, L, nb = 180, 220, 3
+    a = crand(rs, nb, n, L)
+    a[1][:, ::7] = 0.0
+    a[2][:] = 0.0
+    Lb = lib.load()
+    ad = lib.to_device(a)
+    k = min(n, L)
+    vh, s, rank = lib.empty((nb, k, L)), lib.empty((nb, k), "f64"), lib.empty((nb,), "i32")
+    sraw = lib.empty((nb, k), "f64")
+    ws, wsn = lib.workspace(Lb.mpsb_svd_trunc_workspace(nb, n, L, 0))
+    lib.check(Lb.mpsb_svd_trunc(nb, n, L, lib.ptr(ad), L, n * L, k, 1e-12, 1, k, lib.ptr(vh), None, lib.ptr(s),
+                                lib.ptr(sraw), lib.ptr(rank), ws, wsn, lib.stream_ptr()), "mpsb_svd_trunc")
+    ranks = lib.to_host(rank)
+    assert ranks[2] == 0
+    for b in range(2):
+        ref = la.svd(a[b], compute_uv=False)
+        kk = int(np.sum(ref / ref[0] > 1e-12))
+        assert ranks[b] == kk
+        np.testing.assert_allclose(lib.to_host(sraw)[b][:kk], ref[:kk], rtol=1e-10, atol=1e-13 * ref[0])
+        v = lib.to_host(vh)[b][:kk]
+        np.testing.assert_allclose(v @ v.conj().T, np.eye(kk), atol=1e-11)
+        np.testing.assert_allclose(la.norm(a[b] @ v.conj().T, axis=0), ref[:kk], rtol=1e-9, atol=1e-12 * ref[0])
+
+
+def test_svd_resident_small_batches(lib):
+    """Tiny matrices in small batches run all sweeps inside one launch (matrix resident in shared memory)."""
+    rs = np.random.RandomState(5)
+    Lb = lib.load()
+    for n, L, nb in [(2, 2, 1), (7, 5, 4), (16, 16, 30), (33, 40, 9), (48, 64, 5), (20, 250, 3)]:
+        a = crand(rs, nb, n, L) * np.exp(-0.2 * np.arange(L))[None, None, :]
+        ad = lib.to_device(a)
+        k = min(n, L)
+        vh, s, rank = lib.empty((nb, k, L)), lib.empty((nb, k), "f64"), lib.empty((nb,), "i32")
+        sraw = lib.empty((nb, k), "f64")
+        ws, wsn = lib.workspace(Lb.mpsb_svd_trunc_workspace(nb, n, L, 0))
+        n0 = Lb.mpsb_launch_count()
+        lib.check(Lb.mpsb_svd_trunc(nb, n, L, lib.ptr(ad), L, n * L, k, 0.0, 1, k, lib.ptr(vh), None, lib.ptr(s),
+                                    lib.ptr(sraw), lib.ptr(rank), ws, wsn, lib.stream_ptr()), "mpsb_svd_trunc")
+        assert Lb.mpsb_launch_count() - n0 <= 6 + nb, "expected the single-launch resident path (+ one pack per problem)"
+        for b in range(nb):
+            ref = la.svd(a[b], compute_uv=False)
+            np.testing.assert_allclose(lib.to_host(sraw)[b], ref, rtol=1e-10, atol=1e-14 * ref[0])
+            v = lib.to_host(vh)[b]
+            np.testing.assert_allclose(v @ v.conj().T, np.eye(k), atol=1e-11)
