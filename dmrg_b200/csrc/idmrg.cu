@@ -111,6 +111,31 @@ struct Heff {
     cplx *Lt, *WW, *T1, *T3;
     size_t n;           // chil*d*d*chir
 };
+// Wavefunction prediction (new; no counterpart in the reference, which restarts ARPACK from a random vector):
+//   XL[a,s,c] = S[a] B[a,s,c] Sinv[c]        XR[c,t,b] = A[c,t,b] S[b]
+// so that theta_trial[a,s,t,b] = sum_c XL[a,s,c] XR[c,t,b] = (S B) Sprev^-1 (A S).  Element-wise, HBM-bound.
+__global__ void __launch_bounds__(256)
+predict_scale_kernel(int chi, int chip, int d, const cplx* __restrict__ B, const cplx* __restrict__ A,
+                     const double* __restrict__ S, const double* __restrict__ Sinv, cplx* __restrict__ XL,
+                     cplx* __restrict__ XR) {
+    const long long total = (long long)chi * d * chip;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    {   // B[a][s][c]
+        const int c = (int)(e % chip);
+        const int a = (int)(e / ((long long)d * chip));
+        const double f = S[a] * Sinv[c];
+        const cplx x = B[e];
+        XL[e] = make_double2(f * x.x, f * x.y);
+    }
+    {   // A[c][t][b]
+        const int b = (int)(e % chi);
+        const double f = S[b];
+        const cplx x = A[e];
+        XR[e] = make_double2(f * x.x, f * x.y);
+    }
+}
+
 size_t heff_bytes(int chil, int chir, int d, int w) {
     const size_t n = (size_t)chil * d * d * chir;
     return al((size_t)w * chil * chil * sizeof(cplx)) + al((size_t)w * w * d * d * d * d * sizeof(cplx)) +
@@ -376,6 +401,31 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     if (resid_host) *resid_host = resid;
     if (n_matvec_host) *n_matvec_host = n_mv;
     return 0;
+}
+
+size_t mpsb_predict_workspace(int chi, int chip, int d) {
+    return 2 * al((size_t)chi * d * chip * sizeof(cplx));
+}
+
+int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
+                       void* theta, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(chi >= 1 && chip >= 1 && d >= 1 && A && B && S && S_prev_inv && theta, "predict_theta: bad arguments");
+    const size_t need = mpsb_predict_workspace(chi, chip, d);
+    MPSB_REQUIRE(ws && ws_bytes >= need, "predict_theta: workspace %zu B < required %zu B", ws_bytes, need);
+    cplx* XL = static_cast<cplx*>(ws);
+    cplx* XR = reinterpret_cast<cplx*>(static_cast<unsigned char*>(ws) + need / 2);
+    const long long total = (long long)chi * d * chip;
+    predict_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(chi, chip, d, static_cast<const cplx*>(B),
+                                                                          static_cast<const cplx*>(A), S, S_prev_inv, XL, XR);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    GemmArgs g;
+    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    g.A = XL; g.B = XR; g.C = static_cast<cplx*>(theta);
+    g.M = chi * d; g.N = d * chi; g.K = chip;
+    g.lda = chip; g.ldb = d * chi; g.ldc = d * chi; g.opA = 0; g.opB = 0;
+    return zgemm(g, st);
 }
 
 size_t mpsb_env_workspace(int chi, int chin, int d, int w) {

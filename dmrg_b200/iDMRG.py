@@ -149,6 +149,106 @@ def next_LR_device(Ld, Rd, Md, trunc=None, swap_conj=False, seed=0):
     return Ln, Rn, E, S
 
 
+def _overlap(a, b):
+    """<a|b> of two device tensors of equal shape: one batched 1x1 GEMM per row, summed on the host."""
+    rows = int(a.shape[0]) * int(a.shape[1])
+    cols = a.numel() // rows
+    part = _lib.empty((rows,))
+    _lib.zgemm(a.reshape(rows, cols), b.reshape(rows, cols), part, 1, 1, cols, cols, 1, 1, opA=_lib.OP_J, opB=_lib.OP_T,
+               batch1=rows, sA=(cols, 0), sB=(cols, 0), sC=(1, 0))
+    return complex(_lib.to_host(part).sum())
+
+
+class Chain:
+    """iDMRG run that keeps its matrix product state (new).
+
+    The reference's `next_LR` (`DMRG/iDMRG.py:49-61`) returns the grown environments and forgets U, S, V.  `Chain`
+    keeps them: `A` (left-orthonormal, = U), `B` (right-orthonormal, = V) and the normalised Schmidt values `S` of
+    the centre bond, plus `S_prev` of the step before.  That buys two things the reference cannot do:
+
+    * observables of the infinite chain - `to_mps()` hands the two centre sites to `dmrg_b200.MPS` (measure, corr);
+    * wavefunction prediction - every step after the second starts Lanczos from (S B) S_prev^-1 (A S) instead of
+      a random vector (`mpsb_predict_theta`), which cuts the matvec count several-fold near convergence;
+      `fidelity[-1]` = |<prediction|ground state>| is the usual iDMRG convergence measure.
+
+    Energies are the same as `next_LR`'s (the start vector does not change the eigenpair Lanczos converges to)."""
+
+    def __init__(self, M, trunc=10, L=None, R=None, swap_conj=False, seed=0, predict=True, cutoff=1e-12):
+        M = np.asarray(M)
+        w = M.shape[0]
+        if L is None:                                      # open boundaries of a lower-triangular MPO (:69-70)
+            L = np.zeros((1, 1, w), dtype=complex)
+            L[0, 0, w - 1] = 1
+        if R is None:
+            R = np.zeros((1, 1, w), dtype=complex)
+            R[0, 0, 0] = 1
+        self.M = _lib.to_device(M)
+        self.L, self.R = _lib.to_device(np.asarray(L)), _lib.to_device(np.asarray(R))
+        self.trunc, self.swap_conj, self.seed, self.predict, self.cutoff = trunc, swap_conj, seed, predict, cutoff
+        self.A = self.B = self.S = self.S_prev = None
+        self.energies, self.n_matvec, self.fidelity = [], [], []
+
+    @property
+    def n_sites(self):
+        return 2 * len(self.energies)
+
+    def _prediction(self):
+        lib = _lib.load()
+        chip, d, chi = (int(v) for v in self.A.shape)
+        if len(self.S_prev) != chip or len(self.S) != chi:
+            return None
+        inv = np.where(self.S_prev > self.cutoff * self.S_prev[0], 1.0 / np.maximum(self.S_prev, 1e-300), 0.0)
+        theta = _lib.empty((chi, d, d, chi))
+        S, Sinv = _lib.to_device(self.S, np.float64), _lib.to_device(inv, np.float64)
+        ws, wsn = _lib.workspace(lib.mpsb_predict_workspace(chi, chip, d))
+        _lib.check(lib.mpsb_predict_theta(chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S), _lib.ptr(Sinv),
+                                          _lib.ptr(theta), ws, wsn, _lib.stream_ptr()), "mpsb_predict_theta")
+        return theta
+
+    def step(self):
+        """One growth step (two sites); returns the total energy of the enlarged chain like `next_LR`."""
+        guess = self._prediction() if (self.predict and self.S_prev is not None) else None
+        E, theta = ground_state(self.L, self.M, self.R, seed=self.seed, theta0=guess)
+        self.n_matvec.append(last_info["n_matvec"])
+        if guess is not None:
+            nrm = np.sqrt(abs(_overlap(guess, guess)))
+            self.fidelity.append(abs(_overlap(guess, theta)) / nrm if nrm > 0 else 0.0)
+        sh = tuple(theta.shape)
+        U, S_all, V = _halve_public(theta, sh, self.trunc)     # one SVD with carried identity: U and V share a gauge
+        self.L = _env(True, self.L, U.contiguous(), self.M, self.swap_conj)
+        self.R = _env(False, self.R, V.contiguous(), self.M, self.swap_conj)
+        s = _lib.to_host(S_all)[:U.shape[2]]
+        self.S_prev, self.S = self.S, s / np.linalg.norm(s)
+        self.A, self.B = U.contiguous(), V.contiguous()
+        self.energies.append(E)
+        last_info["S"] = _lib.to_host(S_all)
+        return E
+
+    def run(self, n):
+        for _ in range(n):
+            self.step()
+        return self.energies[-1]
+
+    def energy_per_site(self):
+        """Bond energy (E_n - E_{n-1}) / 2: the estimate of e_inf that converges fastest with the chain length."""
+        if len(self.energies) < 2:
+            return self.energies[-1] / 2
+        return (self.energies[-1] - self.energies[-2]) / 2
+
+    def entropy(self):
+        p = self.S ** 2
+        p = p[p > 0]
+        return float(-np.sum(p * np.log(p)))
+
+    def to_mps(self):
+        """The two centre sites as a canonical `MPS` (open legs = the orthonormal block bases): site 0 = A S, site 1 = B."""
+        from .MPS import MPS
+        a = _lib.to_host(self.A) * self.S[np.newaxis, np.newaxis, :]
+        mps = MPS([a, _lib.to_host(self.B)], trun=max(int(self.trunc), len(self.S)), err=0.0)
+        mps.canon()
+        return mps
+
+
 def next_LR(L, R, M, trunc=None, swap_conj=False, seed=0):
     """One iDMRG growth step (`DMRG/iDMRG.py:49-61`): returns (L', R', E) where E is the total energy
     of the enlarged open chain.  numpy in, numpy out."""

@@ -130,6 +130,17 @@ int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U,
 int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
                    void* R_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Start vector for the next growth step from the tensors of the last one (new; the reference restarts ARPACK from a
+ * random vector at DMRG/iDMRG.py:57).  With theta_n = A S B from the last split (A [chip][d][chi] left-orthonormal,
+ * B [chi][d][chip] right-orthonormal, S [chi] normalised, all from ONE SVD so that their gauges match) and the
+ * Schmidt values S_prev [chip] of the step before,
+ *     theta[a,s,t,b] = sum_c S[a] B[a,s,c] S_prev_inv[c] A[c,t,b] S[b]          ([chi][d][d][chi], not normalised)
+ * is the two-site tensor of the enlarged chain shifted by one site (McCulloch, arXiv:0804.2509).  S_prev_inv holds
+ * 1/S_prev (0 where the caller cuts the pseudo-inverse). */
+size_t mpsb_predict_workspace(int chi, int chip, int d);
+int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
+                       void* theta, void* ws, size_t ws_bytes, void* stream);
+
 /* out[j * ldo + i] = conj?(in[i * ldi + j]) for i < rows, j < cols (layout helper of the shim). */
 int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int ldo, int conj, void* stream);
 

@@ -154,3 +154,62 @@ def test_idmrg_matches_oracle_at_chi24_with_entropy(lib):
     Sg = iDMRG.last_info["S"]
     assert abs(io_.entropy_from_S(Sg, 24) - io_.entropy_from_S(So, 24)) < 1e-8
     np.testing.assert_allclose(Sg[:12], So[:12], rtol=1e-8)
+
+
+def test_chain_prediction_same_energies_fewer_matvecs(lib, golden):
+    """the stored-state run with wavefunction prediction reproduces the reference's energies
+    (goldens of the shipped driver) while needing far fewer H_eff applications once the state settles."""
+    from dmrg_b200 import iDMRG
+    g = golden("idmrg_energies.npz")
+    W = g["W"]
+    plain = iDMRG.Chain(W, trunc=10, predict=False)
+    pred = iDMRG.Chain(W, trunc=10, predict=True)
+    for i in range(40):
+        plain.step()
+        pred.step()
+    e_ref = g["tfim_e_trunc10"] * (2 * np.arange(40) + 2)
+    np.testing.assert_allclose(plain.energies, e_ref, rtol=1e-9)
+    np.testing.assert_allclose(pred.energies, e_ref, rtol=1e-9)
+    np.testing.assert_allclose(pred.S, plain.S, rtol=1e-7, atol=1e-10)
+    assert pred.n_sites == 80 and len(pred.fidelity) == 38
+    assert pred.fidelity[-1] > 0.999 and pred.fidelity[-1] <= 1 + 1e-12
+    late_plain, late_pred = np.mean(plain.n_matvec[-10:]), np.mean(pred.n_matvec[-10:])
+    assert late_pred < 0.6 * late_plain, (late_plain, late_pred)
+
+
+def test_chain_observables_through_mps(lib):
+    """The kept A, S, B give observables of the infinite chain: the bond energy measured on the two centre sites
+    equals the energy increment per site of the growth, and the Schmidt values are those of the centre bond."""
+    from dmrg_b200 import iDMRG
+    from dmrg_b200.MPO import MPO
+    from dmrg_b200.spin import sigma
+    W = (-MPO('sx') - MPO('sz') ** 2).tomatrix()
+    ch = iDMRG.Chain(W, trunc=24)
+    ch.run(30)
+    mps = ch.to_mps()
+    assert abs(mps.dot(mps) - 1) < 1e-10
+    np.testing.assert_allclose(np.asarray(mps.s[1], dtype=float), ch.S, rtol=1e-9, atol=1e-12)
+    zz = mps.measure(0, np.kron(sigma[3], sigma[3]))
+    x0, x1 = mps.measure(0, sigma[1]), mps.measure(1, sigma[1])
+    e_bond = -zz - 0.5 * (x0 + x1)
+    assert abs(e_bond - ch.energy_per_site()) < 2e-4          # finite-chi, finite-length: both approach -4/pi
+    assert abs(e_bond + 4 / np.pi) < 2e-3
+    assert abs(x0 - x1) < 1e-4                                 # mirror symmetry of the growth
+    assert 0.3 < ch.entropy() < 1.5
+    assert abs(io_.entropy_from_S(ch.S) - ch.entropy()) < 1e-12
+
+
+def test_predict_theta_kernel(lib):
+    rs = np.random.RandomState(3)
+    chi, chip, d = 12, 7, 3
+    A, B = crand(rs, chip, d, chi), crand(rs, chi, d, chip)
+    S, Sp = np.abs(rs.randn(chi)) + 0.1, np.abs(rs.randn(chip)) + 0.1
+    L = lib.load()
+    th = lib.empty((chi, d, d, chi))
+    Ad, Bd = lib.to_device(A), lib.to_device(B)
+    Sd, Sid = lib.to_device(S, np.float64), lib.to_device(1 / Sp, np.float64)
+    ws, wsn = lib.workspace(L.mpsb_predict_workspace(chi, chip, d))
+    lib.check(L.mpsb_predict_theta(chi, chip, d, lib.ptr(Ad), lib.ptr(Bd), lib.ptr(Sd), lib.ptr(Sid), lib.ptr(th), ws, wsn,
+                                   lib.stream_ptr()), "mpsb_predict_theta")
+    ref = np.einsum('a,asc,c,ctb,b->astb', S, B, 1 / Sp, A, S)
+    np.testing.assert_allclose(lib.to_host(th), ref, atol=1e-12 * abs(ref).max())

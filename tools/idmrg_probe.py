@@ -38,3 +38,18 @@ elif which == "heis":
     Wh = (2 * MPO('P', op=spin.P()) * MPO('N', op=spin.N()) + 2 * MPO('N', op=spin.N()) * MPO('P', op=spin.P()) + MPO('sz') ** 2).tomatrix()
     for chi in [int(c) for c in sys.argv[3:]]:
         run("Heisenberg", Wh, chi, int(sys.argv[2]), 4 * (0.25 - np.log(2)))
+elif which == "chain":                       # python tools/idmrg_probe.py chain <tfim|heis> <steps> <chi> [nopredict]
+    model, steps, chi = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    if model == "heis":
+        W = (2 * MPO('P', op=spin.P()) * MPO('N', op=spin.N()) + 2 * MPO('N', op=spin.N()) * MPO('P', op=spin.P()) + MPO('sz') ** 2).tomatrix()
+    else:
+        W = (-MPO('sx') - MPO('sz') ** 2).tomatrix()
+    ch = iDMRG.Chain(W, trunc=chi, predict="nopredict" not in sys.argv)
+    for i in range(steps):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        ch.step()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        if i >= steps - 4 or i % 8 == 0:
+            fid = ch.fidelity[-1] if ch.fidelity else float('nan')
+            print(f"{model} chi={chi} step {i}: bond {ch.A.shape[2]} e_bond {ch.energy_per_site():.12f} matvecs {ch.n_matvec[-1]} "
+                  f"1-F {1 - fid:.2e} time {dt*1e3:.1f} ms", flush=True)
