@@ -104,6 +104,27 @@ def idmrg_leg(with_cpu):
             nmv.append(iDMRG.last_info["n_matvec"])
         out[f"chi{chi}"] = {"ms": 1e3 * statistics.mean(times[-6:]), "matvecs": statistics.mean(nmv[-6:]),
                             "energy_per_site_step16": E / 32}
+    # stored-state run with wavefunction prediction (dmrg_b200.iDMRG.Chain): same energies, fewer H_eff products
+    def chain_leg(Wm, chi, steps, tail):
+        ch = iDMRG.Chain(Wm, trunc=chi)
+        times = []
+        for i in range(steps):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            ch.step()
+            torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+        w, d = Wm.shape[0], Wm.shape[2]
+        nmv = statistics.mean(ch.n_matvec[-tail:])
+        sec = statistics.mean(times[-tail:])
+        flop = 8.0 * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
+        return {"ms": 1e3 * sec, "matvecs": nmv, "bond": int(ch.A.shape[2]), "one_minus_fidelity": 1 - ch.fidelity[-1],
+                "e_bond": ch.energy_per_site(), "contraction_tflops": flop / sec / 1e12}
+    for chi in (32, 128):
+        out[f"chi{chi}_predict"] = chain_leg(W, chi, 16, 6)
+    from dmrg_b200 import spin
+    Wh = (2 * MPO('P', op=spin.P()) * MPO('N', op=spin.N()) + 2 * MPO('N', op=spin.N()) * MPO('P', op=spin.P())
+          + MPO('sz') ** 2).tomatrix()
+    out["heisenberg_chi1024_predict"] = dict(chain_leg(Wh, 1024, 13, 2), model="Heisenberg (config 5), d=2, w=5, complex128 arithmetic",
+                                             note="contraction_tflops counts complex flops (SURVEY 8d F_iDMRG-step, c = 8)")
     if with_cpu:
         from threadpoolctl import threadpool_limits
         from oracle import idmrg_oracle as io_
