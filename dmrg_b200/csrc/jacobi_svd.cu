@@ -2125,7 +2125,8 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
         // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
         // to itself the 1024-thread fused kernel has half the latency (tools/tebd_small_probe.py).
-        const bool latency_mode = pl.batch <= 148 && smem <= 220 * 1024;
+        static const int latency_batch = env_int("MPSB_SVD_QR_LATENCY_BATCH", 148);
+        const bool latency_mode = pl.batch <= latency_batch && smem <= 220 * 1024;
         int grid_rc = -1;
         if (qr_enabled && pl.qr_grid) {
             SvdPlan base = pl;
