@@ -11,14 +11,23 @@
 // used, DMRG/MPS.py:451).  When U or a gauge carry is wanted the caller appends columns to the
 // work matrix (identity, or the neighbouring site tensor); they receive the same rotations.
 //
-// Pipeline per problem:  qr_precond_kernel (columns in descending-norm order; makes the row Gram
-// matrix scaled-diagonally dominant so Jacobi needs ~8 sweeps even for exponentially decaying
-// Schmidt spectra instead of 30+)  ->  jacobi_round_kernel x (sweeps x rounds)  ->  finalise_kernel
-// (row norms, bitonic sort, reference truncation rule, coalesced scatter into the MPS tensors).
+// Pipeline per call:  QR preconditioning (columns in descending-norm order; makes the row Gram matrix
+// scaled-diagonally dominant so Jacobi needs ~11 sweeps even for exponentially decaying Schmidt spectra instead
+// of 30+)  ->  Jacobi sweeps until a sweep applies no rotation  ->  finalise_kernel (row norms, bitonic sort,
+// reference truncation rule, coalesced scatter into the MPS tensors).
 //
-// Data movement: every Jacobi CTA owns two blocks of `bsz` rows; the rows are pulled into shared
-// memory with the TMA engine's 1-D bulk copy (cp.async.bulk, SASS UBLKCP) and pushed back the same
-// way.  One warp rotates one row pair: inner products by warp shuffles, rotation in place in smem.
+// Which kernels run is decided by the plan (svd_make_plan) from the batch size and the shape:
+//   QR      qr_blocked_kernel      large batches: 256 threads and ~40 KB per problem, 4 problems per SM
+//           qr_precond_kernel      batch <= 148: one SM per problem, 1024 threads (half the latency)
+//           qr_grid_kernel         <= 4 large problems: columns of each dealt out to up to 148 CTAs (cooperative)
+//   Jacobi  jacobi_cross_kernel    rounds >= 1, rows of <= 256 columns: register-resident rows, TMA-streamed partners
+//           jacobi_gram_kernel     round 0 and rows of 257-730 columns: Gram block + rotations + update on DMMA
+//           jacobi_gram_tiled_kernel   longer rows: the same through two 256-column tile buffers
+//           jacobi_resident_kernel     tiny problems in small batches: whole matrix in shared memory, one launch
+//           jacobi_round_kernel<B>     generic fallback (any block size, rows that fit shared memory)
+//
+// Data movement: rows travel between global and shared memory with the TMA engine's 1-D bulk copy
+// (cp.async.bulk, SASS UBLKCP) completing on mbarriers.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
