@@ -123,6 +123,12 @@ def idmrg_leg(with_cpu):
     from dmrg_b200 import spin
     Wh = (2 * MPO('P', op=spin.P()) * MPO('N', op=spin.N()) + 2 * MPO('N', op=spin.N()) * MPO('P', op=spin.P())
           + MPO('sz') ** 2).tomatrix()
+    ss = sum(np.kron(a, a) for a in spin.S(1)[1:])
+    from dmrg_b200.MPO import two_site_mpo
+    Wa = two_site_mpo((ss + ss @ ss / 3).real, 3).astype(complex)
+    ak = chain_leg(Wa, 64, 10, 3)
+    ak.update(model="AKLT spin-1 (config 2), d=3, w=%d" % Wa.shape[0], e_bond_error=abs(ak["e_bond"] + 2.0 / 3.0))
+    out["aklt_chi64_predict"] = ak
     out["heisenberg_chi1024_predict"] = dict(chain_leg(Wh, 1024, 13, 2), model="Heisenberg (config 5), d=2, w=5, complex128 arithmetic",
                                              note="contraction_tflops counts complex flops (SURVEY 8d F_iDMRG-step, c = 8)")
     if with_cpu:
@@ -138,6 +144,29 @@ def idmrg_leg(with_cpu):
         out["cpu_chi32"] = {"ms": 1e3 * statistics.mean(t[-2:]), "kind": "port (matrix-free numpy + ARPACK, 1 process, 1 BLAS thread)",
                             "note": "the reference's own next_LR builds the dense 4096^2 H_eff: 9-12 s per step (SURVEY section 6)"}
     return out
+
+
+def tebd_chain_leg():
+    """BASELINE config 3 shape: ONE chain, L = 128, chi = 128, d = 2 - every half sweep is a batch of 63/64 saturated
+    bonds through MPS.iTEBD_double (random canonical state, TFIM gate); ms per Trotter step = two half sweeps."""
+    import torch
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200.spin import sigma
+    rs = np.random.RandomState(7)
+    Lc = 128
+    x = [min(2 ** i, 2 ** (Lc - i), CHI) for i in range(Lc + 1)]
+    s = MPS([rs.randn(x[i], D, x[i + 1]) + 1j * rs.randn(x[i], D, x[i + 1]) for i in range(Lc)], trun=CHI, err=1e-14)
+    s.canon()
+    Z, X, I2 = sigma[3], sigma[1], np.eye(2)
+    Hb = -np.kron(Z, Z) - 0.5 * (np.kron(X, I2) + np.kron(I2, X))
+    s.iTEBD_double(Hb, 0.05, 1)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    k = 4
+    s.iTEBD_double(Hb, 0.05 * k, k)
+    torch.cuda.synchronize(); el = time.perf_counter() - t0
+    return {"workload": "one chain L=128 chi=128 d=2, iTEBD_double (2nd order), all bonds saturated",
+            "ms_per_trotter_step": 1e3 * el / k, "bond_updates_per_s": (2 * k + 1) * (Lc - 1) / 2 / el,
+            "max_bond": int(s.x.max())}
 
 
 def run_reference(args):
@@ -369,6 +398,7 @@ def main():
             "hbm_peak_gbs": peaks.get("hbm_gbs")}
     if world == 1 and not args.no_idmrg:
         line["idmrg"] = idmrg_leg(not args.no_cpu)
+        line["tebd_chain"] = tebd_chain_leg()
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(args.cpu_updates)
     print(json.dumps(line))

@@ -42,6 +42,18 @@ namespace {
 constexpr int QR_THREADS = 1024;
 constexpr int FIN_THREADS = 256;
 
+// The convergence test |x_p . x_q|^2 > tol^2 |x_p|^2 |x_q|^2 is relative, so that small singular values keep their
+// relative accuracy.  Its right-hand side underflows for rows at the 1e-80 level (products of Schmidt values that are
+// themselves rounding noise reach 1e-260 in an iDMRG run on a rank-deficient state): such pairs would rotate for ever.
+// PAIR_FLOOR is added to the threshold (folded into the FMA that forms it, so it costs nothing): pairs with
+// |x_p|^2 |x_q|^2 below ~1e-260 are left alone, and finalise_kernel emits rows with |x|^2 <= ROW_DEAD as zero vectors
+// (singular values 1e-62 below the scale of a normalised state carry no information).
+constexpr double PAIR_FLOOR = 1e-290;
+// Householder columns with |x|^2 at or below this are treated as zero columns: tau = 2 / (v^H v) would overflow for
+// a subnormal norm (LAPACK's zlarfg rescales instead; here such a column is 1e-145 below a normalised state).
+constexpr double QR_TINY = 1e-290;
+constexpr double ROW_DEAD = 1e-125;    // tol^2 * ROW_DEAD^2 stays well above PAIR_FLOOR: every pair of live rows is tested relatively
+
 struct SvdState {           // device scratch, carved out of the caller's workspace
     int* rot;               // [batch] rotations applied in the current sweep
     int* done;              // [batch] 1 once a sweep applied no rotation
@@ -204,7 +216,7 @@ qr_precond_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
         const double sigma = block_sum(loc, red);          // contains the barriers that order vcur[k] reads
         const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
         const double normx2 = a2 + sigma;
-        if (!(normx2 > 0.0)) {                              // zero column: no reflector, the pending one stays pending
+        if (!(normx2 > QR_TINY)) {                              // zero column: no reflector, the pending one stays pending
             for (int i = k + tid; i < n; i += NT) X[(size_t)i * ld + pc] = make_double2(0.0, 0.0);
             if (tid == 0) colDone[pc] = 1;
             __syncthreads();
@@ -425,7 +437,7 @@ qr_grid_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, int 
             const double sigma = block_sum(loc, red);
             const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
             const double normx2 = a2 + sigma;
-            if (!(normx2 > 0.0)) {
+            if (!(normx2 > QR_TINY)) {
                 for (int i = k + tid; i < n; i += QG_THREADS) X[(size_t)i * ld + pc] = make_double2(0.0, 0.0);
                 if (tid == 0) { meta[cu].tau = 0.0; meta[cu].valid = 0; colDone[pc - c_lo] = 1; }
             } else {
@@ -644,7 +656,7 @@ qr_blocked_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
             const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
             const double normx2 = a2 + sigma;
             __syncthreads();                                   // everybody has read alpha / row kb
-            if (!(normx2 > 0.0)) {                             // zero column: identity reflector
+            if (!(normx2 > QR_TINY)) {                             // zero column: identity reflector
                 if (tid == 0) { taus[b] = 0.0; vdiag[b] = make_double2(0.0, 0.0); betas[b] = make_double2(0.0, 0.0); }
                 __syncthreads();
                 continue;
@@ -848,7 +860,7 @@ __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restric
         const double a = warp_sum(a0 + a1), b = warp_sum(b0 + b1);
         const double cr = warp_sum(cr0 + cr1), ci = warp_sum(ci0 + ci1);
         const double ac2 = cr * cr + ci * ci;
-        if (!(ac2 > tol2 * a * b)) return 0;
+        if (!(ac2 > fma(tol2 * a, b, PAIR_FLOOR))) return 0;
         double cs, gr, gi;
         jacobi_angle(a, b, cr, ci, ac2, cs, gr, gi);
 #pragma unroll
@@ -876,7 +888,7 @@ __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restric
     }
     a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
     const double ac2 = cr * cr + ci * ci;
-    if (!(ac2 > tol2 * a * b)) return 0;
+    if (!(ac2 > fma(tol2 * a, b, PAIR_FLOOR))) return 0;
     double cs, gr, gi;
     jacobi_angle(a, b, cr, ci, ac2, cs, gr, gi);
     for (int c = lane; c < ltot_r; c += 32) {
@@ -1042,7 +1054,7 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
     }
     const double crs = warp_sum(cr0 + cr1), cis = warp_sum(ci0 + ci1);      // scaled inner product x_p . x_q^H
     const double ac2 = r.e * eq * fma(crs, crs, cis * cis);                  // |c|^2 of the true rows
-    if (!(ac2 > tol2 * r.a * bq)) return 0;
+    if (!(ac2 > fma(tol2 * r.a, bq, PAIR_FLOOR))) return 0;
     // t/|c| = sgn(z) / (|z| + sqrt(z^2 + |c|^2)) from MUFU seeds + one Newton step each; the tangent may be
     // 1e-12 off without harm because ...
     const double z = 0.5 * (bq - r.a);
@@ -1277,7 +1289,7 @@ __device__ __forceinline__ int gram_tournament(GramSmem& sm, int nsteps, double 
             const cplx c = sm.G[p][q];
             const double ac2 = c.x * c.x + c.y * c.y;
             double cs = 1.0, gr = 0.0, gi = 0.0;
-            if (ac2 > tol2 * a * b) {
+            if (ac2 > fma(tol2 * a, b, PAIR_FLOOR)) {
                 jacobi_angle_fast(a, b, c.x, c.y, ac2, cs, gr, gi);
                 ++my_rot;
             }
@@ -1672,7 +1684,7 @@ __device__ __forceinline__ int rotate_rows(cplx* __restrict__ P, cplx* __restric
     }
     a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
     const double ac2 = cr * cr + ci * ci;
-    if (!(ac2 > tol2 * a * b)) return 0;
+    if (!(ac2 > fma(tol2 * a, b, PAIR_FLOOR))) return 0;
     double cs, gr, gi;
     jacobi_angle(a, b, cr, ci, ac2, cs, gr, gi);
 #pragma unroll
@@ -1855,7 +1867,7 @@ finalise_kernel(const cplx* __restrict__ Xall, long long strideX, int n, int n_p
             o.s_raw[(size_t)mat * o.s_raw_stride + i] = (i < nsv) ? sqrt(fmax(key[i], 0.0)) : 0.0;
     const int naug = ltot - ldot;
     for (int i = warp; i < o.k_cap; i += nw) {
-        const bool keep = i < k && key[i] > 0.0;
+        const bool keep = i < k && key[i] > ROW_DEAD;
         const cplx* row = X + (size_t)(keep ? idx[i] : 0) * ld;
         const double inv = keep ? 1.0 / sqrt(key[i]) : 0.0;
         if (o.vh) {

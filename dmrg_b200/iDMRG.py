@@ -197,9 +197,12 @@ class Chain:
         chip, d, chi = (int(v) for v in self.A.shape)
         if len(self.S_prev) != chip or len(self.S) != chi:
             return None
+        # Schmidt values that are rounding noise (rank-deficient states: AKLT keeps 4 of 64) are cut on BOTH bonds:
+        # the guess then has exact zeros on the dead states instead of products of noise that underflow step by step.
         inv = np.where(self.S_prev > self.cutoff * self.S_prev[0], 1.0 / np.maximum(self.S_prev, 1e-300), 0.0)
+        cur = np.where(self.S > self.cutoff * self.S[0], self.S, 0.0)
         theta = _lib.empty((chi, d, d, chi))
-        S, Sinv = _lib.to_device(self.S, np.float64), _lib.to_device(inv, np.float64)
+        S, Sinv = _lib.to_device(cur, np.float64), _lib.to_device(inv, np.float64)
         ws, wsn = _lib.workspace(lib.mpsb_predict_workspace(chi, chip, d))
         _lib.check(lib.mpsb_predict_theta(chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S), _lib.ptr(Sinv),
                                           _lib.ptr(theta), ws, wsn, _lib.stream_ptr()), "mpsb_predict_theta")

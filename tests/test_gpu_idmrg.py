@@ -213,3 +213,20 @@ def test_predict_theta_kernel(lib):
                                    lib.stream_ptr()), "mpsb_predict_theta")
     ref = np.einsum('a,asc,c,ctb,b->astb', S, B, 1 / Sp, A, S)
     np.testing.assert_allclose(lib.to_host(th), ref, atol=1e-12 * abs(ref).max())
+
+
+def test_chain_prediction_on_rank_deficient_state(lib):
+    """AKLT at chi = 64 (config 2): the state has Schmidt rank 4, the other 60 kept values are noise.  The prediction
+    must not feed products of noise back into the solver (regression: energies went wild at step 6)."""
+    from dmrg_b200 import iDMRG, spin
+    from dmrg_b200.MPO import two_site_mpo
+    ss = sum(np.kron(a, a) for a in spin.S(1)[1:])
+    W = two_site_mpo((ss + ss @ ss / 3).real, 3)
+    ch = iDMRG.Chain(W, trunc=64)
+    for i in range(12):
+        ch.step()
+        if i >= 2:
+            assert abs(ch.energy_per_site() + 2 / 3) < 1e-9, (i, ch.energy_per_site())
+    p = ch.S ** 2
+    assert np.sum(p[:4]) > 1 - 1e-12
+    assert ch.fidelity[-1] > 1 - 1e-6

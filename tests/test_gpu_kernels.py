@@ -346,3 +346,33 @@ def test_svd_resident_small_batches(lib):
             np.testing.assert_allclose(lib.to_host(sraw)[b], ref, rtol=1e-10, atol=1e-14 * ref[0])
             v = lib.to_host(vh)[b]
             np.testing.assert_allclose(v @ v.conj().T, np.eye(k), atol=1e-11)
+
+
+def test_svd_rows_at_underflow_scale(lib):
+    """Rows 60 to 250 decades below the leading ones (products of noise-level Schmidt values in an iDMRG run on a
+    rank-deficient state) must neither spin the relative convergence test for ever nor come back as unnormalised
+    junk: live rows stay orthonormal, rows below 1e-62 of the scale come back as zero vectors."""
+    from dmrg_b200.MPS import _device_svd
+    rs = np.random.RandomState(11)
+    n = 96
+    expo = np.concatenate([[0, 0, 3, 3, 20, 40, 55], [70, 100, 130, 160, 200, 250], np.full(n - 13 - 20, 300.0)])
+    scale = np.concatenate([10.0 ** (-expo), np.zeros(20)])
+    m = scale[:, None] * crand(rs, n, n)
+    md = lib.to_device(m)
+    for want_u in (False, True):
+        u, s_all, vh, k = _device_svd(md, n, n, 64, 0.0, want_u=want_u, normalise=0)
+        assert lib.load().mpsb_last_svd_sweeps() < 25
+        s = lib.to_host(s_all)
+        v = lib.to_host(vh)
+        live = s[:k] > 1e-60
+        assert live.sum() == 7
+        g = v[live] @ v[live].conj().T
+        np.testing.assert_allclose(g, np.eye(7), atol=1e-11)
+        ref = la.svd(m, compute_uv=False)
+        np.testing.assert_allclose(s[:4], ref[:4], rtol=1e-10)
+        dead = s[:k] < 1e-63
+        assert dead.sum() >= 50 and np.all(v[dead] == 0)
+        if want_u:
+            uu = lib.to_host(u)
+            np.testing.assert_allclose(uu[:, live].conj().T @ uu[:, live], np.eye(7), atol=1e-11)
+            np.testing.assert_allclose((uu[:, live] * s[:k][live]) @ v[live], m, atol=1e-12)
