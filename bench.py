@@ -221,6 +221,7 @@ def main():
     from dmrg_b200 import _lib as L
     lib = L.load()
     import ctypes
+    numa_cpus = L.bind_host_thread_to_gpu() if world > 1 else None     # pinned buffers on the GPU's NUMA node
 
     n = args.chains
     Bi_h, Bj_h, Sl_h, U_h = make_inputs(n, 1000 + rank * n)
@@ -384,7 +385,8 @@ def main():
                        "chains_per_gpu": n, "chi": CHI, "d": D,
                        "inputs": "right-isometric B tensors, Gaussian Schmidt spectrum, per-chain GUE gate dt=0.05",
                        "l2": f"inputs {2 * n * site * 16 / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)",
-                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
+                       "host_thread_bound_to_gpu_numa_node": bool(numa_cpus)},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},

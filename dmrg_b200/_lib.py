@@ -102,6 +102,30 @@ def device():
     return t.device("cuda", t.cuda.current_device())
 
 
+def bind_host_thread_to_gpu():
+    """Pin the calling host thread to the CPUs next to the current GPU (NVML's ideal affinity), so that pinned host
+    buffers allocated afterwards live on that NUMA node.  Multi-GPU runs that stream host-resident batches
+    (`batched.HostBondUpdater`) otherwise push half of their PCIe traffic across the socket interconnect.  Returns
+    the CPU set chosen, or None when NVML is unavailable (the call is then a no-op)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        t = torch()
+        uuid = str(t.cuda.get_device_properties(t.cuda.current_device()).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def stream_ptr():
     return _c.c_void_p(torch().cuda.current_stream().cuda_stream)
 
