@@ -369,14 +369,19 @@ class MPS:
     # ---- updates -----------------------------------------------------------------------------------------------
     def update_single(self, U, i, unitary=True):
         """M[i][l,e,r] = sum_c U[e,c] M[i][l,c,r] (DMRG/MPS.py:413-425)."""
-        self._flush()
-        t = self._dev[i]
-        xl, d, xr = (int(v) for v in t.shape)
-        Ud = _lib.to_device(U)
-        _lib.check(_lib.load().mpsb_one_site(1, xl, xr, d, _lib.ptr(t), 0, _lib.ptr(Ud), 0, _lib.ptr(t), 0,
-                                             _lib.stream_ptr()), "mpsb_one_site")
+        self._apply_one_site(_lib.to_device(U), [i])
         if not unitary:
             self.ortho_left_site(i)
+
+    def _apply_one_site(self, U_dev, sites):
+        """The same one-site gate (already on the device) on several sites: one upload, one launch per site."""
+        self._flush()
+        lib = _lib.load()
+        for i in sites:
+            t = self._dev[i]
+            xl, d, xr = (int(v) for v in t.shape)
+            _lib.check(lib.mpsb_one_site(1, xl, xr, d, _lib.ptr(t), 0, _lib.ptr(U_dev), 0, _lib.ptr(t), 0,
+                                         _lib.stream_ptr()), "mpsb_one_site")
 
     def update_double(self, U, i, unitary=True):
         """Two-site gate on sites (i, i+1) with SVD truncation (DMRG/MPS.py:428-457)."""

@@ -111,16 +111,12 @@ class BMPS(MPS):
             return worker
 
         def single(k):
-            U1 = la.expm(-1j * (self.omega0 * self.N - (self.K / 2) * self.N ** 2) * k * t)
-
-            def _single():
-                for i in range(self.l):
-                    self.update_single(U1, i)
-            return _single
+            U1 = _lib.to_device(la.expm(-1j * (self.omega0 * self.N - (self.K / 2) * self.N ** 2) * k * t))
+            return lambda: self._apply_one_site(U1, range(self.l))
 
         def tail(k):
-            U2 = la.expm(-1j * self.u * self.Ht * k * t)
-            return lambda: self.update_single(U2, self.l)
+            U2 = _lib.to_device(la.expm(-1j * self.u * self.Ht * k * t))
+            return lambda: self._apply_one_site(U2, [self.l])
 
         def coupling(k):
             mpo = self.MPO(k * t)
