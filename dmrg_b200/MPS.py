@@ -455,8 +455,39 @@ class MPS:
                 self.Sr[i] = sr[b, :k].copy()
 
     def update_k(self, U, i, k, unitary=True):
-        """General multiple sites update (not implemented in the reference either, DMRG/MPS.py:459-461)."""
-        raise NotImplementedError
+        """Gate on the k neighbouring sites i .. i+k-1 (declared in the reference, DMRG/MPS.py:459-461, where it raises
+        NotImplementedError).  U has 2k legs of size d, outputs first - the convention of `update_double`
+        (U[a,b,c,j] = <a b|U|c j>, :445) - or is the d^k x d^k matrix.  The k-site tensor is formed by GEMMs, the
+        gate acts on the fused physical leg, and sites are split off from the right exactly as `update_double` does
+        it (:446-455): SVD of Lambda_l * theta, B' = Vh, the rest = theta . Vh^H, k-1 times."""
+        d = self.dim
+        if k == 1:
+            return self.update_single(np.asarray(U).reshape(d, d), i, unitary)
+        assert k >= 2 and i + k <= self.L, "sites out of range"
+        lib = _lib.load()
+        D = d ** k
+        Um = _lib.to_device(np.asarray(U).reshape(D, D))
+        blk = self._block_dev(i, k)                                   # B_i ... B_{i+k-1} as [xl, d^k, xr]
+        xl, xr = int(blk.shape[0]), int(blk.shape[2])
+        T = _lib.empty((xl, D, xr))
+        _lib.zgemm(Um, blk, T, D, xr, D, D, xr, xr, batch1=xl, sB=(D * xr, 0), sC=(D * xr, 0))
+        sl = self._schmidt(i)
+        cur = xr
+        for j in range(k - 1, 0, -1):                                 # split site i+j off the right end
+            rows, cols = xl * d ** j, d * cur
+            Tm = T.reshape(rows, cols)
+            m = _lib.empty((rows, cols))
+            _lib.check(lib.mpsb_scale_rows(rows, cols, _lib.ptr(Tm), cols, _lib.ptr(sl), d ** j, _lib.ptr(m), cols,
+                                           _lib.stream_ptr()), "mpsb_scale_rows")
+            _, s, vh, kk = _device_svd(m, rows, cols, self.trun, self.err, want_u=False)
+            self._dev[i + j] = vh.reshape(kk, d, cur).contiguous()
+            self.x[i + j] = kk
+            self.s[i + j] = _lib.to_host(s)
+            T = _lib.matmul(Tm, vh.contiguous(), opB=_lib.OP_C)       # theta . Vh^H: [xl * d^j, kk]
+            cur = kk
+        self._dev[i] = T.reshape(xl, d, cur)
+        if not unitary:
+            self.ortho_left_site(i + k - 1)
 
     def iTEBD_double(self, H, t, n, order=2):
         """Second-order Suzuki-Trotter evolution exp(-i H t) with n slices for a nearest-neighbour two-site

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mpsb_mpo_site": (_i, [_i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),
     "mpsb_predict_workspace": (_sz, [_i, _i, _i]),
     "mpsb_predict_theta": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mpsb_scale_rows": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "mpsb_transpose": (_i, [_i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "mpsb_gauge_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "mpsb_gauge_left": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

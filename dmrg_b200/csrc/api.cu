@@ -249,6 +249,13 @@ int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int l
                           static_cast<cudaStream_t>(stream));
 }
 
+int mpsb_scale_rows(int rows, int cols, const void* in, int ldi, const double* s, int group, void* out, int ldo,
+                    void* stream) {
+    MPSB_REQUIRE(in && s && out, "scale_rows: null buffer");
+    return scale_rows(rows, cols, static_cast<const cplx*>(in), ldi, s, group, static_cast<cplx*>(out), ldo,
+                      static_cast<cudaStream_t>(stream));
+}
+
 int mpsb_one_site(int batch, int chil, int chir, int d, const void* M, long long sM, const void* U, long long sU,
                   void* M_out, long long sMo, void* stream) {
     return one_site(batch, chil, chir, d, static_cast<const cplx*>(M), sM, static_cast<const cplx*>(U), sU,

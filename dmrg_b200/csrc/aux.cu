@@ -171,6 +171,29 @@ int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int l
     return 0;
 }
 
+// out[i][j] = s[i / group] * in[i][j]: the Lambda_l scaling of a (chi_l * group) x cols matrix view (DMRG/MPS.py:446).
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(int rows, int cols, const cplx* __restrict__ in, int ldi, const double* __restrict__ s, int group,
+                  cplx* __restrict__ out, int ldo) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)rows * cols) return;
+    const int i = (int)(e / cols), j = (int)(e - (long long)i * cols);
+    const double f = s[i / group];
+    const cplx x = in[(size_t)i * ldi + j];
+    out[(size_t)i * ldo + j] = make_double2(f * x.x, f * x.y);
+}
+
+int scale_rows(int rows, int cols, const cplx* in, int ldi, const double* s, int group, cplx* out, int ldo,
+               cudaStream_t st) {
+    MPSB_REQUIRE(rows >= 0 && cols >= 0 && group >= 1, "scale_rows: bad dims");
+    const long long total = (long long)rows * cols;
+    if (total == 0) return 0;
+    scale_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rows, cols, in, ldi, s, group, out, ldo);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int perm_last_to_first(const cplx* in, int n_ab, int n_c, cplx* out, cudaStream_t st) {
     return transpose_conj(in, n_c, n_ab, n_c, out, n_ab, 0, st);
 }

@@ -104,6 +104,9 @@ int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, c
                      int identity, cudaStream_t st);
 // out[j * ldo + i] = conj?(in[i * ldi + j]),  i < rows, j < cols
 int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st);
+// out[i][j] = s[i / group] * in[i][j]
+int scale_rows(int rows, int cols, const cplx* in, int ldi, const double* s, int group, cplx* out, int ldo,
+               cudaStream_t st);
 // out[c][a][b] = in[a][b][c]  (n_ab = a*b merged)   and the inverse
 int perm_last_to_first(const cplx* in, int n_ab, int n_c, cplx* out, cudaStream_t st);
 int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_t st);

@@ -141,6 +141,12 @@ size_t mpsb_predict_workspace(int chi, int chip, int d);
 int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
                        void* theta, void* ws, size_t ws_bytes, void* stream);
 
+/* out[i * ldo + j] = s[i / group] * in[i * ldi + j]: the Lambda_l scaling `self.Sl[i][:, newaxis, ...] * theta`
+ * (DMRG/MPS.py:446) of a tensor viewed as a (chi_l * group) x cols matrix.  Used by the multi-site update
+ * (MPS.update_k, DMRG/MPS.py:459-461), whose splits have unequal local dimensions on the two sides. */
+int mpsb_scale_rows(int rows, int cols, const void* in, int ldi, const double* s, int group, void* out, int ldo,
+                    void* stream);
+
 /* out[j * ldo + i] = conj?(in[i * ldi + j]) for i < rows, j < cols (layout helper of the shim). */
 int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int ldo, int conj, void* stream);
 

@@ -132,6 +132,36 @@ class OracleMPS:
         if not unitary:
             self.ortho_left_site(i + 1)
 
+    def update_k(self, U, i, k):
+        """k-site gate (declared at DMRG/MPS.py:459-461, NotImplemented there): the scheme of `update_double`
+        (:445-455) applied k-1 times from the right.  For k = 2 this IS update_double."""
+        d = self.dim
+        D = d ** k
+        theta = self.M[i]
+        for j in range(1, k):
+            theta = np.tensordot(theta, self.M[i + j], axes=([theta.ndim - 1], [0]))
+        xl, xr = theta.shape[0], theta.shape[-1]
+        T = np.einsum('ac,lcr->lar', np.asarray(U).reshape(D, D), theta.reshape(xl, D, xr))
+        cur = xr
+        for j in range(k - 1, 0, -1):
+            Tm = T.reshape(xl * d ** j, d * cur)
+            m = (np.repeat(self.s[i], d ** j)[:, None]) * Tm
+            _, s, vh = svd_truncate(m, self.trun, self.err)
+            kk = len(s)
+            self.M[i + j] = vh.reshape(kk, d, cur)
+            self.x[i + j] = kk
+            self.s[i + j] = s
+            T = Tm @ vh.conj().T
+            cur = kk
+        self.M[i] = T.reshape(xl, d, cur)
+
+    def to_dense(self):
+        """Full state vector psi[c_0 .. c_{L-1}] of a chain with trivial outer bonds (test helper)."""
+        psi = self.s[0][:, None, None] * self.M[0]
+        for j in range(1, self.L):
+            psi = np.tensordot(psi, self.M[j], axes=([psi.ndim - 1], [0]))
+        return psi.reshape(-1)
+
     def half_sweep(self, U, parity):
         """Body of `_even_update` / `_odd_update`, DMRG/MPS.py:479-480, 487-488."""
         for i in range(parity, self.L - 1, 2):

@@ -309,3 +309,62 @@ def test_non_unitary_update_branch(lib):
     e_gpu = sum(s.measure(i, Hb) for i in range(L - 1))
     e_ora = sum(o.measure(i, Hb) for i in range(L - 1))
     assert abs(e_gpu - e_ora) < 1e-10
+
+
+def test_update_k_multi_site_gates(lib):
+    """`update_k` (NotImplementedError in the reference, DMRG/MPS.py:459-461) against the oracle's
+    restatement (itself checked against dense state vectors in tests/test_oracle.py) - Schmidt values on every bond,
+    overlap with the oracle state, and k = 2 identical to update_double."""
+    from dmrg_b200.MPS import MPS
+    rs = np.random.RandomState(4)
+    L, d = 6, 2
+    chis = [1, 2, 4, 8, 4, 2, 1]
+    tens = [rs.randn(chis[j], d, chis[j + 1]) + 1j * rs.randn(chis[j], d, chis[j + 1]) for j in range(L)]
+    for k, i in [(2, 1), (3, 0), (3, 2), (4, 1), (1, 3)]:
+        D = d ** k
+        A = rs.randn(D, D) + 1j * rs.randn(D, D)
+        U = la.expm(-0.3j * (A + A.conj().T)).reshape([d] * (2 * k))
+        g = MPS([t.copy() for t in tens], trun=64, err=1e-14)
+        g.canon()
+        o = OracleMPS([t.copy() for t in tens], trun=64, err=1e-14)
+        o.canon()
+        g.update_k(U, i, k)
+        if k == 1:
+            o.update_single(U, i)
+        else:
+            o.update_k(U, i, k)
+        assert [int(v) for v in g.x] == [int(v) for v in o.x]
+        for b in range(L + 1):
+            np.testing.assert_allclose(np.asarray(g.s[b], dtype=float), o.s[b], rtol=1e-10, atol=1e-13)
+        ref = MPS([np.array(m) for m in o.M[:L]], trun=64, err=1e-14)      # oracle state as a device MPS (B form, s[0] = 1)
+        ref.s = np.array([np.asarray(v) for v in o.s] , dtype=object)
+        assert abs(abs(g.dot(ref)) - 1) < 1e-11
+        if k == 2:
+            h = MPS([t.copy() for t in tens], trun=64, err=1e-14)
+            h.canon()
+            h.update_double(U, i)
+            for b in range(L + 1):
+                np.testing.assert_allclose(np.asarray(g.s[b], dtype=float), np.asarray(h.s[b], dtype=float), rtol=1e-10, atol=1e-13)
+    # d = 3, three sites, truncation active
+    rs = np.random.RandomState(8)
+    chis = [1, 3, 6, 6, 3, 1]
+    tens = [rs.randn(chis[j], 3, chis[j + 1]) + 1j * rs.randn(chis[j], 3, chis[j + 1]) for j in range(5)]
+    A = rs.randn(27, 27) + 1j * rs.randn(27, 27)
+    U = la.expm(-0.2j * (A + A.conj().T))
+    g = MPS([t.copy() for t in tens], dim=3, trun=5, err=1e-8)
+    o = OracleMPS([t.copy() for t in tens], trun=5, err=1e-8)
+    g.canon(); o.canon()
+    g.update_k(U, 1, 3); o.update_k(U, 1, 3)
+    assert [int(v) for v in g.x] == [int(v) for v in o.x]
+    for b in range(6):
+        np.testing.assert_allclose(np.asarray(g.s[b], dtype=float), o.s[b], rtol=1e-10, atol=1e-13)
+
+
+def test_scale_rows_kernel(lib):
+    rs = np.random.RandomState(1)
+    a = rs.randn(12, 7) + 1j * rs.randn(12, 7)
+    s = np.abs(rs.randn(4)) + 0.1
+    out = lib.empty((12, 7))
+    ad, sd = lib.to_device(a), lib.to_device(s, np.float64)
+    lib.check(lib.load().mpsb_scale_rows(12, 7, lib.ptr(ad), 7, lib.ptr(sd), 3, lib.ptr(out), 7, lib.stream_ptr()), "scale")
+    np.testing.assert_allclose(lib.to_host(out), np.repeat(s, 3)[:, None] * a, rtol=1e-15)

@@ -158,3 +158,29 @@ def test_bmps_free_hopping_keeps_coherent_product():
     A = np.diag(np.ones(5), 1) + np.diag(np.ones(5), -1)
     ct = la.expm(-1j * 0.4 * A) @ c0
     np.testing.assert_allclose(o.occupations()[:6], abs(ct) ** 2, atol=2e-5)     # Trotter error O(dt^2) + cutoff
+
+
+def test_oracle_update_k_against_dense_state():
+    """k-site gates: k = 2 is update_double; k = 3, 4 reproduce the exactly evolved state vector."""
+    rs = np.random.RandomState(4)
+    L, d = 6, 2
+    chis = [1, 2, 4, 8, 4, 2, 1]
+    tens = [rs.randn(chis[j], d, chis[j + 1]) + 1j * rs.randn(chis[j], d, chis[j + 1]) for j in range(L)]
+    base = OracleMPS(tens, trun=64, err=1e-14)
+    base.canon()
+    for k, i in [(2, 1), (3, 0), (3, 2), (4, 1)]:
+        D = d ** k
+        A = rs.randn(D, D) + 1j * rs.randn(D, D)
+        U = la.expm(-0.3j * (A + A.conj().T))
+        a = base.copy()
+        psi0 = a.to_dense()
+        a.update_k(U.reshape([d] * (2 * k)), i, k)
+        full = np.kron(np.kron(np.eye(d ** i), U), np.eye(d ** (L - i - k)))
+        np.testing.assert_allclose(a.to_dense(), full @ psi0, atol=1e-13)
+        for b in range(L + 1):
+            assert abs(la.norm(a.s[b]) - 1) < 1e-13
+        if k == 2:
+            b2 = base.copy()
+            b2.update_double(U.reshape([d] * 4), i)
+            for b in range(L + 1):
+                np.testing.assert_allclose(a.s[b], b2.s[b], atol=1e-14)
