@@ -3,4 +3,4 @@
 Importing the package is free of side effects; the CUDA library (`libmps_b200.so`, built in-tree by
 `__graft_entry__.build()`) is loaded on first use and there is no CPU fallback.
 """
-__all__ = ['MPS', 'spin', 'Ising', 'ST', 'iDMRG', 'MPO', 'AKLT', 'batched']
+__all__ = ['MPS', 'spin', 'Ising', 'ST', 'iDMRG', 'DMRG', 'MPO', 'AKLT', 'batched', 'transmit']

@@ -303,8 +303,55 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
     double t_enq = 0.0, t_wait = 0.0, t_host = 0.0;
     auto now = [] { return std::chrono::high_resolution_clock::now(); };
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    // Convergence is also polled inside the FIRST cycle (after 4 steps, then every 8: one small download and a host
+    // eigen-solve of the projected matrix, ~0.1 ms).  A start vector that is already the answer - finite-DMRG sweeps
+    // after the first - then costs a few products instead of a whole 24-step cycle.  Later cycles run to their end:
+    // stopping them the moment the tolerance is met was measured to cost more products over an iDMRG run (each step
+    // then starts from a slightly less converged prediction).
+    static const int poll_env = getenv("MPSB_LANCZOS_POLL") ? atoi(getenv("MPSB_LANCZOS_POLL")) : 1;
+    int mm = m;
+    double beta_last = 0.0;
+    std::vector<int> idx;
+    // Ritz data of the basis V[0 .. formed): fills T (eigenvalues on the diagonal), Y, idx (ascending), E, resid, mm.
+    auto evaluate = [&](int formed) -> int {
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(h1.data(), C1, sizeof(cplx) * kk * formed, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(h2.data(), C2, sizeof(cplx) * kk * formed, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx) * formed, cudaMemcpyDeviceToHost, st));
+        auto tb = now();
+        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+        auto tc = now();
+        t_wait += us(tb, tc);
+        mm = formed;
+        beta_last = 0.0;
+        for (int j = j0; j < formed; ++j) {
+            for (int i = 0; i <= j; ++i) {
+                const double v = h1[(size_t)j * kk + i].x + h2[(size_t)j * kk + i].x;
+                Hp[(size_t)i * m + j] = v;
+                Hp[(size_t)j * m + i] = v;
+            }
+            const double bj = std::sqrt(hn[j].x > 0.0 ? hn[j].x : 0.0);
+            beta_last = bj;
+            if (j + 1 < m) { Hp[(size_t)(j + 1) * m + j] = bj; Hp[(size_t)j * m + j + 1] = bj; }
+            if (!(bj > 1e-14 * (std::fabs(Hp[0]) + 1e-300)) || !std::isfinite(bj)) { mm = j + 1; break; }
+        }
+        T.assign((size_t)mm * mm, 0.0);
+        for (int i = 0; i < mm; ++i)
+            for (int q = 0; q < mm; ++q) T[(size_t)i * mm + q] = Hp[(size_t)i * m + q];
+        sym_eig_host(mm, T, Y);
+        idx.resize(mm);
+        for (int i = 0; i < mm; ++i) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return T[(size_t)a * mm + a] < T[(size_t)b * mm + b]; });
+        const int best = idx[0];
+        E = T[(size_t)best * mm + best];
+        resid = std::fabs(beta_last * Y[(size_t)(mm - 1) * mm + best]);
+        t_host += us(tc, now());
+        return 0;
+    };
+    auto small_enough = [&] { return resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0); };
     for (int restart = 0; restart < max_restarts && !converged; ++restart) {
         auto ta = now();
+        int formed = m;
+        bool evaluated = false;
         for (int j = j0; j < m; ++j) {
             cplx* wv = V + (size_t)(j + 1) * vstride;
             rc = heff_apply(h, V + (size_t)j * vstride, wv, st);
@@ -321,40 +368,22 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
             if (rc) return rc;
             rc = znormalise((long long)n, N2 + j, wv, st);
             if (rc) return rc;
-        }
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(h1.data(), C1, sizeof(cplx) * kk * m, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(h2.data(), C2, sizeof(cplx) * kk * m, cudaMemcpyDeviceToHost, st));
-        auto tb = now();
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx) * m, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-        auto tc = now();
-        t_enq += us(ta, tb);
-        t_wait += us(tb, tc);
-        // assemble the new columns of the projected matrix; stop at an invariant subspace
-        int mm = m;
-        double beta_last = 0.0;
-        for (int j = j0; j < m; ++j) {
-            for (int i = 0; i <= j; ++i) {
-                const double v = h1[(size_t)j * kk + i].x + h2[(size_t)j * kk + i].x;
-                Hp[(size_t)i * m + j] = v;
-                Hp[(size_t)j * m + i] = v;
+            const int done_now = j + 1 - j0;
+            if (poll_env && restart == 0 && j + 1 < m && (done_now == 4 || (done_now > 4 && (done_now - 4) % 8 == 0))) {
+                t_enq += us(ta, now());
+                rc = evaluate(j + 1);
+                if (rc) return rc;
+                ta = now();
+                if (small_enough() || mm < j + 1) { formed = j + 1; evaluated = true; break; }
             }
-            const double bj = std::sqrt(hn[j].x > 0.0 ? hn[j].x : 0.0);
-            beta_last = bj;
-            if (j + 1 < m) { Hp[(size_t)(j + 1) * m + j] = bj; Hp[(size_t)j * m + j + 1] = bj; }
-            if (!(bj > 1e-14 * (std::fabs(Hp[0]) + 1e-300)) || !std::isfinite(bj)) { mm = j + 1; break; }
         }
-        T.assign((size_t)mm * mm, 0.0);
-        for (int i = 0; i < mm; ++i)
-            for (int q = 0; q < mm; ++q) T[(size_t)i * mm + q] = Hp[(size_t)i * m + q];
-        sym_eig_host(mm, T, Y);
-        std::vector<int> idx(mm);
-        for (int i = 0; i < mm; ++i) idx[i] = i;
-        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return T[(size_t)a * mm + a] < T[(size_t)b * mm + b]; });
-        const int best = idx[0];
-        E = T[(size_t)best * mm + best];
-        resid = std::fabs(beta_last * Y[(size_t)(mm - 1) * mm + best]);
-        converged = resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0) || mm < m || restart + 1 == max_restarts;
+        t_enq += us(ta, now());
+        if (!evaluated) {
+            rc = evaluate(formed);
+            if (rc) return rc;
+        }
+        auto tc = now();
+        converged = small_enough() || mm < m || restart + 1 == max_restarts;
         const int keep = converged ? 1 : std::min(LANCZOS_KEEP, mm - 1);
         // Ritz vectors Vk[i] = sum_q Y[q][idx[i]] V[q]
         for (int i = 0; i < keep; ++i)
