@@ -413,6 +413,17 @@ class MPS:
             top = tuple(max(int(self.x[i + j]) for i in bonds) for j in range(3))
             if top[0] * d <= 128 and d * top[2] <= 128:
                 groups = {top: list(bonds)}
+            else:
+                # The few bonds near the ends of a saturated chain (1-2-4, 4-8-16, ...) would each be a call of their
+                # own, every one paying the full single-problem latency; padded into the smallest class that covers
+                # them they ride along with the bulk for a few per cent more work.
+                for key in sorted(groups, key=lambda g: g[0] * g[1] * g[2]):
+                    if len(groups[key]) >= 8:
+                        continue
+                    hosts = [g for g in groups if g != key and all(g[j] >= key[j] for j in range(3))]
+                    if hosts:
+                        host = min(hosts, key=lambda g: g[0] * g[1] * g[2])
+                        groups[host] = groups[host] + groups.pop(key)
         pending = []
         for (PL, PX, PR), idx in groups.items():
             nb = len(idx)
@@ -422,13 +433,20 @@ class MPS:
                 bi, bj = self._dev[idx[0]], self._dev[idx[0] + 1]
                 sl = self._schmidt(idx[0])
             else:
-                bi = _lib.zeros((nb, PL, d, PX))
-                bj = _lib.zeros((nb, PX, d, PR))
+                # one gather per operand; only the bonds smaller than the class are zero-padded first
+                t = _lib.torch()
+
+                def fit(src, shape):
+                    if tuple(src.shape) == shape:
+                        return src
+                    out = _lib.zeros(shape)
+                    out[:src.shape[0], :, :src.shape[2]].copy_(src)
+                    return out
+                bi = t.stack([fit(self._dev[i], (PL, d, PX)) for i in idx])
+                bj = t.stack([fit(self._dev[i + 1], (PX, d, PR)) for i in idx])
                 slh = np.zeros((nb, PL))
                 for b, i in enumerate(idx):
-                    xl, x, xr = int(self.x[i]), int(self.x[i + 1]), int(self.x[i + 2])
-                    bi[b, :xl, :, :x].copy_(self._dev[i])
-                    bj[b, :x, :, :xr].copy_(self._dev[i + 1])
+                    xl = int(self.x[i])
                     slh[b, :xl] = np.asarray(self.s[i], dtype=float) * np.ones(xl)
                 sl = _lib.to_device(slh, np.float64)
             bio = _lib.empty((nb, PL, d, kcap))

@@ -13,7 +13,7 @@ from dmrg_b200 import _lib
 lib = _lib.load()
 rs = np.random.RandomState(0)
 print("MPSB_SVD_RESIDENT_BATCH =", os.environ.get("MPSB_SVD_RESIDENT_BATCH", "(default)"))
-for chi, d, batch in [(10, 10, 1), (10, 10, 13), (16, 10, 13), (32, 2, 1), (32, 2, 64), (20, 2, 8), (64, 2, 1), (64, 3, 1)]:
+for chi, d, batch in [(10, 10, 1), (10, 10, 13), (32, 2, 1), (32, 2, 64), (64, 2, 1), (64, 3, 1), (128, 2, 1), (128, 2, 64), (128, 2, 148), (128, 2, 160)]:
     bi = _lib.to_device(rs.randn(batch, chi, d, chi) + 1j * rs.randn(batch, chi, d, chi))
     bj = _lib.to_device(rs.randn(batch, chi, d, chi) + 1j * rs.randn(batch, chi, d, chi))
     sl = _lib.to_device(np.abs(rs.randn(batch, chi)) + 0.1, np.float64)
