@@ -398,19 +398,18 @@ class MPS:
         step = 8 if v <= 64 else 32
         return (v + step - 1) // step * step
 
-    def _update_bonds(self, U_dev, bonds):
-        """Apply the same gate to disjoint bonds; bonds in the same padded size class share one batched call."""
-        self._flush()
-        lib = _lib.load()
-        d = self.dim
+    @classmethod
+    def _group_bonds(cls, x, bonds, d):
+        """Partition disjoint bonds into batched calls: {(PL, PX, PR): [bond, ...]} with every bond's dimensions
+        (x[i], x[i+1], x[i+2]) <= its class.  Pure bookkeeping (no device work)."""
         groups = {}
         for i in bonds:
-            key = (self._bucket(int(self.x[i])), self._bucket(int(self.x[i + 1])), self._bucket(int(self.x[i + 2])))
+            key = (cls._bucket(int(x[i])), cls._bucket(int(x[i + 1])), cls._bucket(int(x[i + 2])))
             groups.setdefault(key, []).append(i)
         if len(groups) > 1:
             # Small bonds are bound by launch latency, not by work: one call padded to the largest size class beats
             # one call per class (a d = 10 chain with bonds 1,5,10,...,10,8,5,4,3,1 has five classes per half sweep).
-            top = tuple(max(int(self.x[i + j]) for i in bonds) for j in range(3))
+            top = tuple(max(int(x[i + j]) for i in bonds) for j in range(3))
             if top[0] * d <= 128 and d * top[2] <= 128:
                 groups = {top: list(bonds)}
             else:
@@ -424,6 +423,14 @@ class MPS:
                     if hosts:
                         host = min(hosts, key=lambda g: g[0] * g[1] * g[2])
                         groups[host] = groups[host] + groups.pop(key)
+        return groups
+
+    def _update_bonds(self, U_dev, bonds):
+        """Apply the same gate to disjoint bonds; bonds in the same padded size class share one batched call."""
+        self._flush()
+        lib = _lib.load()
+        d = self.dim
+        groups = self._group_bonds(self.x, bonds, d)
         pending = []
         for (PL, PX, PR), idx in groups.items():
             nb = len(idx)

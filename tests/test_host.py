@@ -169,3 +169,30 @@ def test_cat_coherent_wigner_displace():                 # transmit/cat_test.py:
     assert abs(cat.expect(W, rho) - cat.expect(W, s1)) < 1e-12
     assert cat.fock(3, 7)[3] == 1 and cat.fock(3, 7).sum() == 1
     np.testing.assert_allclose(abs(cat.kerr(0.3, 2, 10)), abs(cat.coherent(2, 10)))
+
+
+def test_bond_grouping_for_batched_half_sweeps():
+    """Host bookkeeping of MPS._update_bonds: which bonds share one batched mpsb_tebd_two_site call."""
+    from dmrg_b200.MPS import MPS
+    # saturated L = 128, chi = 128 chain: the edge bonds (1-2-4, 4-8-16, ...) ride along with the bulk -> one call
+    L = 128
+    x = np.array([min(2 ** i, 2 ** (L - i), 128) for i in range(L + 1)])
+    for parity in (0, 1):
+        bonds = list(range(parity, L - 1, 2))
+        g = MPS._group_bonds(x, bonds, 2)
+        assert list(g) == [(128, 128, 128)] and sorted(g[(128, 128, 128)]) == bonds
+    # d = 10 boson chain (transmit/bhopping.py): all bonds small -> one call padded to the largest bond triple
+    x = np.array([1, 5, 10, 10, 10, 10, 8, 5, 4, 3, 1, 1])
+    g = MPS._group_bonds(x, [0, 2, 4, 6, 8], 10)
+    assert list(g) == [(10, 10, 10)] and g[(10, 10, 10)] == [0, 2, 4, 6, 8]
+    # every bond fits its class; a large class with few members is not merged away
+    x = np.array([4] * 30 + [100, 128, 128, 128, 128])
+    bonds = list(range(0, 32, 2))
+    g = MPS._group_bonds(x, bonds, 2)
+    for (PL, PX, PR), idx in g.items():
+        for i in idx:
+            assert x[i] <= PL and x[i + 1] <= PX and x[i + 2] <= PR
+    assert sorted(i for idx in g.values() for i in idx) == bonds
+    assert any(k[1] == 4 for k in g) and any(k[1] == 128 for k in g)
+    # a single class stays as it is
+    assert MPS._group_bonds(np.array([8, 8, 8, 8, 8]), [0, 2], 2) == {(8, 8, 8): [0, 2]}
