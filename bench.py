@@ -76,13 +76,36 @@ def make_inputs(n, seed0):
     return Bi, Bj, Sl, U
 
 
-def cpu_leg(per_worker):
+def make_config(chains, world):
+    """The `config` object of the JSON line - identical for the GPU arm and the reference arm."""
+    site = CHI * D * CHI
+    return {"workload": f"config 4 shard: {chains} independent chains/GPU, one saturated chi={CHI} d={D} complex128 "
+                        f"two-site update each per step (trun={TRUN}, err={ERR})",
+            "chains_per_gpu": chains, "chi": CHI, "d": D,
+            "inputs": "right-isometric B tensors, Gaussian Schmidt spectrum, per-chain GUE gate dt=0.05",
+            "l2": f"inputs {2 * chains * site * 16 / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)",
+            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"}
+
+
+def cpu_leg(per_worker, ref_per_worker=None):
+    """CPU baseline on the host cores: the UNMODIFIED reference (oracle/_ref/DMRG, staged by build()) when it is
+    there, else the oracle port; the port's rate is always reported as `port_value`."""
     from oracle import cpu_bench
     ups, cores, total, wall = cpu_bench.run(per_worker, CHI, D, TRUN, ERR)
-    return {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
+    port = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
             "sample": f"{total} update_double calls on synthetic chi={CHI} d={D} bonds ({per_worker} per worker, one "
                       f"worker per core, OMP_NUM_THREADS=1), oracle/mps_oracle.py (numpy tensordot + LAPACK zgesdd); "
-                      f"wall {wall:.1f} s"}
+                      f"wall {wall:.1f} s; rate = updates / busiest worker's loop time (pool start-up excluded)"}
+    if not cpu_bench.reference_available():
+        return port
+    rp = ref_per_worker or max(2, per_worker)
+    ups_r, cores, total_r, wall_r = cpu_bench.run(rp, CHI, D, TRUN, ERR, kind="reference")
+    return {"value": ups_r, "unit": "updates/s", "cores": cores, "kind": "reference",
+            "sample": f"{total_r} calls of the unmodified DMRG.MPS.MPS.update_double (DMRG/MPS.py:428-457, staged copy "
+                      f"oracle/_ref/DMRG) on synthetic chi={CHI} d={D} bonds ({rp} per worker, one worker process per "
+                      f"core, OMP_NUM_THREADS=1); wall {wall_r:.1f} s; rate = updates / busiest worker's loop time "
+                      f"(pool start-up excluded)",
+            "port_value": ups, "port_sample": port["sample"]}
 
 
 def idmrg_leg(with_cpu):
@@ -189,26 +212,27 @@ def finite_dmrg_leg():
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the box's host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (rank 0 only):
+    the unmodified DMRG.MPS.MPS.update_double when oracle/_ref/DMRG was staged, else the oracle port.  Every step is
+    a bounded sample of the workload; `value` is the mean rate over the timed steps."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    times = []
+    import __graft_entry__ as g
+    g.stage_reference()
+    times, rates = [], []
     for _ in range(args.warmup):
-        cpu_leg(2)
+        cpu_leg(2, 1)
     cb = None
     for _ in range(args.steps):
         t0 = time.perf_counter()
         cb = cpu_leg(args.cpu_updates)
         times.append(time.perf_counter() - t0)
+        rates.append(cb["value"])
+    cb = dict(cb, value=statistics.mean(rates), per_step_values=rates)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": f"config 4 shard: {args.chains} independent chains/GPU, one saturated chi={CHI} d={D} complex128 "
-                                   f"two-site update each per step (trun={TRUN}, err={ERR})",
-                       "chains_per_gpu": args.chains, "chi": CHI, "d": D,
-                       "inputs": "right-isometric B tensors, Gaussian Schmidt spectrum, per-chain GUE gate dt=0.05",
-                       "sample_per_step": f"{cb['cores'] * args.cpu_updates} of the {args.chains} updates (bounded CPU sample)",
-                       "parallelism": "one worker process per host core"},
+            "config": make_config(args.chains, args.gpus),
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "updates/s", "h2d_bytes_per_step": 0,
                                         "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -399,13 +423,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": {"workload": f"config 4 shard: {n} independent chains/GPU, one saturated chi={CHI} d={D} complex128 "
-                                   f"two-site update each per step (trun={TRUN}, err={ERR})",
-                       "chains_per_gpu": n, "chi": CHI, "d": D,
-                       "inputs": "right-isometric B tensors, Gaussian Schmidt spectrum, per-chain GUE gate dt=0.05",
-                       "l2": f"inputs {2 * n * site * 16 / 2**20:.0f} MiB per step > 126 MB L2 (no flush needed)",
-                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
-                       "host_thread_bound_to_gpu_numa_node": bool(numa_cpus)},
+            "config": make_config(n, world), "host_thread_bound_to_gpu_numa_node": bool(numa_cpus),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},

@@ -34,6 +34,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "mpsb_internal.h"
+#include "jacobi_shared.cuh"
 
 namespace mpsb {
 
@@ -42,13 +43,6 @@ namespace {
 constexpr int QR_THREADS = 1024;
 constexpr int FIN_THREADS = 256;
 
-// The convergence test |x_p . x_q|^2 > tol^2 |x_p|^2 |x_q|^2 is relative, so that small singular values keep their
-// relative accuracy.  Its right-hand side underflows for rows at the 1e-80 level (products of Schmidt values that are
-// themselves rounding noise reach 1e-260 in an iDMRG run on a rank-deficient state): such pairs would rotate for ever.
-// PAIR_FLOOR is added to the threshold (folded into the FMA that forms it, so it costs nothing): pairs with
-// |x_p|^2 |x_q|^2 below ~1e-260 are left alone, and finalise_kernel emits rows with |x|^2 <= ROW_DEAD as zero vectors
-// (singular values 1e-62 below the scale of a normalised state carry no information).
-constexpr double PAIR_FLOOR = 1e-290;
 // Householder columns with |x|^2 at or below this are treated as zero columns: tau = 2 / (v^H v) would overflow for
 // a subnormal norm (LAPACK's zlarfg rescales instead; here such a column is 1e-145 below a normalised state).
 constexpr double QR_TINY = 1e-290;
@@ -802,15 +796,6 @@ qr_blocked_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
 }
 
 // ---- Jacobi -----------------------------------------------------------------------------------------
-// Round-robin (circle method) pairing of m (even) players: round r in [0, m-1), slot s in [0, m/2).
-__device__ __forceinline__ void rr_pair(int m, int r, int s, int& p, int& q) {
-    const int mm = m - 1;
-    if (s == 0) { p = mm; q = r % mm; return; }
-    int a = (r + s) % mm, b = (r - s) % mm;
-    if (b < 0) b += mm;
-    p = a; q = b;
-}
-
 // Rotation parameters from the 2x2 Gram block [[a, c], [conj(c), b]]: the small-angle Jacobi rotation
 //   P' = cs P - g Q,   Q' = conj(g) P + cs Q,   g = sn c/|c|,
 // with t = sgn(z)|c| / (|z| + sqrt(z^2 + |c|^2)), z = (b - a)/2.  One sqrt, one reciprocal, one rsqrt
@@ -1004,24 +989,6 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
 //         x_p' = x_p - tau_p x_q,   x_q' = x_q + sig_q x_p,   d' = cs * d        (8 FMA per column, not 12),
 //     tau_p = tau d_q/d_p, sig_q = conj(tau) d_p/d_q, tau = t c/|c|; the scales are folded back into the rows at
 //     the end of the task (at most 8 rotations per row, so d >= cs_min^8 stays far from underflow).
-// MUFU seeds (about 20 bits) and Newton refinements: each refinement is 2-3 dependent FP64 operations instead
-// of the ~20-instruction IEEE division / square-root sequences.
-__device__ __forceinline__ double rcp_approx(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-}
-__device__ __forceinline__ double rsqrt_approx(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-}
-__device__ __forceinline__ double newton_rcp(double x, double r) { return fma(r, fma(-x, r, 1.0), r); }
-__device__ __forceinline__ double newton_rsqrt(double x, double y) {
-    const double h = 0.5 * x * y;
-    return fma(y, fma(-h, y, 0.5), y);
-}
-
 constexpr int CROSS_THREADS = 128;     // 4 warps, each owning TWO rows of block I in registers
 #ifndef MPSB_CROSS_MINBLOCKS
 #define MPSB_CROSS_MINBLOCKS 3
@@ -1992,6 +1959,30 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
                      int inner, double tol2, double eabs2, int launch_id, cudaStream_t st) {
     static const int cross_enabled = env_int("MPSB_JACOBI_CROSS", 1);
     const int ltot_r = round_up(pl.ltot, 32);
+    // rows of <= 256 columns: column-split kernel for every round (round 0 plays the full 16-row tournament)
+    const int cs_mode = env_int("MPSB_JACOBI_COLSPLIT", 1);      // 0: off, 1: one column per lane, 2: two
+    if (cs_mode && pl.n_pad / 8 > 2 && colsplit_supported(pl.bsz, ltot_r, pl.n_pad / 8)) {
+        ColsplitArgs a;
+        a.X = X;
+        a.strideX = (long long)pl.n_pad * pl.ld;
+        a.mat0 = mat0;
+        a.count = count;
+        a.ld = pl.ld;
+        a.ldot = pl.ldot;
+        a.ltot_r = ltot_r;
+        a.nblk = pl.n_pad / 8;
+        a.round = round;
+        a.full16 = (round == 0);
+        a.cpl = cs_mode == 2 ? 2 : 1;
+        a.rot = s.rot;
+        a.done = s.done;
+        a.tol2 = tol2;
+        a.phase_clk = g_prof.enabled > 1 ? s.phase_clk : nullptr;
+        a.stamps = s.stamps;
+        a.stamp_stride = s.stamp_stride;
+        a.launch_id = launch_id;
+        return launch_jacobi_colsplit(a, st);
+    }
     if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
         const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
         const bool full = (ltot_r == 256 && pl.ldot == 256);

@@ -21,6 +21,31 @@ __global__ void dmma_kernel(double* out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + d0 + d1 + e0 + e1 + f0 + f1;
 }
+// Both kinds interleaved in every warp: if DMMA and DFMA were independent pipes the combined rate would approach the sum.
+__global__ void mixed_kernel(double* out, int iters) {
+    double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+    double a0 = threadIdx.x, a1 = 1.0, a2 = 2.0, a3 = 3.0, a4 = 4.0, a5 = 5.0, a6 = 6.0, a7 = 7.0;
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    const double bb = 1.0000001, cc = 0.9999999;
+    for (int i = 0; i < iters; ++i) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        a0 = fma(a0, bb, cc); a1 = fma(a1, bb, cc); a2 = fma(a2, bb, cc); a3 = fma(a3, bb, cc);
+        a4 = fma(a4, bb, cc); a5 = fma(a5, bb, cc); a6 = fma(a6, bb, cc); a7 = fma(a7, bb, cc);
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+        a0 = fma(a0, bb, cc); a1 = fma(a1, bb, cc); a2 = fma(a2, bb, cc); a3 = fma(a3, bb, cc);
+        a4 = fma(a4, bb, cc); a5 = fma(a5, bb, cc); a6 = fma(a6, bb, cc); a7 = fma(a7, bb, cc);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + d0 + d1 + a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+// throughput of 64-bit warp shuffles (two SHFL.BFLY each) next to nothing else
+__global__ void shfl_kernel(double* out, int iters) {
+    double a0 = threadIdx.x, a1 = 1.0, a2 = 2.0, a3 = 3.0;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __shfl_xor_sync(0xffffffffu, a0, 1); a1 = __shfl_xor_sync(0xffffffffu, a1, 2);
+        a2 = __shfl_xor_sync(0xffffffffu, a2, 4); a3 = __shfl_xor_sync(0xffffffffu, a3, 8);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
+}
 // latency: one dependent chain per thread, one warp per SM sub-partition
 __global__ void dfma_latency(double* out, int iters, long long* clk) {
     double a = threadIdx.x;
@@ -45,6 +70,20 @@ int main() {
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep) printf("DMMA  %4d thr x 296 CTAs: %.2f TFLOP/s\n", threads, 2.0 * 256 * 4 * iters * 296.0 * (threads / 32) / (ms * 1e-3) / 1e12);
         }
+    }
+    for (int threads : {256, 512, 1024}) {
+        float ms;
+        mixed_kernel<<<148 * 2, threads>>>(out, iters);
+        cudaEventRecord(e0); mixed_kernel<<<148 * 2, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double dfma = 2.0 * 16 * iters * 296.0 * threads, dmma = 2.0 * 256 * 2 * iters * 296.0 * (threads / 32);
+        printf("MIXED %4d thr x 296 CTAs: DFMA %.2f + DMMA %.2f = %.2f TFLOP/s\n", threads, dfma / (ms * 1e-3) / 1e12,
+               dmma / (ms * 1e-3) / 1e12, (dfma + dmma) / (ms * 1e-3) / 1e12);
+        shfl_kernel<<<148 * 2, threads>>>(out, iters);
+        cudaEventRecord(e0); shfl_kernel<<<148 * 2, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("SHFL64 %4d thr x 296 CTAs: %.1f 32-bit warp shuffles / clock / SM (at 1.965 GHz)\n", threads,
+               8.0 * iters * 296.0 * (threads / 32) / (ms * 1e-3) / 148.0 / 1.965e9);
     }
     dfma_latency<<<1, 32>>>(out, 10000, clk); cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, clk, 8, cudaMemcpyDeviceToHost);
