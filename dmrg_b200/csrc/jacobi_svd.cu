@@ -64,7 +64,7 @@ struct SvdState {           // device scratch, carved out of the caller's worksp
 // its CTA can leave before loading a single row.  Stamps are launch numbers (monotone within one SVD call).
 __host__ __device__ inline int stamp_ints(int n_pad, int bsz) {
     const int nblk = n_pad / bsz;
-    return (bsz == 8 && nblk >= 4 && nblk <= 512) ? nblk + (nblk - 1) * (nblk / 2) : 0;
+    return (bsz == 8 && nblk >= 4 && nblk <= 512) ? nblk + nblk * nblk + nblk / 2 : 0;
 }
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1004,9 +1004,11 @@ struct RegRow {
 // One Jacobi pair between a register row and the streamed row y (scale dq, eq = dq^2, true norm^2 bq).
 // Returns 1 if a rotation was applied.
 // FULL: all 256 columns take part in the inner product (no per-column predicates in the hot loop).
+// sort: de Rijk's rule - if the rotation leaves the register row (lower block) with the smaller norm, the two
+// results trade places (free: only the names of the registers change).
 template <bool FULL>
 __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, double& eq, double& bq, int ldot,
-                                          double tol2, int lane) {
+                                          double tol2, int lane, bool sort) {
     double cr0 = 0.0, ci0 = 0.0, cr1 = 0.0, ci1 = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -1039,13 +1041,24 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
     const double cs = newton_rsqrt(wv, newton_rsqrt(wv, rsqrt_approx(wv)));
     const double cs2 = cs * cs;
     const double delta = k * ac2;                                            // t |c|
-    r.d *= cs;
-    r.e *= cs2;
-    r.a -= delta;
+    const double an = r.a - delta, bn = bq + delta;
+    const double dpn = r.d * cs, epn = r.e * cs2, dqn = dq * cs, eqn = eq * cs2;
     r.dirty = true;
-    dq *= cs;
-    eq *= cs2;
-    bq += delta;
+    if (sort && an < bn) {                                                   // identical in every lane
+        r.d = dqn; r.e = eqn; r.a = bn;
+        dq = dpn; eq = epn; bq = an;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const cplx xo = r.x[j], yo = y[j];
+            y[j].x = fma(-tpr, yo.x, fma(tpi, yo.y, xo.x));
+            y[j].y = fma(-tpr, yo.y, fma(-tpi, yo.x, xo.y));
+            r.x[j].x = fma(sqr, xo.x, fma(-sqi, xo.y, yo.x));
+            r.x[j].y = fma(sqr, xo.y, fma(sqi, xo.x, yo.y));
+        }
+        return 1;
+    }
+    r.d = dpn; r.e = epn; r.a = an;
+    dq = dqn; eq = eqn; bq = bn;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const cplx xo = r.x[j], yo = y[j];
@@ -1062,7 +1075,7 @@ __global__ void __launch_bounds__(CROSS_THREADS, MPSB_CROSS_MINBLOCKS)
 jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                     int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
                     unsigned long long* __restrict__ phase_clk, int* __restrict__ stamps, int stamp_stride,
-                    int launch_id) {
+                    int launch_id, int modulus) {
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [8][ltot_r]
     __shared__ double nq[8], dqs[8], eqs[8];                  // true norm^2, scale d and d^2 of the rows of block J
@@ -1073,9 +1086,10 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
     const long long t_start = phase_clk ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int bI, bJ;
-    rr_pair(nblk, round, blockIdx.x, bI, bJ);
+    if (modulus) mod_pair(nblk, round, blockIdx.x, bI, bJ);      // bI < bJ: the register rows belong to the lower block
+    else rr_pair(nblk, round, blockIdx.x, bI, bJ);
     int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
-    const int chk_idx = nblk + round * (nblk >> 1) + blockIdx.x;
+    const int chk_idx = modulus ? stamp_pair_index(nblk, bI, bJ) : nblk + round * (nblk >> 1) + blockIdx.x;
     if (stp) {                                               // verified clean since both blocks last changed
         const int chk = stp[chk_idx];
         if (chk > stp[bI] && chk > stp[bJ]) return;
@@ -1141,8 +1155,8 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
             y[j] = (FULL || c < ltot_r) ? rq[c] : make_double2(0.0, 0.0);
         }
         double dq = dqs[q], eq = eqs[q], bq = nq[q];
-        const int n0 = cross_pair<FULL>(r0, y, dq, eq, bq, ldot, tol2, lane);
-        const int n1 = cross_pair<FULL>(r1, y, dq, eq, bq, ldot, tol2, lane);
+        const int n0 = cross_pair<FULL>(r0, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
+        const int n1 = cross_pair<FULL>(r1, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
         nrot += n0 + n1;
         // Even rows of block J are visited in even steps, odd rows in odd steps, so steps 6 and 7 are the last
         // visits: fold the accumulated scale back into the row there.
@@ -1955,12 +1969,67 @@ int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, i
     return 0;
 }
 
+// Modulus ordering (rows of <= 256 columns, 8-row blocks): step `round` in [0, nblk) = one launch of the register-
+// resident cross kernel over the step's cross pairs plus, on even steps, the two self tasks (pairs inside blocks
+// round/2 and round/2 + nblk/2) on the sub-group kernel.
+bool use_modulus_order(const SvdPlan& pl) {
+    const int nblk = pl.n_pad / 8, ltot_r = round_up(pl.ltot, 32);
+    return env_int("MPSB_JACOBI_ORDER", 1) == 1 && pl.bsz == 8 && ltot_r <= 256 && nblk >= 4 && (nblk & 1) == 0 &&
+           !pl.resident && colsplit_supported(pl.bsz, ltot_r, nblk);
+}
+int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, double tol2,
+                        int launch_id, cudaStream_t st) {
+    const int ltot_r = round_up(pl.ltot, 32), nblk = pl.n_pad / 8;
+    const long long strideX = (long long)pl.n_pad * pl.ld;
+    unsigned long long* pc = g_prof.enabled > 1 ? s.phase_clk : nullptr;
+    const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
+    const bool full = (ltot_r == 256 && pl.ldot == 256);
+    if (int rc = ensure_dynamic_smem(full ? reinterpret_cast<const void*>(jacobi_cross_kernel<true>)
+                                          : reinterpret_cast<const void*>(jacobi_cross_kernel<false>), smem))
+        return rc;
+    dim3 grid(mod_cross_pairs(nblk, round), count);
+    if (full)
+        jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
+                                                                     s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride,
+                                                                     launch_id, 1);
+    else
+        jacobi_cross_kernel<false><<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
+                                                                      s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride,
+                                                                      launch_id, 1);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    if ((round & 1) == 0) {
+        ColsplitArgs a;
+        a.X = X;
+        a.strideX = strideX;
+        a.mat0 = mat0;
+        a.count = count;
+        a.ld = pl.ld;
+        a.ldot = pl.ldot;
+        a.ltot_r = ltot_r;
+        a.nblk = nblk;
+        a.round = round;
+        a.full16 = 2;
+        a.cpl = -1;
+        a.rot = s.rot;
+        a.done = s.done;
+        a.tol2 = tol2;
+        a.phase_clk = nullptr;
+        a.stamps = s.stamps;
+        a.stamp_stride = s.stamp_stride;
+        a.launch_id = launch_id;
+        if (int rc = launch_jacobi_colsplit(a, st)) return rc;
+    }
+    return 0;
+}
+
 int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
                      int inner, double tol2, double eabs2, int launch_id, cudaStream_t st) {
     static const int cross_enabled = env_int("MPSB_JACOBI_CROSS", 1);
     const int ltot_r = round_up(pl.ltot, 32);
     // rows of <= 256 columns: column-split kernel for every round (round 0 plays the full 16-row tournament)
-    const int cs_mode = env_int("MPSB_JACOBI_COLSPLIT", 1);      // 0: off, 1: one column per lane, 2: two
+    // MPSB_JACOBI_COLSPLIT: 0 off | 1, 2: single-chain kernel with 1 / 2 columns per lane | 3, 4: sub-group kernel with 4 / 2 warps per sub-group
+    const int cs_mode = env_int("MPSB_JACOBI_COLSPLIT", 0);
     if (cs_mode && pl.n_pad / 8 > 2 && colsplit_supported(pl.bsz, ltot_r, pl.n_pad / 8)) {
         ColsplitArgs a;
         a.X = X;
@@ -1973,7 +2042,7 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
         a.nblk = pl.n_pad / 8;
         a.round = round;
         a.full16 = (round == 0);
-        a.cpl = cs_mode == 2 ? 2 : 1;
+        a.cpl = cs_mode == 4 ? -1 : cs_mode == 3 ? 0 : (cs_mode == 2 ? 2 : 1);
         a.rot = s.rot;
         a.done = s.done;
         a.tol2 = tol2;
@@ -1995,11 +2064,11 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
         if (full)
             jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
                                                                          pl.ldot, ltot_r, nblk, round, s.rot, s.done,
-                                                                         tol2, pc, s.stamps, s.stamp_stride, launch_id);
+                                                                         tol2, pc, s.stamps, s.stamp_stride, launch_id, 0);
         else
             jacobi_cross_kernel<false><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
                                                                           pl.ldot, ltot_r, nblk, round, s.rot, s.done,
-                                                                          tol2, pc, s.stamps, s.stamp_stride, launch_id);
+                                                                          tol2, pc, s.stamps, s.stamp_stride, launch_id, 0);
         MPSB_COUNT_LAUNCH();
         MPSB_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -2169,10 +2238,12 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     const double eabs = 0.0;   // purely relative criterion: kept right singular vectors must be orthonormal to ~tol
     const double tol2 = tol * tol, eabs2 = eabs * eabs;
     const int nblk = pl.n_pad / pl.bsz;
-    const int rounds = nblk - 1;
+    const bool modulus = use_modulus_order(pl);
+    const int rounds = modulus ? nblk : nblk - 1;
     const int inner = (nblk == 2) ? pl.max_sweeps : 1;
     int max_sweeps_seen = 0;
     int launch_id = 1;
+    const int trace = env_int("MPSB_SVD_TRACE", 0);
     if (pl.resident) {
         if (int rc = launch_resident(pl, X, s, tol2, st)) return rc;
         MPSB_CHECK_CUDA(cudaMemcpyAsync(&max_sweeps_seen, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -2183,7 +2254,8 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         int sweep = 0;
         for (; sweep < pl.max_sweeps; ++sweep) {
             for (int r = 0; r < rounds; ++r) {
-                int rc = launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
+                int rc = modulus ? launch_modulus_step(pl, X, s, mat0, count, r, tol2, ++launch_id, st)
+                                 : launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
                 if (rc) return rc;
             }
             MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
@@ -2194,6 +2266,12 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
             int n_active = 0;
             MPSB_CHECK_CUDA(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
             MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+            if (trace) {
+                unsigned long long rt = 0;
+                MPSB_CHECK_CUDA(cudaMemcpy(&rt, s.rot_total, sizeof(rt), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "[mpsb] svd trace: chunk %d sweep %2d: %d of %d problems still rotating, %llu rotations so far\n",
+                        mat0 / pl.chunk, sweep, n_active, count, rt);
+            }
             if (n_active == 0) { ++sweep; break; }
         }
         max_sweeps_seen = std::max(max_sweeps_seen, sweep);
@@ -2212,9 +2290,9 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
             MPSB_CHECK_CUDA(cudaMemcpy(c, s.phase_clk, sizeof(c), cudaMemcpyDeviceToHost));
             const double nc = (double)(c[3] ? c[3] : 1);
             fprintf(stderr, "[mpsb] jacobi CTA phases (mean SM clocks): load %.0f rotate %.0f store %.0f over %llu CTAs"
-                            " | gram %.0f tournament %.0f update %.0f\n",
+                            " | gram %.0f tournament %.0f update %.0f | %.0f\n",
                     (double)c[0] / nc, (double)c[1] / nc, (double)c[2] / nc, c[3], (double)c[4] / nc, (double)c[5] / nc,
-                    (double)c[6] / nc);
+                    (double)c[6] / nc, (double)c[7] / nc);
         }
     }
     return 0;

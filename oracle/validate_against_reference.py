@@ -250,7 +250,7 @@ def case_idmrg():
              Rnext_ref=np.einsum('ijk, Ali, Bmj, Cklm', Rr, Vn, Vn.conj(), W))
     out = {"W": W}
     orig_halve = ref_idmrg.halve
-    for trunc, steps in ((10, 40), (16, 12)):
+    for trunc, steps in ((10, 40), (16, 12), (32, 9)):     # trunc = 32 is BASELINE config 1
         ref_idmrg.halve = lambda p, sh, trunc=trunc: orig_halve(p, sh, trunc)
         L, R = np.array([[[0, 0, 1]]]), np.array([[[1, 0, 0]]])
         Lo, Ro = io_.boundary(3)

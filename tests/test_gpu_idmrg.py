@@ -83,7 +83,7 @@ def test_idmrg_tfim_energies_vs_reference_golden(lib, golden):
     g = golden("idmrg_energies.npz")
     W = (-MPO('sx') - MPO('sz') ** 2).tomatrix()
     np.testing.assert_array_equal(W, g["W"])
-    for trunc, steps in ((10, 40), (16, 12)):
+    for trunc, steps in ((10, 40), (16, 12), (32, 9)):       # trunc = 32 is BASELINE config 1 as named
         L, R = np.array([[[0, 0, 1]]]), np.array([[[1, 0, 0]]])
         e = []
         for i in range(steps):

@@ -109,7 +109,7 @@ def test_heff_and_env_golden(golden):
 def test_idmrg_tfim_energies_golden(golden):
     g = golden("idmrg_energies.npz")
     W = g["W"]
-    for trunc, steps in ((10, 20), (16, 12)):
+    for trunc, steps in ((10, 20), (16, 12), (32, 9)):       # trunc = 32: BASELINE config 1
         L, R = io_.boundary(3)
         e = []
         for i in range(steps):
@@ -118,6 +118,7 @@ def test_idmrg_tfim_energies_golden(golden):
         np.testing.assert_allclose(e, g[f"tfim_e_trunc{trunc}"][:steps], rtol=2e-10)
     assert abs(g["tfim_e_trunc10"][0] + 1.1180339887499) < 1e-12
     assert abs(g["tfim_e_trunc10"][39] + 1.2687174555821) < 1e-9
+    assert abs(g["tfim_e_trunc32"][8] + 1.253444929157) < 1e-11         # SURVEY App. C, trunc = 32 series
 
 
 def _bmps_cases(golden):
