@@ -2159,7 +2159,7 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
         p.n_pad = n_even;
     }
     const size_t matbytes = (size_t)p.n_pad * rowbytes;
-    const size_t l2_budget = (size_t)env_int("MPSB_SVD_L2_MB", 1 << 20) * 1024 * 1024;
+    const size_t l2_budget = (size_t)env_int("MPSB_SVD_L2_MB", 1 << 20) * 1024 * 1024;     // default: no chunking
     int chunk = (int)std::max<size_t>(1, l2_budget / matbytes);
     chunk = env_int("MPSB_SVD_CHUNK", chunk);
     if (chunk < 1) chunk = 1;
@@ -2170,6 +2170,7 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
     static const int qr_grid_enabled = env_int("MPSB_SVD_QR_GRID", 1);
     static const int qr_grid_min = env_int("MPSB_SVD_QR_GRID_MIN", 160);
     p.qr_grid = (qr_grid_enabled && batch <= 4 && std::min(n, ldot) >= qr_grid_min) ? 1 : 0;
+    if (p.qr_grid) p.chunk = batch;          // the cooperative QR factors the whole (tiny) batch in one launch
     *plan = p;
     return 0;
 }
@@ -2180,58 +2181,67 @@ size_t svd_state_bytes(const SvdPlan& plan) {
            (plan.qr_grid ? qr_grid_scratch_bytes(plan) * plan.batch : 0);
 }
 
+namespace {
+
+// QR preconditioning of problems [mat0, mat0 + count)
+int launch_qr(const SvdPlan& pl, cplx* X, const SvdState& s, void* state, int mat0, int count, cudaStream_t st) {
+    const long long strideX = (long long)pl.n_pad * pl.ld;
+    cplx* Xc = X + (size_t)mat0 * strideX;
+    double* frob = s.frob2 + mat0;
+    int CW = std::min(pl.ld, QR_THREADS);
+    int G = QR_THREADS / CW;
+    const size_t wbudget = 48 * 1024;       // per w buffer (two are kept)
+    G = std::max(1, std::min<int>(G, (int)(wbudget / ((size_t)pl.ld * sizeof(cplx)))));
+    G = std::min(G, std::max(1, pl.n));
+    const size_t smem = 2 * align_up(pl.n, 8) * sizeof(cplx) + (size_t)2 * G * pl.ld * sizeof(cplx) +
+                        align_up(pl.ldot, 8) * sizeof(double) + align_up(pl.ldot, 8) * sizeof(int) + pl.ld + 64;
+    static const int qr_enabled = env_int("MPSB_SVD_QR", 1);
+    static const int qr_blocked = env_int("MPSB_SVD_QR_BLOCKED", 1);
+    const size_t smem_b = align_up(pl.n, 8) * QB_NB * sizeof(cplx) + align_up(pl.ldot, 8) * (sizeof(double) + sizeof(int)) +
+                          pl.ld + 64;
+    // Very long rows (chi >= 1024 with carried columns) do not leave room for the reflector scratch; the
+    // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
+    // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
+    // to itself the 1024-thread fused kernel has half the latency (tools/tebd_small_probe.py).
+    static const int latency_batch = env_int("MPSB_SVD_QR_LATENCY_BATCH", 148);
+    const bool latency_mode = pl.batch <= latency_batch && smem <= 220 * 1024;
+    int grid_rc = -1;
+    if (qr_enabled && pl.qr_grid) {          // only for batch <= 4: never chunked
+        SvdPlan base = pl;
+        base.qr_grid = 0;
+        unsigned char* scratch = static_cast<unsigned char*>(state) + svd_state_bytes(base);
+        grid_rc = launch_qr_grid(pl, X, s.frob2, scratch, st);
+        if (grid_rc > 0) return grid_rc;
+    }
+    if (grid_rc == 0) {
+    } else if (qr_enabled && qr_blocked && !latency_mode && smem_b <= 200 * 1024) {
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_blocked_kernel), smem_b)) return rc;
+        qr_blocked_kernel<<<count, QB_THREADS, smem_b, st>>>(Xc, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, frob);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+    } else if (qr_enabled && smem <= 220 * 1024) {
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_precond_kernel), smem)) return rc;
+        qr_precond_kernel<<<count, QR_THREADS, smem, st>>>(Xc, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, G, CW, frob);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace
+
+// QR -> sweeps until a sweep applies no rotation, chunk by chunk (one chunk unless MPSB_SVD_L2_MB / MPSB_SVD_CHUNK ask
+// for more: cutting the batch into L2-sized chunks, even with several chunks in flight on separate streams, was
+// measured to be slower - a round of a small chunk cannot fill the GPU and ~3700 dependent launches per chunk add up).
+// Convergence is polled (4-byte D2H + stream sync) only from two sweeps before the count the previous call needed.
 int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, int* sweeps_out) {
     const SvdState s = carve_state(state, pl.batch, stamp_ints(pl.n_pad, pl.bsz));
-    const long long strideX = (long long)pl.n_pad * pl.ld;
     if (s.stamps) MPSB_CHECK_CUDA(cudaMemsetAsync(s.stamps, 0, sizeof(int) * (size_t)pl.batch * s.stamp_stride, st));
     sweep_begin_kernel<<<(pl.batch + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, s.rot_total, s.sweep_total,
                                                                pl.batch, 1);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
 
-    // QR preconditioning for the whole batch
-    {
-        int CW = std::min(pl.ld, QR_THREADS);
-        int G = QR_THREADS / CW;
-        const size_t wbudget = 48 * 1024;       // per w buffer (two are kept)
-        G = std::max(1, std::min<int>(G, (int)(wbudget / ((size_t)pl.ld * sizeof(cplx)))));
-        G = std::min(G, std::max(1, pl.n));
-        const size_t smem = 2 * align_up(pl.n, 8) * sizeof(cplx) + (size_t)2 * G * pl.ld * sizeof(cplx) +
-                            align_up(pl.ldot, 8) * sizeof(double) + align_up(pl.ldot, 8) * sizeof(int) + pl.ld + 64;
-        static const int qr_enabled = env_int("MPSB_SVD_QR", 1);
-        static const int qr_blocked = env_int("MPSB_SVD_QR_BLOCKED", 1);
-        const size_t smem_b = align_up(pl.n, 8) * QB_NB * sizeof(cplx) + align_up(pl.ldot, 8) * (sizeof(double) + sizeof(int)) +
-                              pl.ld + 64;
-        // Very long rows (chi >= 1024 with carried columns) do not leave room for the reflector scratch; the
-        // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
-        // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
-        // to itself the 1024-thread fused kernel has half the latency (tools/tebd_small_probe.py).
-        static const int latency_batch = env_int("MPSB_SVD_QR_LATENCY_BATCH", 148);
-        const bool latency_mode = pl.batch <= latency_batch && smem <= 220 * 1024;
-        int grid_rc = -1;
-        if (qr_enabled && pl.qr_grid) {
-            SvdPlan base = pl;
-            base.qr_grid = 0;
-            unsigned char* scratch = static_cast<unsigned char*>(state) + svd_state_bytes(base);
-            grid_rc = launch_qr_grid(pl, X, s.frob2, scratch, st);
-            if (grid_rc > 0) return grid_rc;
-        }
-        if (grid_rc == 0) {
-        } else if (qr_enabled && qr_blocked && !latency_mode && smem_b <= 200 * 1024) {
-            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_blocked_kernel), smem_b)) return rc;
-            qr_blocked_kernel<<<pl.batch, QB_THREADS, smem_b, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, s.frob2);
-            MPSB_COUNT_LAUNCH();
-            MPSB_CHECK_CUDA(cudaGetLastError());
-        } else if (qr_enabled && smem <= 220 * 1024) {
-            if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_precond_kernel), smem)) return rc;
-            qr_precond_kernel<<<pl.batch, QR_THREADS, smem, st>>>(X, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, G, CW,
-                                                                 s.frob2);
-            MPSB_COUNT_LAUNCH();
-            MPSB_CHECK_CUDA(cudaGetLastError());
-        }
-    }
-
-    prof_mark(3, st);
     const double eps = 2.220446049250313e-16;
     static const double tol_factor = (double)env_int("MPSB_SVD_TOL_X10", 10) / 10.0;
     const double tol = tol_factor * sqrt((double)pl.ldot) * eps;
@@ -2244,37 +2254,51 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     int max_sweeps_seen = 0;
     int launch_id = 1;
     const int trace = env_int("MPSB_SVD_TRACE", 0);
+
     if (pl.resident) {
+        if (int rc = launch_qr(pl, X, s, state, 0, pl.batch, st)) return rc;
+        prof_mark(3, st);
         if (int rc = launch_resident(pl, X, s, tol2, st)) return rc;
         MPSB_CHECK_CUDA(cudaMemcpyAsync(&max_sweeps_seen, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-    }
-    for (int mat0 = 0; mat0 < pl.batch && !pl.resident; mat0 += pl.chunk) {
-        const int count = std::min(pl.chunk, pl.batch - mat0);
-        int sweep = 0;
-        for (; sweep < pl.max_sweeps; ++sweep) {
-            for (int r = 0; r < rounds; ++r) {
-                int rc = modulus ? launch_modulus_step(pl, X, s, mat0, count, r, tol2, ++launch_id, st)
-                                 : launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
-                if (rc) return rc;
+    } else {
+        const int nchunks = (pl.batch + pl.chunk - 1) / pl.chunk;
+        // With one chunk the QR of the batch is timed as its own phase; otherwise QR and sweeps of different chunks
+        // alternate and the "qr" phase of the profile reads zero (its time is inside "jacobi").
+        if (nchunks > 1) prof_mark(3, st);
+        static int last_sweeps = 0;                       // sweeps the previous call needed (any shape: a hint only)
+        const int poll_from = std::max(0, last_sweeps - 2);
+        for (int mat0 = 0; mat0 < pl.batch; mat0 += pl.chunk) {
+            const int count = std::min(pl.chunk, pl.batch - mat0);
+            if (int rc = launch_qr(pl, X, s, state, mat0, count, st)) return rc;
+            if (nchunks == 1) prof_mark(3, st);
+            int sweep = 0;
+            for (; sweep < pl.max_sweeps; ++sweep) {
+                for (int r = 0; r < rounds; ++r) {
+                    int rc = modulus ? launch_modulus_step(pl, X, s, mat0, count, r, tol2, ++launch_id, st)
+                                     : launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
+                    if (rc) return rc;
+                }
+                MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
+                sweep_end_kernel<<<(count + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, s.rot_total, s.sweep_total,
+                                                                      mat0, count);
+                MPSB_COUNT_LAUNCH();
+                MPSB_CHECK_CUDA(cudaGetLastError());
+                if (!(sweep >= poll_from || sweep + 1 == pl.max_sweeps || trace)) continue;
+                int n_active = 0;
+                MPSB_CHECK_CUDA(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+                MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+                if (trace) {
+                    unsigned long long rt = 0;
+                    MPSB_CHECK_CUDA(cudaMemcpy(&rt, s.rot_total, sizeof(rt), cudaMemcpyDeviceToHost));
+                    fprintf(stderr, "[mpsb] svd trace: chunk %d sweep %2d: %d of %d problems still rotating, %llu rotations "
+                                    "so far\n", mat0 / pl.chunk, sweep, n_active, count, rt);
+                }
+                if (n_active == 0) { ++sweep; break; }
             }
-            MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
-            sweep_end_kernel<<<(count + 255) / 256, 256, 0, st>>>(s.rot, s.done, s.n_active, s.rot_total, s.sweep_total,
-                                                                  mat0, count);
-            MPSB_COUNT_LAUNCH();
-            MPSB_CHECK_CUDA(cudaGetLastError());
-            int n_active = 0;
-            MPSB_CHECK_CUDA(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-            MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-            if (trace) {
-                unsigned long long rt = 0;
-                MPSB_CHECK_CUDA(cudaMemcpy(&rt, s.rot_total, sizeof(rt), cudaMemcpyDeviceToHost));
-                fprintf(stderr, "[mpsb] svd trace: chunk %d sweep %2d: %d of %d problems still rotating, %llu rotations so far\n",
-                        mat0 / pl.chunk, sweep, n_active, count, rt);
-            }
-            if (n_active == 0) { ++sweep; break; }
+            max_sweeps_seen = std::max(max_sweeps_seen, sweep);
         }
-        max_sweeps_seen = std::max(max_sweeps_seen, sweep);
+        last_sweeps = max_sweeps_seen;
     }
     if (sweeps_out) *sweeps_out = max_sweeps_seen;
     prof_mark(4, st);
