@@ -6,6 +6,7 @@ fallback: if the shared library or a CUDA device is missing, the first call rais
 """
 import ctypes
 import os
+import threading as _threading
 
 import numpy as np
 
@@ -177,11 +178,26 @@ class Workspace:
         return self.buf
 
 
-_ws = Workspace()
+# One scratch buffer per (host thread, device, stream): calls issued on different streams or devices - or from
+# different threads - never share theta / work-matrix / Krylov scratch (include/mpsb.h: one host thread per
+# (device, stream)).  Kernels of one stream run in order, so reusing that stream's buffer call after call is safe.
+_ws_local = _threading.local()
+
+
+def _workspace_for_current_stream():
+    t = torch()
+    key = (t.cuda.current_device(), int(t.cuda.current_stream().cuda_stream))
+    table = getattr(_ws_local, "table", None)
+    if table is None:
+        table = _ws_local.table = {}
+    ws = table.get(key)
+    if ws is None:
+        ws = table[key] = Workspace()
+    return ws
 
 
 def workspace(nbytes):
-    buf = _ws.get(nbytes)
+    buf = _workspace_for_current_stream().get(nbytes)
     return _c.c_void_p(buf.data_ptr()), _c.c_size_t(buf.numel())
 
 

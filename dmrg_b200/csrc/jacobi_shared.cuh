@@ -12,28 +12,6 @@ namespace mpsb {
 // (singular values 1e-62 below the scale of a normalised state carry no information).
 constexpr double PAIR_FLOOR = 1e-290;
 
-// Arguments of one column-split Jacobi round (jacobi_colsplit.cu): grid = (nblk / 2, count).
-struct ColsplitArgs {
-    cplx* X;
-    long long strideX;
-    int mat0, count;
-    int ld, ldot, ltot_r;       // row pitch, columns entering the inner products, columns rotated (multiple of 32)
-    int nblk, round;
-    int full16;                 // 1: complete tournament of the 16 rows of each block pair (round 0 of a sweep)
-                                // 2: "self" tasks of the modulus ordering: the pairs INSIDE blocks round/2 and
-                                //    round/2 + nblk/2 (grid.x = 1)
-    int cpl;                    // 0: sub-group kernel; 1 or 2: single-chain kernel with that many columns per lane
-    int* rot;
-    const int* done;
-    double tol2;
-    unsigned long long* phase_clk;
-    int* stamps;
-    int stamp_stride;
-    int launch_id;
-};
-bool colsplit_supported(int bsz, int ltot_r, int nblk);
-int launch_jacobi_colsplit(const ColsplitArgs& a, cudaStream_t st);
-
 #ifdef __CUDACC__
 // Round-robin (circle method) pairing of m (even) players: round r in [0, m-1), slot s in [0, m/2).
 __device__ __forceinline__ void rr_pair(int m, int r, int s, int& p, int& q) {

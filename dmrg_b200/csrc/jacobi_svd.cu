@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "mpsb_internal.h"
 #include "jacobi_shared.cuh"
+#include "jacobi_selftask.cuh"
 
 namespace mpsb {
 
@@ -1076,6 +1077,19 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
                     int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
                     unsigned long long* __restrict__ phase_clk, int* __restrict__ stamps, int stamp_stride,
                     int launch_id, int modulus) {
+    // modulus ordering, even steps: the CTA after the cross pairs plays the two self tasks of the step
+    if (modulus && blockIdx.x >= mod_cross_pairs(nblk, round)) {
+        const int mat = mat0 + blockIdx.y;
+        if (done[mat]) return;
+        cplx* X = Xall + (size_t)mat * strideX;
+        int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
+        const int bA = round >> 1, bB = bA + (nblk >> 1), unit = stamp_self_index(nblk, bA);
+        if (FULL) selftask_body<4, true>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
+        else if (ltot_r > 128) selftask_body<4, false>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
+        else if (ltot_r > 64) selftask_body<2, false>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
+        else selftask_body<1, false>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
+        return;
+    }
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [8][ltot_r]
     __shared__ double nq[8], dqs[8], eqs[8];                  // true norm^2, scale d and d^2 of the rows of block J
@@ -1969,13 +1983,13 @@ int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, i
     return 0;
 }
 
-// Modulus ordering (rows of <= 256 columns, 8-row blocks): step `round` in [0, nblk) = one launch of the register-
-// resident cross kernel over the step's cross pairs plus, on even steps, the two self tasks (pairs inside blocks
-// round/2 and round/2 + nblk/2) on the sub-group kernel.
+// Modulus ordering (rows of <= 256 columns, 8-row blocks): step `round` in [0, nblk) = ONE launch of the register-
+// resident cross kernel over the step's cross pairs; on even steps one more CTA per problem plays the two self tasks
+// (pairs inside blocks round/2 and round/2 + nblk/2, which no cross pair of the step touches).
 bool use_modulus_order(const SvdPlan& pl) {
     const int nblk = pl.n_pad / 8, ltot_r = round_up(pl.ltot, 32);
     return env_int("MPSB_JACOBI_ORDER", 1) == 1 && pl.bsz == 8 && ltot_r <= 256 && nblk >= 4 && (nblk & 1) == 0 &&
-           !pl.resident && colsplit_supported(pl.bsz, ltot_r, nblk);
+           !pl.resident;
 }
 int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, double tol2,
                         int launch_id, cudaStream_t st) {
@@ -1987,7 +2001,7 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
     if (int rc = ensure_dynamic_smem(full ? reinterpret_cast<const void*>(jacobi_cross_kernel<true>)
                                           : reinterpret_cast<const void*>(jacobi_cross_kernel<false>), smem))
         return rc;
-    dim3 grid(mod_cross_pairs(nblk, round), count);
+    dim3 grid(mod_cross_pairs(nblk, round) + ((round & 1) ? 0 : 1), count);
     if (full)
         jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
                                                                      s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride,
@@ -1998,28 +2012,6 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
                                                                       launch_id, 1);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
-    if ((round & 1) == 0) {
-        ColsplitArgs a;
-        a.X = X;
-        a.strideX = strideX;
-        a.mat0 = mat0;
-        a.count = count;
-        a.ld = pl.ld;
-        a.ldot = pl.ldot;
-        a.ltot_r = ltot_r;
-        a.nblk = nblk;
-        a.round = round;
-        a.full16 = 2;
-        a.cpl = -1;
-        a.rot = s.rot;
-        a.done = s.done;
-        a.tol2 = tol2;
-        a.phase_clk = nullptr;
-        a.stamps = s.stamps;
-        a.stamp_stride = s.stamp_stride;
-        a.launch_id = launch_id;
-        if (int rc = launch_jacobi_colsplit(a, st)) return rc;
-    }
     return 0;
 }
 
@@ -2027,31 +2019,6 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
                      int inner, double tol2, double eabs2, int launch_id, cudaStream_t st) {
     static const int cross_enabled = env_int("MPSB_JACOBI_CROSS", 1);
     const int ltot_r = round_up(pl.ltot, 32);
-    // rows of <= 256 columns: column-split kernel for every round (round 0 plays the full 16-row tournament)
-    // MPSB_JACOBI_COLSPLIT: 0 off | 1, 2: single-chain kernel with 1 / 2 columns per lane | 3, 4: sub-group kernel with 4 / 2 warps per sub-group
-    const int cs_mode = env_int("MPSB_JACOBI_COLSPLIT", 0);
-    if (cs_mode && pl.n_pad / 8 > 2 && colsplit_supported(pl.bsz, ltot_r, pl.n_pad / 8)) {
-        ColsplitArgs a;
-        a.X = X;
-        a.strideX = (long long)pl.n_pad * pl.ld;
-        a.mat0 = mat0;
-        a.count = count;
-        a.ld = pl.ld;
-        a.ldot = pl.ldot;
-        a.ltot_r = ltot_r;
-        a.nblk = pl.n_pad / 8;
-        a.round = round;
-        a.full16 = (round == 0);
-        a.cpl = cs_mode == 4 ? -1 : cs_mode == 3 ? 0 : (cs_mode == 2 ? 2 : 1);
-        a.rot = s.rot;
-        a.done = s.done;
-        a.tol2 = tol2;
-        a.phase_clk = g_prof.enabled > 1 ? s.phase_clk : nullptr;
-        a.stamps = s.stamps;
-        a.stamp_stride = s.stamp_stride;
-        a.launch_id = launch_id;
-        return launch_jacobi_colsplit(a, st);
-    }
     if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
         const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
         const bool full = (ltot_r == 256 && pl.ldot == 256);
