@@ -356,14 +356,40 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in (Bi_p, Bj_p, Sl_p, U_p))
     d2h = sum(t.numel() * t.element_size() for t in (Bio_p, Bjo_p, Sro_p, rk_p))
 
-    # per-chain observables of the last step (entanglement entropy of the new bond, kept rank), gathered over the
-    # ranks with the path's one collective (outside the timed region)
+    # per-chain observables of the last step, computed through the batched transfer entry point and gathered over the
+    # ranks with the path's one collective (outside the timed region): entanglement entropy of the new bond, kept rank,
+    # <sigma_z> on the left site and the TFIM bond energy <-ZZ - (XI + IX)/2> of the updated pair
+    # (DMRG/MPS.py:358-410 with E_0 = diag(Sl^2); the synthetic bonds have open ends, so these are the reference's
+    # `corr` / `measure` sums for the two updated tensors taken as they are)
     from dmrg_b200.batched import gather_observables
-    p2 = Sro * Sro
-    ent = -(torch.where(p2 > 0, p2 * torch.log(p2.clamp_min(1e-300)), torch.zeros_like(p2))).sum(dim=1)
-    obs = gather_observables(torch.stack([ent, rk.to(torch.float64)], dim=1))
+
+    def transfer(E, A, Bt, op, dd):
+        out = torch.empty((n, A.shape[-1], Bt.shape[-1]), dtype=torch.complex128, device=dev)
+        wsb, wsbn = L.workspace(lib.mpsb_transfer_batched_workspace(n, CHI, CHI, dd, A.shape[-1], Bt.shape[-1]))
+        opd = L.to_device(op)
+        L.check(lib.mpsb_transfer_step_batched(n, CHI, CHI, dd, A.shape[-1], Bt.shape[-1], L.ptr(E), CHI * CHI, L.ptr(A),
+                                               A[0].numel(), L.ptr(Bt), Bt[0].numel(), L.ptr(opd), 0, L.ptr(out),
+                                               out[0].numel(), wsb, wsbn, L.stream_ptr()), "mpsb_transfer_step_batched")
+        return out
+    E0 = torch.zeros((n, CHI, CHI), dtype=torch.complex128, device=dev)
+    E0.diagonal(dim1=1, dim2=2).copy_(L.to_device(L.to_host(Sl) ** 2))
+    sz, sx, i2 = np.diag([1.0, -1.0]), np.array([[0.0, 1.0], [1.0, 0.0]]), np.eye(2)
+    z_left = transfer(E0, Bio, Bio, sz, D).diagonal(dim1=1, dim2=2).contiguous()
+    blk = torch.empty((n, CHI, D * D, CHI), dtype=torch.complex128, device=dev)
+    L.zgemm(Bio, Bjo, blk, CHI * D, D * CHI, CHI, CHI, D * CHI, D * CHI, batch1=n, sA=(site, 0), sB=(site, 0),
+            sC=(CHI * D * D * CHI, 0))
+    hb = -np.kron(sz, sz) - 0.5 * (np.kron(sx, i2) + np.kron(i2, sx))
+    e_bond = transfer(E0, blk, blk, hb.T, D * D).diagonal(dim1=1, dim2=2).contiguous()
+    p2 = L.to_host(Sro) ** 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ent = -np.where(p2 > 0, p2 * np.log(p2), 0.0).sum(axis=1)
+    local = np.stack([ent, L.to_host(rk).astype(float), L.to_host(z_left).sum(axis=1).real,
+                      L.to_host(e_bond).sum(axis=1).real], axis=1)
+    obs = gather_observables(torch.from_numpy(local).to(dev))
     obs_summary = {"chains": int(obs.shape[0]), "mean_entropy": float(obs[:, 0].mean().item()),
-                   "mean_rank": float(obs[:, 1].mean().item())}
+                   "mean_rank": float(obs[:, 1].mean().item()), "mean_sigma_z_left": float(obs[:, 2].mean().item()),
+                   "mean_bond_energy": float(obs[:, 3].mean().item()),
+                   "gathered": "entropy, rank, <sigma_z>, <h_bond> per chain, one all-gather"}
 
     if rank != 0:
         if world > 1:
@@ -406,7 +432,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
     except (OSError, ValueError):
         pass
-    roofline = {"kernel": "jacobi_cross_kernel + jacobi_gram_kernel (all Jacobi sweeps of one step)", "bound": "fp64",
+    roofline = {"kernel": "jacobi_cross_kernel (all Jacobi sweeps of one step, modulus ordering; self tasks ride in the same launches)", "bound": "fp64",
                 "achieved": jac_flop / jac_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": jac_flop / jac_s / 1e12 / fp64_peak,
                 "traffic": traffic,

@@ -38,6 +38,14 @@ SIGNATURES = {
     "mpsb_scale_rows": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "mpsb_transpose": (_i, [_i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "mpsb_gauge_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "mpsb_gauge_batched_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "mpsb_gauge_left_batched": (_i, [_i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _i, _vp, _ll, _vp, _ll, _vp,
+                                     _ll, _vp, _vp, _sz, _vp]),
+    "mpsb_gauge_right_batched": (_i, [_i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _i, _vp, _ll, _vp, _ll, _vp,
+                                      _ll, _vp, _vp, _sz, _vp]),
+    "mpsb_transfer_batched_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "mpsb_transfer_step_batched": (_i, [_i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz,
+                                        _vp]),
     "mpsb_gauge_left": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_gauge_right": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_transfer_workspace": (_sz, [_i, _i, _i, _i, _i]),

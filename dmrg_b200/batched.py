@@ -31,6 +31,7 @@ class ChainBatch:
         self.M = _lib.zeros((self.L, self.n, P, d, P))
         self.S = _lib.zeros((self.L + 1, self.n, P), "f64")
         self.rank = _lib.zeros((self.L + 1, self.n), "i32")
+        self.canonical = False
 
     @classmethod
     def from_chains(cls, chains, cap, trun=None, err=1e-6):
@@ -51,6 +52,7 @@ class ChainBatch:
                 Sh[b, c, :len(s)] = s
                 Rh[b, c] = len(s)
         self.M, self.S, self.rank = _lib.to_device(Mh), _lib.to_device(Sh, np.float64), _lib.to_device(Rh, np.int32)
+        self.canonical = True          # by contract of this constructor (call canon() otherwise)
         return self
 
     @classmethod
@@ -103,7 +105,111 @@ class ChainBatch:
             return make
         {1: ST.ST1, 2: ST.ST2, 4: ST.ST4}[order]((worker(0), worker(1)), nsteps)
 
+    # ---- gauge ------------------------------------------------------------------------------------------------
+    def canon(self):
+        """Canonical B form of every chain: left sweep, right sweep, boundary phases divided back in - the reference's
+        `MPS.canon` (DMRG/MPS.py:295-302: `ortho_left_site` :246-264 for every site, `ortho_right_site` :266-284 back,
+        `unify_end` :286-293) for all n chains at once: 2 L batched gauge calls, no per-site host synchronisation (the
+        ranks stay on the device).  Chains must be closed (bond dimension 1 at both ends), as `ChainBatch` builds them."""
+        lib = _lib.load()
+        n, P, d, L = self.n, self.P, self.dim, self.L
+        site = P * d * P
+        right = _lib.zeros((n, P, 1))          # the reference's dummy boundary tensors (DMRG/MPS.py:124-125), padded
+        left = _lib.zeros((n, 1, P))
+        right[:, 0, 0] = 1.0
+        left[:, 0, 0] = 1.0
+        ws, wsn = _lib.workspace(lib.mpsb_gauge_batched_workspace(n, P, P, d, d * P, P))
+        for i in range(L):
+            nxt, nn, sn = (self.M[i + 1], d * P, site) if i + 1 < L else (right, 1, P)
+            _lib.check(lib.mpsb_gauge_left_batched(n, P, P, d, _lib.ptr(self.M[i]), site, _lib.ptr(self.S[i]), P,
+                                                   _lib.ptr(nxt), sn, nn, self.trun, self.err, P, _lib.ptr(self.M[i]),
+                                                   site, _lib.ptr(self.S[i + 1]), P, _lib.ptr(nxt), sn,
+                                                   _lib.ptr(self.rank[i + 1]), ws, wsn, _lib.stream_ptr()),
+                       "mpsb_gauge_left_batched")
+        for i in reversed(range(L)):
+            prv, npv, sp = (self.M[i - 1], P * d, site) if i > 0 else (left, 1, P)
+            _lib.check(lib.mpsb_gauge_right_batched(n, P, P, d, _lib.ptr(self.M[i]), site, _lib.ptr(self.S[i + 1]), P,
+                                                    _lib.ptr(prv), sp, npv, self.trun, self.err, P, _lib.ptr(self.M[i]),
+                                                    site, _lib.ptr(self.S[i]), P, _lib.ptr(prv), sp,
+                                                    _lib.ptr(self.rank[i]), ws, wsn, _lib.stream_ptr()),
+                       "mpsb_gauge_right_batched")
+        # unify_end: the phases parked in the boundary tensors go back into the end sites (one gate per chain)
+        for tensor, i in ((left[:, 0, 0], 0), (right[:, 0, 0], L - 1)):
+            ph = _lib.to_host(tensor.contiguous())
+            U = _lib.to_device(np.eye(d)[None, :, :] / ph[:, None, None])
+            _lib.check(lib.mpsb_one_site(n, P, P, d, _lib.ptr(self.M[i]), site, _lib.ptr(U), d * d, _lib.ptr(self.M[i]),
+                                         site, _lib.stream_ptr()), "mpsb_one_site")
+        self.canonical = True
+
     # ---- observables ---------------------------------------------------------------------------------------
+    def _transfer(self, E, A, B, op):
+        """One batched transfer-matrix step (DMRG/MPS.py:351-355, 384-388 for every chain): E [n, ka, kb],
+        A [n, ka, d, oa], B [n, kb, d, rb], op None | [d, d] (shared) | [n, d, d] (one per chain) -> [n, oa, rb]."""
+        lib = _lib.load()
+        n, ka, d, oa = (int(v) for v in A.shape)
+        kb, rb = int(B.shape[1]), int(B.shape[3])
+        out = _lib.empty((n, oa, rb))
+        ws, wsn = _lib.workspace(lib.mpsb_transfer_batched_workspace(n, ka, kb, d, oa, rb))
+        op_dev, s_op = None, 0
+        if op is not None:
+            op = np.asarray(op, dtype=complex)
+            op_dev, s_op = _lib.to_device(op), (d * d if op.ndim == 3 else 0)
+        _lib.check(lib.mpsb_transfer_step_batched(n, ka, kb, d, oa, rb, _lib.ptr(E), ka * kb, _lib.ptr(A), ka * d * oa,
+                                                  _lib.ptr(B), kb * d * rb, _lib.ptr(op_dev), s_op, _lib.ptr(out), oa * rb,
+                                                  ws, wsn, _lib.stream_ptr()), "mpsb_transfer_step_batched")
+        return out
+
+    def _schmidt_weights(self, bond):
+        """diag(S[bond]^2) per chain as a device tensor [n, P, P] (the reference starts `corr` from
+        np.diag(Sl**2), DMRG/MPS.py:380)."""
+        s2 = _lib.to_device(_lib.to_host(self.S[bond]) ** 2)
+        E = _lib.zeros((self.n, self.P, self.P))
+        E.diagonal(dim1=1, dim2=2).copy_(s2)
+        return E
+
+    @staticmethod
+    def _traces(E):
+        return _lib.to_host(E.diagonal(dim1=1, dim2=2).contiguous()).sum(axis=1)
+
+    def corr(self, *ops):
+        """<prod_i op_i> of every chain for (site, operator) pairs in site order: array [n] (DMRG/MPS.py:358-389 per
+        chain).  An operator is [d, d] (the same for all chains) or [n, d, d]."""
+        assert getattr(self, "canonical", False), "canon() first"
+        D = dict(ops)
+        if not D:
+            return np.ones(self.n)
+        start, end = min(D), max(D) + 1
+        E = self._schmidt_weights(start)
+        for i in range(start, end):
+            E = self._transfer(E, self.M[i], self.M[i], D.get(i))
+        return self._traces(E).real
+
+    def _block(self, start, nsites):
+        """Product of `nsites` consecutive site tensors of every chain: [n, P, d^nsites, P] (DMRG/MPS.py:323-337)."""
+        n, P, d = self.n, self.P, self.dim
+        blk, dd = self.M[start], d
+        for i in range(start + 1, start + nsites):
+            out = _lib.empty((n, P, dd * d, P))
+            _lib.zgemm(blk, self.M[i], out, P * dd, d * P, P, P, d * P, d * P, batch1=n, sA=(P * dd * P, 0),
+                       sB=(P * d * P, 0), sC=(P * dd * d * P, 0))
+            blk, dd = out, dd * d
+        return blk
+
+    def measure(self, start, op, Hermitian=True):
+        """Expectation value of an operator on n_sites = log_d(sqrt(op.size)) consecutive sites for every chain: array
+        [n] (DMRG/MPS.py:391-410 per chain; like the reference it returns <op^T>).  `op` is
+        [d^k, d^k] or one per chain [n, d^k, d^k]."""
+        assert getattr(self, "canonical", False), "canon() first"
+        op = np.asarray(op)
+        per_chain = op.ndim == 3
+        size = op[0].size if per_chain else op.size
+        nsites = round(np.log(size) / np.log(self.dim) / 2)
+        blk = self._block(start, nsites)
+        opT = np.swapaxes(op, -1, -2)
+        E = self._transfer(self._schmidt_weights(start), blk, blk, np.ascontiguousarray(opT))
+        ret = self._traces(E)
+        return ret.real if Hermitian else ret
+
     def entropies(self):
         """Von Neumann entropy (nats) of every bond of every chain: array [n, L+1]."""
         p = _lib.to_host(self.S) ** 2

@@ -162,11 +162,11 @@ int mpsb_svd_trunc(int batch, int rows, int cols, const void* A, int lda, long l
     cplx* X = static_cast<cplx*>(ar.take(L.X));
     void* state = ar.take(L.state);
     const SvdPlan& pl = L.plan;
-    const long long strideX = (long long)pl.n_pad * pl.ld;
-    for (int b = 0; b < batch; ++b) {
-        MatSrc dot = {static_cast<const cplx*>(A) + (size_t)b * sA, lda, 1, 0, nullptr, 1, 1};
+    {
+        MatSrc dot = {static_cast<const cplx*>(A), lda, 1, 0, nullptr, 1, 1};
+        dot.bs = sA;
         MatSrc aug = {nullptr, 0, 0, 0, nullptr, 1, 1};
-        rc = pack_work_matrix(X + (size_t)b * strideX, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, Uh ? 1 : 0, st);
+        rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, Uh ? 1 : 0, st, batch);
         if (rc) return rc;
     }
     rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
@@ -274,25 +274,29 @@ int mpsb_mpo_site(int batch, int chil, int chir, int d, int wl, int wr, const vo
 // orthogonalisation  X = [ diag(s) U^H | Vh M_next ]  (DMRG/MPS.py:257-264).
 // Right step: X = [ M_i Sr | M_prev^H ], rows = left bond l; afterwards X = [ diag(s) Vh | (M_prev U)^H ]
 // (DMRG/MPS.py:277-284).
-size_t mpsb_gauge_workspace(int chil, int chir, int d, int nother, int k_cap) {
+size_t mpsb_gauge_batched_workspace(int batch, int chil, int chir, int d, int nother, int k_cap) {
     SvdLayout L, R;
-    if (svd_layout(1, chir, chil * d, nother, &L)) return 0;
-    if (svd_layout(1, chil, d * chir, nother, &R)) return 0;
-    const size_t left = L.total + al((size_t)k_cap * chil * d * sizeof(cplx));
-    const size_t right = R.total + al((size_t)k_cap * (nother > 0 ? nother : 1) * sizeof(cplx));
+    if (svd_layout(batch, chir, chil * d, nother, &L)) return 0;
+    if (svd_layout(batch, chil, d * chir, nother, &R)) return 0;
+    const size_t left = L.total + al((size_t)batch * k_cap * chil * d * sizeof(cplx));
+    const size_t right = R.total + al((size_t)batch * k_cap * (nother > 0 ? nother : 1) * sizeof(cplx));
     return left > right ? left : right;
 }
+size_t mpsb_gauge_workspace(int chil, int chir, int d, int nother, int k_cap) {
+    return mpsb_gauge_batched_workspace(1, chil, chir, d, nother, k_cap);
+}
 
-int mpsb_gauge_left(int chil, int chir, int d, const void* M, const double* Sl, const void* M_next, int nnext,
-                    int trun, double err, int k_cap, void* M_out, double* Sr_out, void* M_next_out, int* rank,
-                    void* ws, size_t ws_bytes, void* stream) {
+int mpsb_gauge_left_batched(int batch, int chil, int chir, int d, const void* M, long long sM, const double* Sl,
+                            long long sSl, const void* M_next, long long sMn, int nnext, int trun, double err, int k_cap,
+                            void* M_out, long long sMo, double* Sr_out, long long sSr, void* M_next_out, long long sMno,
+                            int* rank, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && nnext >= 0 && k_cap >= 1, "gauge_left: bad dims");
+    MPSB_REQUIRE(batch >= 1 && chil >= 1 && chir >= 1 && d >= 1 && nnext >= 0 && k_cap >= 1, "gauge_left: bad dims");
     const int rows = chir, ldot = chil * d;
     SvdLayout L;
-    int rc = svd_layout(1, rows, ldot, nnext, &L);
+    int rc = svd_layout(batch, rows, ldot, nnext, &L);
     if (rc) return rc;
-    const size_t tmp_bytes = al((size_t)k_cap * ldot * sizeof(cplx));
+    const size_t tmp_bytes = al((size_t)batch * k_cap * ldot * sizeof(cplx));
     MPSB_REQUIRE(ws && ws_bytes >= L.total + tmp_bytes, "gauge_left: workspace %zu B < required %zu B", ws_bytes,
                  L.total + tmp_bytes);
     Arena ar(ws, ws_bytes);
@@ -302,32 +306,36 @@ int mpsb_gauge_left(int chil, int chir, int d, const void* M, const double* Sl, 
     const SvdPlan& pl = L.plan;
     // X[r][(l,c)] = conj(Sl[l] M[l,c,r]);   X[r][ldot + q] = M_next[r][q]
     MatSrc dot = {static_cast<const cplx*>(M), 1, chir, 1, Sl, d, chil};
+    dot.bs = sM; dot.scale_bs = sSl;
     MatSrc aug = {static_cast<const cplx*>(M_next), nnext, 1, 0, nullptr, 1, 1};
-    rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, 0, st);
+    aug.bs = sMn;
+    rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, 0, st, batch);
     if (rc) return rc;
     rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
     if (rc) return rc;
     SvdOutputs o;
     memset(&o, 0, sizeof(o));
-    o.vh = tmp; o.vh_stride = 0; o.vh_ld = ldot;                       // rows i: conj(U[:, i])
-    o.aug = nnext ? static_cast<cplx*>(M_next_out) : nullptr; o.aug_stride = 0; o.aug_ld = nnext; o.aug_conj = 0;
-    o.s = Sr_out; o.s_stride = 0; o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
+    o.vh = tmp; o.vh_stride = (long long)k_cap * ldot; o.vh_ld = ldot;        // rows i: conj(U[:, i])
+    o.aug = nnext ? static_cast<cplx*>(M_next_out) : nullptr; o.aug_stride = sMno; o.aug_ld = nnext; o.aug_conj = 0;
+    o.s = Sr_out; o.s_stride = sSr; o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
     rc = svd_finalise(pl, X, state, o, st);
     if (rc) return rc;
     // M_out[(l,c)][i] = conj(tmp[i][(l,c)])
-    return transpose_conj(tmp, ldot, k_cap, ldot, static_cast<cplx*>(M_out), k_cap, 1, st);
+    return transpose_conj(tmp, ldot, k_cap, ldot, static_cast<cplx*>(M_out), k_cap, 1, st, batch, (long long)k_cap * ldot,
+                          sMo);
 }
 
-int mpsb_gauge_right(int chil, int chir, int d, const void* M, const double* Sr, const void* M_prev, int nprev,
-                     int trun, double err, int k_cap, void* M_out, double* Sl_out, void* M_prev_out, int* rank,
-                     void* ws, size_t ws_bytes, void* stream) {
+int mpsb_gauge_right_batched(int batch, int chil, int chir, int d, const void* M, long long sM, const double* Sr,
+                             long long sSr, const void* M_prev, long long sMp, int nprev, int trun, double err, int k_cap,
+                             void* M_out, long long sMo, double* Sl_out, long long sSl, void* M_prev_out, long long sMpo,
+                             int* rank, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && nprev >= 0 && k_cap >= 1, "gauge_right: bad dims");
+    MPSB_REQUIRE(batch >= 1 && chil >= 1 && chir >= 1 && d >= 1 && nprev >= 0 && k_cap >= 1, "gauge_right: bad dims");
     const int rows = chil, ldot = d * chir;
     SvdLayout L;
-    int rc = svd_layout(1, rows, ldot, nprev, &L);
+    int rc = svd_layout(batch, rows, ldot, nprev, &L);
     if (rc) return rc;
-    const size_t tmp_bytes = al((size_t)k_cap * (nprev > 0 ? nprev : 1) * sizeof(cplx));
+    const size_t tmp_bytes = al((size_t)batch * k_cap * (nprev > 0 ? nprev : 1) * sizeof(cplx));
     MPSB_REQUIRE(ws && ws_bytes >= L.total + tmp_bytes, "gauge_right: workspace %zu B < required %zu B", ws_bytes,
                  L.total + tmp_bytes);
     Arena ar(ws, ws_bytes);
@@ -337,53 +345,76 @@ int mpsb_gauge_right(int chil, int chir, int d, const void* M, const double* Sr,
     const SvdPlan& pl = L.plan;
     // X[l][(c,r)] = M[l,c,r] Sr[r];   X[l][ldot + a] = conj(M_prev[a][l])
     MatSrc dot = {static_cast<const cplx*>(M), ldot, 1, 0, Sr, 1, chir};
+    dot.bs = sM; dot.scale_bs = sSr;
     MatSrc aug = {static_cast<const cplx*>(M_prev), 1, chil, 1, nullptr, 1, 1};
-    rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, 0, st);
+    aug.bs = sMp;
+    rc = pack_work_matrix(X, pl.n_pad, pl.ld, rows, pl.ldot, pl.ltot, dot, aug, 0, st, batch);
     if (rc) return rc;
     rc = svd_orthogonalise(pl, X, state, st, &g_last_sweeps);
     if (rc) return rc;
     SvdOutputs o;
     memset(&o, 0, sizeof(o));
-    o.vh = static_cast<cplx*>(M_out); o.vh_stride = 0; o.vh_ld = ldot;
-    o.aug = nprev ? tmp : nullptr; o.aug_stride = 0; o.aug_ld = nprev; o.aug_conj = 1;   // tmp[i][a] = (M_prev U)[a][i]
-    o.s = Sl_out; o.s_stride = 0; o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
+    o.vh = static_cast<cplx*>(M_out); o.vh_stride = sMo; o.vh_ld = ldot;
+    o.aug = nprev ? tmp : nullptr; o.aug_stride = (long long)k_cap * nprev; o.aug_ld = nprev; o.aug_conj = 1;   // tmp[i][a] = (M_prev U)[a][i]
+    o.s = Sl_out; o.s_stride = sSl; o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = 1;
     rc = svd_finalise(pl, X, state, o, st);
     if (rc) return rc;
     if (nprev == 0) return 0;
-    return transpose_conj(tmp, nprev, k_cap, nprev, static_cast<cplx*>(M_prev_out), k_cap, 0, st);
+    return transpose_conj(tmp, nprev, k_cap, nprev, static_cast<cplx*>(M_prev_out), k_cap, 0, st, batch,
+                          (long long)k_cap * nprev, sMpo);
+}
+
+int mpsb_gauge_left(int chil, int chir, int d, const void* M, const double* Sl, const void* M_next, int nnext,
+                    int trun, double err, int k_cap, void* M_out, double* Sr_out, void* M_next_out, int* rank,
+                    void* ws, size_t ws_bytes, void* stream) {
+    return mpsb_gauge_left_batched(1, chil, chir, d, M, 0, Sl, 0, M_next, 0, nnext, trun, err, k_cap, M_out, 0, Sr_out, 0,
+                                   M_next_out, 0, rank, ws, ws_bytes, stream);
+}
+
+int mpsb_gauge_right(int chil, int chir, int d, const void* M, const double* Sr, const void* M_prev, int nprev,
+                     int trun, double err, int k_cap, void* M_out, double* Sl_out, void* M_prev_out, int* rank,
+                     void* ws, size_t ws_bytes, void* stream) {
+    return mpsb_gauge_right_batched(1, chil, chir, d, M, 0, Sr, 0, M_prev, 0, nprev, trun, err, k_cap, M_out, 0, Sl_out, 0,
+                                    M_prev_out, 0, rank, ws, ws_bytes, stream);
 }
 
 // ---- dot / corr: transfer-matrix step -----------------------------------------------------------------------
-size_t mpsb_transfer_workspace(int ka, int kb, int d, int oa, int rb) {
+size_t mpsb_transfer_batched_workspace(int batch, int ka, int kb, int d, int oa, int rb) {
     (void)kb; (void)oa;
-    return al((size_t)ka * d * rb * sizeof(cplx)) * 2;
+    return al((size_t)batch * ka * d * rb * sizeof(cplx)) * 2;
+}
+size_t mpsb_transfer_workspace(int ka, int kb, int d, int oa, int rb) {
+    return mpsb_transfer_batched_workspace(1, ka, kb, d, oa, rb);
 }
 
-int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, const void* A, const void* B,
-                       const void* Op, void* E_out, void* ws, size_t ws_bytes, void* stream) {
+int mpsb_transfer_step_batched(int batch, int ka, int kb, int d, int oa, int rb, const void* E, long long sE, const void* A,
+                               long long sA, const void* B, long long sB, const void* Op, long long sOp, void* E_out,
+                               long long sEo, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t need = mpsb_transfer_workspace(ka, kb, d, oa, rb);
+    MPSB_REQUIRE(batch >= 1, "transfer_step: bad batch");
+    const size_t need = mpsb_transfer_batched_workspace(batch, ka, kb, d, oa, rb);
     MPSB_REQUIRE(ws && ws_bytes >= need, "transfer_step: workspace %zu B < required %zu B", ws_bytes, need);
     Arena ar(ws, ws_bytes);
-    cplx* T = static_cast<cplx*>(ar.take((size_t)ka * d * rb * sizeof(cplx)));
-    cplx* T2 = static_cast<cplx*>(ar.take((size_t)ka * d * rb * sizeof(cplx)));
+    const long long sT = (long long)ka * d * rb;
+    cplx* T = static_cast<cplx*>(ar.take((size_t)batch * sT * sizeof(cplx)));
+    cplx* T2 = static_cast<cplx*>(ar.take((size_t)batch * sT * sizeof(cplx)));
     // T[k][(j,r)] = sum_l E[k][l] B[l][(j,r)]
     GemmArgs g;
     g.A = static_cast<const cplx*>(E); g.B = static_cast<const cplx*>(B); g.C = T;
     g.M = ka; g.N = d * rb; g.K = kb; g.lda = kb; g.ldb = d * rb; g.ldc = d * rb; g.opA = 0; g.opB = 0;
-    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    g.batch1 = batch; g.batch2 = 1; g.sA1 = sE; g.sB1 = sB; g.sC1 = sT; g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
     int rc = zgemm(g, st);
     if (rc) return rc;
     const cplx* Tuse = T;
     if (Op) {   // T2[k][i][r] = sum_j Op[i][j] T[k][j][r]
         if (d <= 16) {
-            rc = one_site(1, ka, rb, d, T, 0, static_cast<const cplx*>(Op), 0, T2, 0, st);
+            rc = one_site(batch, ka, rb, d, T, sT, static_cast<const cplx*>(Op), sOp, T2, sT, st);
         } else {   // fused multi-site operators (measure on n sites: d^n x d^n): one small GEMM per left index
             GemmArgs h;
             h.A = static_cast<const cplx*>(Op); h.B = T; h.C = T2;
             h.M = d; h.N = rb; h.K = d; h.lda = d; h.ldb = rb; h.ldc = rb; h.opA = 0; h.opB = 0;
-            h.batch1 = ka; h.batch2 = 1; h.sA1 = 0; h.sB1 = (long long)d * rb; h.sC1 = (long long)d * rb;
-            h.sA2 = h.sB2 = h.sC2 = 0; h.accumulate = 0;
+            h.batch1 = batch; h.batch2 = ka; h.sA1 = sOp; h.sB1 = sT; h.sC1 = sT;
+            h.sA2 = 0; h.sB2 = (long long)d * rb; h.sC2 = (long long)d * rb; h.accumulate = 0;
             rc = zgemm(h, st);
         }
         if (rc) return rc;
@@ -392,7 +423,13 @@ int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, con
     // E'[o][r] = sum_{(k,i)} conj(A[(k,i)][o]) T[(k,i)][r]
     g.A = static_cast<const cplx*>(A); g.B = Tuse; g.C = static_cast<cplx*>(E_out);
     g.M = oa; g.N = rb; g.K = ka * d; g.lda = oa; g.ldb = rb; g.ldc = rb; g.opA = 2; g.opB = 0;
+    g.sA1 = sA; g.sB1 = sT; g.sC1 = sEo;
     return zgemm(g, st);
+}
+
+int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, const void* A, const void* B,
+                       const void* Op, void* E_out, void* ws, size_t ws_bytes, void* stream) {
+    return mpsb_transfer_step_batched(1, ka, kb, d, oa, rb, E, 0, A, 0, B, 0, Op, 0, E_out, 0, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

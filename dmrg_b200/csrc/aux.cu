@@ -8,11 +8,11 @@ namespace mpsb {
 
 namespace {
 
-__device__ __forceinline__ cplx fetch(const MatSrc& m, int i, int j) {
-    cplx v = m.src[(long long)i * m.rs + (long long)j * m.cs];
+__device__ __forceinline__ cplx fetch(const MatSrc& m, int b, int i, int j) {
+    cplx v = m.src[(long long)b * m.bs + (long long)i * m.rs + (long long)j * m.cs];
     if (m.conj) v.y = -v.y;
     if (m.scale) {
-        const double s = m.scale[(j / m.sdiv) % m.smod];
+        const double s = m.scale[(long long)b * m.scale_bs + (j / m.sdiv) % m.smod];
         v.x *= s;
         v.y *= s;
     }
@@ -24,23 +24,26 @@ pack_kernel(cplx* __restrict__ X, int n_pad, int ld, int rows, int ldot, int lto
             int identity) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)n_pad * ld) return;
+    const int b = blockIdx.y;
     const int j = (int)(e % ld), i = (int)(e / ld);
     cplx v = make_double2(0.0, 0.0);
     if (i < rows) {
-        if (j < ldot) v = fetch(dot, i, j);
+        if (j < ldot) v = fetch(dot, b, i, j);
         else if (j < ltot) {
-            if (aug.src) v = fetch(aug, i, j - ldot);
+            if (aug.src) v = fetch(aug, b, i, j - ldot);
             else if (identity && (j - ldot) == i) v = make_double2(1.0, 0.0);
         }
     }
-    X[e] = v;
+    X[(size_t)b * n_pad * ld + e] = v;
 }
 
 // 32x32 tile transpose through shared memory (padded against bank conflicts).
 __global__ void __launch_bounds__(256)
 transpose_kernel(const cplx* __restrict__ in, int ldi, int rows, int cols, cplx* __restrict__ out, int ldo,
-                 int conj) {
+                 int conj, long long s_in, long long s_out) {
     __shared__ cplx tile[32][33];
+    in += (size_t)blockIdx.z * s_in;
+    out += (size_t)blockIdx.z * s_out;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     for (int r = ty; r < 32; r += 8) {
@@ -153,19 +156,22 @@ __global__ void __launch_bounds__(256) dscal_kernel(long long n, double alpha, c
 }  // namespace
 
 int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, const MatSrc& dot, const MatSrc& aug,
-                     int identity, cudaStream_t st) {
+                     int identity, cudaStream_t st, int batch) {
     const long long total = (long long)n_pad * ld;
-    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, n_pad, ld, rows, ldot, ltot, dot, aug, identity);
+    MPSB_REQUIRE(batch >= 1 && batch <= 65535, "pack: batch %d exceeds grid.y", batch);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    pack_kernel<<<grid, 256, 0, st>>>(X, n_pad, ld, rows, ldot, ltot, dot, aug, identity);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st) {
+int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st,
+                   int batch, long long s_in, long long s_out) {
     if (rows == 0 || cols == 0) return 0;
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-    MPSB_REQUIRE(grid.y <= 65535, "transpose: %d rows exceed grid.y", rows);
-    transpose_kernel<<<grid, 256, 0, st>>>(in, ldi, rows, cols, out, ldo, conj);
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+    MPSB_REQUIRE(grid.y <= 65535 && batch >= 1 && batch <= 65535, "transpose: %d rows / batch %d exceed the grid", rows, batch);
+    transpose_kernel<<<grid, 256, 0, st>>>(in, ldi, rows, cols, out, ldo, conj, s_in, s_out);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -97,13 +97,17 @@ struct MatSrc {
     int conj;
     const double* scale;   // may be null; indexed by column j as (j / sdiv) % smod
     int sdiv, smod;
+    long long bs = 0;       // element stride of `src` between the problems of a batch
+    long long scale_bs = 0; // element stride of `scale` between the problems of a batch
 };
 // X[i][0:ldot] <- dot (rows x ldot), X[i][ldot:ltot] <- aug (rows x (ltot-ldot)) or identity when
 // aug.src == nullptr and identity != 0; everything else in the n_pad x ld buffer is zeroed.
+// Batched: problem b reads dot.src + b * dot.bs (scale + b * scale_bs), writes X + b * n_pad * ld - one launch.
 int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, const MatSrc& dot, const MatSrc& aug,
-                     int identity, cudaStream_t st);
-// out[j * ldo + i] = conj?(in[i * ldi + j]),  i < rows, j < cols
-int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st);
+                     int identity, cudaStream_t st, int batch = 1);
+// out[j * ldo + i] = conj?(in[i * ldi + j]),  i < rows, j < cols; batched with element strides s_in / s_out
+int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st,
+                   int batch = 1, long long s_in = 0, long long s_out = 0);
 // out[i][j] = s[i / group] * in[i][j]
 int scale_rows(int rows, int cols, const cplx* in, int ldi, const double* s, int group, cplx* out, int ldo,
                cudaStream_t st);

@@ -47,8 +47,8 @@ gate_scale_kernel(int chil, int chir, int d, const cplx* __restrict__ theta0, lo
 
 constexpr int ONE_SITE_DMAX = 16;
 __global__ void __launch_bounds__(256)
-one_site_kernel(int chil, int chir, int d, const cplx* __restrict__ M, long long sM, const cplx* __restrict__ U,
-                long long sU, cplx* __restrict__ Mo, long long sMo) {
+one_site_kernel(int chil, int chir, int d, const cplx* M, long long sM, const cplx* __restrict__ U, long long sU,
+                cplx* Mo, long long sMo) {      // M and Mo may be the same buffer (in-place gate): no __restrict__
     const int b = blockIdx.y;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)chil * chir) return;

@@ -96,12 +96,32 @@ int mpsb_gauge_right(int chil, int chir, int d, const void* M, const double* Sr,
                      int trun, double err, int k_cap, void* M_out, double* Sl_out, void* M_prev_out, int* rank,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* Batched forms for `batch` independent chains whose tensors share one (zero-padded) shape - ChainBatch.canon
+ * (the reference canonicalises chain by chain: DMRG/MPS.py:295-302 inside a Python loop over MPS objects).  s* are
+ * element strides between consecutive chains; Sr_out / Sl_out / rank hold one entry (row) per chain. */
+size_t mpsb_gauge_batched_workspace(int batch, int chil, int chir, int d, int nother, int k_cap);
+int mpsb_gauge_left_batched(int batch, int chil, int chir, int d, const void* M, long long sM, const double* Sl,
+                            long long sSl, const void* M_next, long long sMn, int nnext, int trun, double err, int k_cap,
+                            void* M_out, long long sMo, double* Sr_out, long long sSr, void* M_next_out, long long sMno,
+                            int* rank, void* ws, size_t ws_bytes, void* stream);
+int mpsb_gauge_right_batched(int batch, int chil, int chir, int d, const void* M, long long sM, const double* Sr,
+                             long long sSr, const void* M_prev, long long sMp, int nprev, int trun, double err, int k_cap,
+                             void* M_out, long long sMo, double* Sl_out, long long sSl, void* M_prev_out, long long sMpo,
+                             int* rank, void* ws, size_t ws_bytes, void* stream);
+
 /* Transfer-matrix step shared by MPS.dot and MPS.corr (DMRG/MPS.py:351-355, 384-388):
  *     E'[o,r] = sum_{k,l,i,j} E[k,l] conj(A[k,i,o]) Op[i,j] B[l,j,r]      (Op = NULL means identity)
  * A is [ka][d][oa], B is [kb][d][rb], E is [ka][kb], E' is [oa][rb]. */
 size_t mpsb_transfer_workspace(int ka, int kb, int d, int oa, int rb);
 int mpsb_transfer_step(int ka, int kb, int d, int oa, int rb, const void* E, const void* A, const void* B,
                        const void* Op, void* E_out, void* ws, size_t ws_bytes, void* stream);
+
+/* The same for `batch` chains (ChainBatch.corr / measure, DMRG/MPS.py:358-410 per chain in the reference);
+ * sOp = 0 shares one operator between the chains. */
+size_t mpsb_transfer_batched_workspace(int batch, int ka, int kb, int d, int oa, int rb);
+int mpsb_transfer_step_batched(int batch, int ka, int kb, int d, int oa, int rb, const void* E, long long sE, const void* A,
+                               long long sA, const void* B, long long sB, const void* Op, long long sOp, void* E_out,
+                               long long sEo, void* ws, size_t ws_bytes, void* stream);
 
 /* Matrix-free effective-Hamiltonian product (replaces building DMRG/iDMRG.py:38-40 and the dense
  * matvec inside eigsh, :57):

@@ -368,3 +368,87 @@ def test_scale_rows_kernel(lib):
     ad, sd = lib.to_device(a), lib.to_device(s, np.float64)
     lib.check(lib.load().mpsb_scale_rows(12, 7, lib.ptr(ad), 7, lib.ptr(sd), 3, lib.ptr(out), 7, lib.stream_ptr()), "scale")
     np.testing.assert_allclose(lib.to_host(out), np.repeat(s, 3)[:, None] * a, rtol=1e-15)
+
+
+def test_chain_batch_canon_and_observables_match_per_chain_mps(lib):
+    """ChainBatch.canon / corr / measure (batched gauge and transfer entry points) against one `MPS` per chain:
+    random NON-canonical chains of different bond dimensions, padded to a common capacity.  Tolerance 1e-10 on Schmidt
+    values, <Z>, <ZZ>, a two-site and a per-chain operator (DMRG/MPS.py:246-302, 358-410)."""
+    from dmrg_b200.MPS import MPS
+    from dmrg_b200.batched import ChainBatch
+    from dmrg_b200.spin import sigma
+    n, Lc, cap = 6, 8, 16
+    Z, X = sigma[3], sigma[1]
+    H2 = -np.kron(Z, Z) - 0.7 * (np.kron(X, np.eye(2)) + np.kron(np.eye(2), X))
+    chains, singles = [], []
+    for c in range(n):
+        rs = np.random.RandomState(900 + c)
+        top = 4 + 2 * c
+        x = [min(2 ** i, 2 ** (Lc - i), top) for i in range(Lc + 1)]
+        Ms = [rs.randn(x[i], 2, x[i + 1]) + 1j * rs.randn(x[i], 2, x[i + 1]) for i in range(Lc)]
+        chains.append((Ms, [np.ones(1)] + [np.ones(x[b]) for b in range(1, Lc + 1)]))
+        m = MPS([t.copy() for t in Ms], 2, trun=cap, err=1e-12)
+        m.canon()
+        singles.append(m)
+    batch = ChainBatch.from_chains(chains, cap=cap, trun=cap, err=1e-12)
+    batch.canon()
+    ranks = batch.ranks()
+    for c in range(n):
+        _, ss = batch.chain(c)
+        for b in range(Lc + 1):
+            ref = np.asarray(singles[c].s[b], dtype=float)
+            assert ranks[c, b] == len(ref)
+            np.testing.assert_allclose(ss[b], ref, rtol=1e-10, atol=1e-13)
+    z3 = batch.corr((3, Z))
+    zz = batch.corr((2, Z), (5, Z))
+    e2 = batch.measure(3, H2)
+    ops = np.stack([np.cos(0.3 * c) * Z + np.sin(0.3 * c) * X for c in range(n)])
+    per = batch.corr((4, ops))
+    for c in range(n):
+        assert abs(z3[c] - singles[c].corr((3, Z))) < 1e-10
+        assert abs(zz[c] - singles[c].corr((2, Z), (5, Z))) < 1e-10
+        assert abs(e2[c] - singles[c].measure(3, H2)) < 1e-10
+        assert abs(per[c] - singles[c].corr((4, ops[c]))) < 1e-10
+    # canon() after a truncating Trotter step restores unit norm: <1> = 1 for every chain
+    batch.tebd(H2, 0.1, 1)
+    batch.canon()
+    np.testing.assert_allclose(batch.corr((0, np.eye(2))), np.ones(n), atol=1e-12)
+
+
+def test_two_streams_do_not_share_scratch(lib):
+    """Calls issued on two CUDA streams draw their scratch from separate workspaces: two batches
+    updated concurrently on two streams equal the same batches updated one after the other."""
+    import torch
+    from dmrg_b200.batched import ChainBatch
+    from dmrg_b200.spin import sigma
+    Z, X = sigma[3], sigma[1]
+    H2 = -np.kron(Z, Z) - 0.5 * (np.kron(X, np.eye(2)) + np.kron(np.eye(2), X))
+    U = lib.to_device(la.expm(-0.2j * H2).reshape(2, 2, 2, 2))
+
+    def make(seed):
+        return ChainBatch.from_chains([_random_canonical_chain(seed + c, 8, 16) for c in range(8)], cap=16, trun=16, err=1e-12)
+
+    serial = [make(50), make(70)]
+    for b in serial:
+        for i in range(0, 7, 2):
+            b.apply_bond(U, i)
+    torch.cuda.synchronize()
+    conc = [make(50), make(70)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for i in range(0, 7, 2):
+        for b, st in zip(conc, streams):
+            with torch.cuda.stream(st):
+                b.apply_bond(U, i)
+    torch.cuda.synchronize()
+    for a, b in zip(serial, conc):
+        np.testing.assert_array_equal(lib.to_host(a.S), lib.to_host(b.S))
+        np.testing.assert_array_equal(lib.to_host(a.M), lib.to_host(b.M))
+
+
+def _random_canonical_chain(seed, Lc, chi):
+    rs = np.random.RandomState(seed)
+    x = [min(2 ** i, 2 ** (Lc - i), chi) for i in range(Lc + 1)]
+    o = OracleMPS([rs.randn(x[i], 2, x[i + 1]) + 1j * rs.randn(x[i], 2, x[i + 1]) for i in range(Lc)], trun=chi, err=1e-12)
+    o.canon()
+    return [m.copy() for m in o.M[:Lc]], [np.array(v) for v in o.s]
