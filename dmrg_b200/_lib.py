@@ -37,6 +37,15 @@ SIGNATURES = {
     "mpsb_predict_theta": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_scale_rows": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "mpsb_transpose": (_i, [_i, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "mpsb_transpose_batched": (_i, [_i, _i, _i, _vp, _i, _ll, _vp, _i, _ll, _i, _vp]),
+    "mpsb_heff_batched_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "mpsb_heff_matvec_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz, _vp]),
+    "mpsb_lanczos_batched_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "mpsb_lanczos_ground_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _pd, _pd, _pi,
+                                         _vp, _sz, _vp]),
+    "mpsb_env_batched_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "mpsb_env_left_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _ll, _vp, _sz, _vp]),
+    "mpsb_env_right_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _ll, _vp, _sz, _vp]),
     "mpsb_gauge_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "mpsb_gauge_batched_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mpsb_gauge_left_batched": (_i, [_i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _i, _vp, _ll, _vp, _ll, _vp,

@@ -249,6 +249,12 @@ int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int l
                           static_cast<cudaStream_t>(stream));
 }
 
+int mpsb_transpose_batched(int batch, int rows, int cols, const void* in, int ldi, long long s_in, void* out, int ldo,
+                           long long s_out, int conj, void* stream) {
+    return transpose_conj(static_cast<const cplx*>(in), ldi, rows, cols, static_cast<cplx*>(out), ldo, conj,
+                          static_cast<cudaStream_t>(stream), batch, s_in, s_out);
+}
+
 int mpsb_scale_rows(int rows, int cols, const void* in, int ldi, const double* s, int group, void* out, int ldo,
                     void* stream) {
     MPSB_REQUIRE(in && s && out, "scale_rows: null buffer");

@@ -67,10 +67,12 @@ constexpr int DOT_THREADS = 256;
 // `part` holds m * nchunk partial sums followed by m ticket counters (zero on entry, zero again on exit).
 __global__ void __launch_bounds__(DOT_THREADS)
 dot_fused_kernel(const cplx* __restrict__ V, long long ldv, long long n, const cplx* __restrict__ w,
-                 cplx* __restrict__ part, int nchunk, int m_cap, cplx* __restrict__ y) {
+                 cplx* __restrict__ part, int nchunk, int m_cap, cplx* __restrict__ y, BlasBatch bb) {
     __shared__ double sr[DOT_THREADS / 32], si[DOT_THREADS / 32];
     __shared__ int is_last;
     const int j = blockIdx.y, ch = blockIdx.x;
+    V += (size_t)blockIdx.z * bb.sV; w += (size_t)blockIdx.z * bb.sw;
+    part += (size_t)blockIdx.z * bb.spart; y += (size_t)blockIdx.z * bb.sc;
     unsigned int* tickets = reinterpret_cast<unsigned int*>(part + (size_t)m_cap * nchunk);
     const long long per = (n + nchunk - 1) / nchunk;
     const long long lo = (long long)ch * per, hi = lo + per < n ? lo + per : n;
@@ -117,9 +119,10 @@ dot_fused_kernel(const cplx* __restrict__ V, long long ldv, long long n, const c
 
 __global__ void __launch_bounds__(256)
 axpy_multi_kernel(const cplx* __restrict__ V, long long ldv, int m, long long n, const cplx* __restrict__ c,
-                  double sign, cplx* __restrict__ w) {
+                  double sign, cplx* __restrict__ w, BlasBatch bb) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    V += (size_t)blockIdx.y * bb.sV; w += (size_t)blockIdx.y * bb.sw; c += (size_t)blockIdx.y * bb.sc;
     cplx acc = w[i];
     for (int j = 0; j < m; ++j) {
         cplx cj = c[j];
@@ -133,9 +136,11 @@ axpy_multi_kernel(const cplx* __restrict__ V, long long ldv, int m, long long n,
 }
 
 // w *= 1/sqrt(nrm2[0].x); a vanishing norm (Lanczos breakdown) zeroes the vector instead of producing NaNs
-__global__ void __launch_bounds__(256) normalise_kernel(long long n, const cplx* __restrict__ nrm2, cplx* __restrict__ w) {
+__global__ void __launch_bounds__(256) normalise_kernel(long long n, const cplx* __restrict__ nrm2, cplx* __restrict__ w,
+                                                        BlasBatch bb) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    nrm2 += (size_t)blockIdx.y * bb.sc; w += (size_t)blockIdx.y * bb.sw;
     const double v2 = nrm2[0].x;
     const double sc = v2 > 0.0 ? rsqrt(v2) : 0.0;
     cplx v = w[i];
@@ -208,28 +213,31 @@ int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_
 }
 
 int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
-                int m_cap, cudaStream_t st) {
+                int m_cap, cudaStream_t st, BlasBatch bb) {
     if (m == 0) return 0;
-    MPSB_REQUIRE(m <= 65535 && m <= m_cap && nchunk >= 1, "zdotc_multi: bad m=%d (cap %d) nchunk=%d", m, m_cap, nchunk);
-    dim3 grid(nchunk, m);
-    dot_fused_kernel<<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk, m_cap, y);
+    MPSB_REQUIRE(m <= 65535 && m <= m_cap && nchunk >= 1 && bb.batch >= 1 && bb.batch <= 65535,
+                 "zdotc_multi: bad m=%d (cap %d) nchunk=%d batch=%d", m, m_cap, nchunk, bb.batch);
+    dim3 grid(nchunk, m, bb.batch);
+    dot_fused_kernel<<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk, m_cap, y, bb);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
-                cudaStream_t st) {
+                cudaStream_t st, BlasBatch bb) {
     if (m == 0 || n == 0) return 0;
-    axpy_multi_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(V, ldv, m, n, c, sign, w);
+    dim3 grid((unsigned)((n + 255) / 256), bb.batch);
+    axpy_multi_kernel<<<grid, 256, 0, st>>>(V, ldv, m, n, c, sign, w, bb);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st) {
+int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st, BlasBatch bb) {
     if (n == 0) return 0;
-    normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, nrm2, w);
+    dim3 grid((unsigned)((n + 255) / 256), bb.batch);
+    normalise_kernel<<<grid, 256, 0, st>>>(n, nrm2, w, bb);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;

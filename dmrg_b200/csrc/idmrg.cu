@@ -24,10 +24,12 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 // WW[i][k][B][C][b][c] = sum_j W[i][j][B][b] W[j][k][C][c]
-__global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, cplx* __restrict__ WW) {
+__global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, long long sW, cplx* __restrict__ WW) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = w * w * d * d * d * d;
     if (e >= total) return;
+    W += (size_t)blockIdx.y * sW;
+    WW += (size_t)blockIdx.y * total;
     int r = e;
     const int c = r % d; r /= d;
     const int b = r % d; r /= d;
@@ -49,11 +51,14 @@ __global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, cplx* 
 // One thread per (A, B, C, dr) producing the w values of k (contiguous store).  Zero blocks of the
 // (lower-triangular, mostly empty) MPO are skipped; the test is uniform across the warp.
 __global__ void __launch_bounds__(256)
-ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, const cplx* __restrict__ T1,
-                cplx* __restrict__ T3) {
+ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, long long sWW,
+                const cplx* __restrict__ T1, cplx* __restrict__ T3) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)chil * d * d * chir;
     if (e >= total) return;
+    WW += (size_t)blockIdx.y * sWW;                      // chain of the batch
+    T1 += (size_t)blockIdx.y * total * w;
+    T3 += (size_t)blockIdx.y * total * w;
     const int dr = (int)(e % chir);
     long long r = e / chir;
     const int C = (int)(r % d); r /= d;
@@ -81,11 +86,14 @@ ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, c
 // Left environment:  T2[C][i][l][B] = sum_{k,m} W[k][C][l][m] T1[k][i][m][B]
 // Right environment: T2[C][l][i][B] = sum_{k,m} W[C][k][l][m] T1[k][i][B][m]
 __global__ void __launch_bounds__(256)
-env_w_kernel(int right, int chi, int chin, int d, int w, const cplx* __restrict__ W, const cplx* __restrict__ T1,
-             cplx* __restrict__ T2) {
+env_w_kernel(int right, int chi, int chin, int d, int w, const cplx* __restrict__ W, long long sW,
+             const cplx* __restrict__ T1, cplx* __restrict__ T2) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)w * chi * d * chin;
     if (e >= total) return;
+    W += (size_t)blockIdx.y * sW;
+    T1 += (size_t)blockIdx.y * total;
+    T2 += (size_t)blockIdx.y * total;
     const int B = (int)(e % chin);
     long long r = e / chin;
     int i, l;
@@ -107,7 +115,10 @@ env_w_kernel(int right, int chi, int chin, int d, int w, const cplx* __restrict_
 
 struct Heff {
     int chil, chir, d, w;
+    int batch;          // independent chains, every tensor below has a leading chain index
     const cplx* R;      // as given: [D][dr][k]
+    long long sR;       // chain stride of R
+    long long sWW;      // chain stride of WW (0: one MPO shared by all chains)
     cplx *Lt, *WW, *T1, *T3;
     size_t n;           // chil*d*d*chir
 };
@@ -136,44 +147,54 @@ predict_scale_kernel(int chi, int chip, int d, const cplx* __restrict__ B, const
     }
 }
 
-size_t heff_bytes(int chil, int chir, int d, int w) {
+size_t heff_bytes(int chil, int chir, int d, int w, int batch = 1) {
     const size_t n = (size_t)chil * d * d * chir;
-    return al((size_t)w * chil * chil * sizeof(cplx)) + al((size_t)w * w * d * d * d * d * sizeof(cplx)) +
-           al(n * w * sizeof(cplx)) * 2;
+    return al((size_t)batch * w * chil * chil * sizeof(cplx)) + al((size_t)batch * w * w * d * d * d * d * sizeof(cplx)) +
+           al((size_t)batch * n * w * sizeof(cplx)) * 2;
 }
+// L, R: one environment per chain (strides sL, sR in elements); W: one MPO per chain (sW) or a shared one (sW = 0).
 int heff_prepare(Heff& h, int chil, int chir, int d, int w, const cplx* L, const cplx* W, const cplx* R, void* ws,
-                 cudaStream_t st) {
-    h.chil = chil; h.chir = chir; h.d = d; h.w = w; h.R = R;
+                 cudaStream_t st, int batch = 1, long long sL = 0, long long sW = 0, long long sR = 0) {
+    h.chil = chil; h.chir = chir; h.d = d; h.w = w; h.R = R; h.batch = batch; h.sR = sR;
     h.n = (size_t)chil * d * d * chir;
+    const int ww = w * w * d * d * d * d;
     unsigned char* p = static_cast<unsigned char*>(ws);
-    h.Lt = reinterpret_cast<cplx*>(p); p += al((size_t)w * chil * chil * sizeof(cplx));
-    h.WW = reinterpret_cast<cplx*>(p); p += al((size_t)w * w * d * d * d * d * sizeof(cplx));
-    h.T1 = reinterpret_cast<cplx*>(p); p += al(h.n * w * sizeof(cplx));
+    h.Lt = reinterpret_cast<cplx*>(p); p += al((size_t)batch * w * chil * chil * sizeof(cplx));
+    h.WW = reinterpret_cast<cplx*>(p); p += al((size_t)batch * ww * sizeof(cplx));
+    h.T1 = reinterpret_cast<cplx*>(p); p += al((size_t)batch * h.n * w * sizeof(cplx));
     h.T3 = reinterpret_cast<cplx*>(p);
-    int rc = perm_last_to_first(L, chil * chil, w, h.Lt, st);   // Lt[i][A][a] = L[A][a][i]
+    // Lt[i][A][a] = L[A][a][i]
+    int rc = transpose_conj(L, w, chil * chil, w, h.Lt, chil * chil, 0, st, batch, sL, (long long)w * chil * chil);
     if (rc) return rc;
-    const int total = w * w * d * d * d * d;
-    ww_build_kernel<<<(total + 127) / 128, 128, 0, st>>>(w, d, W, h.WW);
+    const int nww = (sW == 0) ? 1 : batch;
+    h.sWW = (sW == 0) ? 0 : ww;
+    dim3 grid((ww + 127) / 128, nww);
+    ww_build_kernel<<<grid, 128, 0, st>>>(w, d, W, sW, h.WW);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
-int heff_apply(const Heff& h, const cplx* theta, cplx* out, cudaStream_t st) {
+// theta / out: [batch][n] with chain strides s_theta / s_out
+int heff_apply(const Heff& h, const cplx* theta, cplx* out, cudaStream_t st, long long s_theta = 0, long long s_out = 0) {
     const int ncol = h.d * h.d * h.chir;
     GemmArgs g;
     // T1[(i,A)][(b,c,dr)] = sum_a Lt[(i,A)][a] theta[a][(b,c,dr)]
     g.A = h.Lt; g.B = theta; g.C = h.T1;
     g.M = h.w * h.chil; g.N = ncol; g.K = h.chil; g.lda = h.chil; g.ldb = ncol; g.ldc = ncol; g.opA = 0; g.opB = 0;
-    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    g.batch1 = h.batch; g.batch2 = 1;
+    g.sA1 = (long long)h.w * h.chil * h.chil; g.sB1 = s_theta; g.sC1 = (long long)h.n * h.w;
+    g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
     int rc = zgemm(g, st);
     if (rc) return rc;
-    ww_apply_kernel<<<(unsigned)((h.n + 255) / 256), 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.T1, h.T3);
+    dim3 grid((unsigned)((h.n + 255) / 256), h.batch);
+    ww_apply_kernel<<<grid, 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.sWW, h.T1, h.T3);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     // out[(A,B,C)][D] = sum_{(dr,k)} T3[(A,B,C)][(dr,k)] R[D][(dr,k)]
     g.A = h.T3; g.B = h.R; g.C = out;
     g.M = h.chil * h.d * h.d; g.N = h.chir; g.K = h.chir * h.w; g.lda = g.K; g.ldb = g.K; g.ldc = h.chir;
     g.opA = 0; g.opB = 1;
+    g.sA1 = (long long)h.n * h.w; g.sB1 = h.sR; g.sC1 = s_out;
     return zgemm(g, st);
 }
 
@@ -219,154 +240,208 @@ using namespace mpsb;
 
 extern "C" {
 
+size_t mpsb_heff_batched_workspace(int batch, int chil, int chir, int d, int w) {
+    return heff_bytes(chil, chir, d, w, batch);
+}
 size_t mpsb_heff_workspace(int chil, int chir, int d, int w) { return heff_bytes(chil, chir, d, w); }
 
-int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
-                     void* out, void* ws, size_t ws_bytes, void* stream) {
+int mpsb_heff_matvec_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                             long long sW, const void* R, long long sR, const void* theta, long long s_theta, void* out,
+                             long long s_out, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && w >= 1, "heff_matvec: bad dims");
-    const size_t need = heff_bytes(chil, chir, d, w);
+    MPSB_REQUIRE(batch >= 1 && chil >= 1 && chir >= 1 && d >= 1 && w >= 1, "heff_matvec: bad dims");
+    const size_t need = heff_bytes(chil, chir, d, w, batch);
     MPSB_REQUIRE(ws && ws_bytes >= need, "heff_matvec: workspace %zu B < required %zu B", ws_bytes, need);
     Heff h;
     int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
-                          static_cast<const cplx*>(R), ws, st);
+                          static_cast<const cplx*>(R), ws, st, batch, sL, sW, sR);
     if (rc) return rc;
-    return heff_apply(h, static_cast<const cplx*>(theta), static_cast<cplx*>(out), st);
+    return heff_apply(h, static_cast<const cplx*>(theta), static_cast<cplx*>(out), st, s_theta, s_out);
+}
+
+int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
+                     void* out, void* ws, size_t ws_bytes, void* stream) {
+    return mpsb_heff_matvec_batched(1, chil, chir, d, w, L, 0, W, 0, R, 0, theta, 0, out, 0, ws, ws_bytes, stream);
 }
 
 constexpr int LANCZOS_KEEP = 8;        // Ritz vectors carried across a (thick) restart
+constexpr int LANCZOS_NCHUNK = 64;
 
-size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
+size_t mpsb_lanczos_batched_workspace(int batch, int chil, int chir, int d, int w, int krylov) {
     const size_t n = (size_t)chil * d * d * chir;
-    const int nchunk = 64;
     const size_t kk = (size_t)krylov + 2;
-    return heff_bytes(chil, chir, d, w) + al(n * sizeof(cplx)) * (kk + LANCZOS_KEEP) + al(kk * (nchunk + 1) * sizeof(cplx)) +
-           al(kk * kk * sizeof(cplx)) * 2 + al(kk * sizeof(cplx)) * 2 + al(kk * LANCZOS_KEEP * sizeof(cplx));
+    const size_t b = (size_t)batch;
+    return heff_bytes(chil, chir, d, w, batch) + b * al(n * sizeof(cplx)) * (kk + LANCZOS_KEEP) +
+           al(b * kk * (LANCZOS_NCHUNK + 1) * sizeof(cplx)) + al(b * kk * kk * sizeof(cplx)) * 2 + al(b * kk * sizeof(cplx)) +
+           al(b * kk * LANCZOS_KEEP * sizeof(cplx));
+}
+size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
+    return mpsb_lanczos_batched_workspace(1, chil, chir, d, w, krylov);
 }
 
-// Thick-restart Lanczos with full (twice-applied) reorthogonalisation.
-//  * A cycle extends the orthonormal basis V[0..m] one product at a time; the Gram-Schmidt coefficients stay on the
-//    device (the axpy kernel reads them there) and the new vector is normalised from the device-resident norm, so a
-//    cycle runs without host synchronisation; coefficients are read back once per cycle.
-//  * The projected matrix Hp = V^H H V is assembled from those coefficients (column j: h_ij = c1_i + c2_i, i <= j,
-//    and the norm beta_j below the diagonal).  After a restart its leading block is diag(theta) of the kept Ritz
-//    vectors and the couplings to the continued Lanczos vector are measured by the same Gram-Schmidt pass.
-//  * Restart: keep the LANCZOS_KEEP lowest Ritz vectors (V Y) plus the residual vector v_{m}.
-int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
-                        int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
-                        int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
+// Thick-restart Lanczos with full (twice-applied) reorthogonalisation for `batch` independent chains in lock step
+// (same shapes; per-chain environments, start vectors and - with sW != 0 - MPOs).
+//  * A cycle extends the orthonormal basis V[0..m] of every chain one product at a time; every product, inner-product
+//    pass and update is ONE batched launch over all chains.  The Gram-Schmidt coefficients stay on the device (the
+//    axpy kernel reads them there) and the new vectors are normalised from device-resident norms, so a cycle runs
+//    without host synchronisation; coefficients are read back once per cycle.
+//  * The projected matrices Hp = V^H H V are assembled per chain from those coefficients (column j: h_ij = c1_i +
+//    c2_i, i <= j, and the norm beta_j below the diagonal) and diagonalised on the host.  After a restart the leading
+//    block is diag(theta) of the kept Ritz vectors; the couplings to the continued Lanczos vector are measured by the
+//    same Gram-Schmidt pass.
+//  * Restart: keep the LANCZOS_KEEP lowest Ritz vectors (V Y) plus the residual vector v_m.
+//  * A chain that has converged (or whose Krylov space closed) has its Ritz vector copied to theta and is FROZEN: it
+//    keeps riding along in the batched launches, its later numbers are ignored.  The call ends when every chain is
+//    frozen or max_restarts is reached.
+int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                                long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
+                                int max_restarts, double tol, double* energy_host, double* resid_host, int* n_matvec_host,
+                                void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(chil >= 1 && chir >= 1 && d >= 1 && w >= 1 && krylov >= 2 && max_restarts >= 1,
+    MPSB_REQUIRE(batch >= 1 && chil >= 1 && chir >= 1 && d >= 1 && w >= 1 && krylov >= 2 && max_restarts >= 1,
                  "lanczos_ground: bad arguments");
-    const size_t need = mpsb_lanczos_workspace(chil, chir, d, w, krylov);
+    const size_t need = mpsb_lanczos_batched_workspace(batch, chil, chir, d, w, krylov);
     MPSB_REQUIRE(ws && ws_bytes >= need, "lanczos_ground: workspace %zu B < required %zu B", ws_bytes, need);
     const size_t n = (size_t)chil * d * d * chir;
-    const int nchunk = 64;
+    const int nchunk = LANCZOS_NCHUNK;
     int m = krylov;
     if ((size_t)m > n) m = (int)n;
     const size_t kk = (size_t)krylov + 2;
+    const size_t nb = (size_t)batch;
     unsigned char* p = static_cast<unsigned char*>(ws);
     Heff h;
     int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
-                          static_cast<const cplx*>(R), p, st);
+                          static_cast<const cplx*>(R), p, st, batch, sL, sW, sR);
     if (rc) return rc;
-    p += heff_bytes(chil, chir, d, w);
+    p += heff_bytes(chil, chir, d, w, batch);
     const size_t vstride = al(n * sizeof(cplx)) / sizeof(cplx);
-    cplx* V = reinterpret_cast<cplx*>(p);                 p += al(n * sizeof(cplx)) * kk;
-    cplx* Vk = reinterpret_cast<cplx*>(p);                p += al(n * sizeof(cplx)) * LANCZOS_KEEP;   // Ritz vectors
-    cplx* part = reinterpret_cast<cplx*>(p);              p += al(kk * (nchunk + 1) * sizeof(cplx));   // partials + tickets
-    cplx* C1 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-1 coefficients, row j
-    cplx* C2 = reinterpret_cast<cplx*>(p);                p += al(kk * kk * sizeof(cplx));   // pass-2 coefficients
-    cplx* N2 = reinterpret_cast<cplx*>(p);                p += al(kk * sizeof(cplx));        // ||w_j||^2
-    p += al(kk * sizeof(cplx));                                                              // (spare slot kept so workspace sizes stay stable)
-    cplx* Yd = reinterpret_cast<cplx*>(p);                                                     // [keep][kk] Ritz coefficients
+    const long long sV = (long long)(vstride * kk), sVk = (long long)(vstride * LANCZOS_KEEP);
+    const long long sPart = (long long)(kk * (nchunk + 1)), sC = (long long)(kk * kk), sN = (long long)kk,
+                    sY = (long long)(kk * LANCZOS_KEEP);
+    cplx* V = reinterpret_cast<cplx*>(p);                 p += nb * al(n * sizeof(cplx)) * kk;             // [chain][kk][vstride]
+    cplx* Vk = reinterpret_cast<cplx*>(p);                p += nb * al(n * sizeof(cplx)) * LANCZOS_KEEP;   // Ritz vectors
+    cplx* part = reinterpret_cast<cplx*>(p);              p += al(nb * kk * (nchunk + 1) * sizeof(cplx));   // partials + tickets
+    cplx* C1 = reinterpret_cast<cplx*>(p);                p += al(nb * kk * kk * sizeof(cplx));   // pass-1 coefficients, row j
+    cplx* C2 = reinterpret_cast<cplx*>(p);                p += al(nb * kk * kk * sizeof(cplx));   // pass-2 coefficients
+    cplx* N2 = reinterpret_cast<cplx*>(p);                p += al(nb * kk * sizeof(cplx));        // ||w_j||^2
+    cplx* Yd = reinterpret_cast<cplx*>(p);                                                          // [chain][keep][kk]
     cplx* th = static_cast<cplx*>(theta);
-    std::vector<cplx> h1(kk * kk), h2(kk * kk), hn(kk), hc(kk * LANCZOS_KEEP);
-    std::vector<double> Hp((size_t)m * m, 0.0), T, Y;
+    auto bat = [&](long long sv, long long sw, long long sc) {
+        BlasBatch b;
+        b.batch = batch; b.sV = sv; b.sw = sw; b.sc = sc; b.spart = sPart;
+        return b;
+    };
+    struct Chain {
+        std::vector<double> Hp, T, Y;
+        std::vector<int> idx;
+        double E = 0.0, resid = 0.0, beta_last = 0.0;
+        int mm = 0;
+        bool frozen = false;
+    };
+    std::vector<Chain> ch(nb);
+    for (auto& c : ch) c.Hp.assign((size_t)m * m, 0.0);
+    std::vector<cplx> h1(nb * kk * kk), h2(nb * kk * kk), hn(nb * kk), hc(nb * kk * LANCZOS_KEEP);
     int n_mv = 0;
-    double E = 0.0, resid = 0.0;
 
-    MPSB_CHECK_CUDA(cudaMemsetAsync(part, 0, al(kk * (nchunk + 1) * sizeof(cplx)), st));
-    // normalise the start vector into V[0]
-    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st);
+    MPSB_CHECK_CUDA(cudaMemsetAsync(part, 0, al(nb * kk * (nchunk + 1) * sizeof(cplx)), st));
+    // normalise the start vectors into V[chain][0]
+    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st, bat(s_theta, s_theta, sN));
     if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(cplx), N2, kk * sizeof(cplx), sizeof(cplx), nb,
+                                      cudaMemcpyDeviceToHost, st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-    MPSB_REQUIRE(hn[0].x > 0.0 && std::isfinite(hn[0].x), "lanczos_ground: start vector has norm^2 = %g", hn[0].x);
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-    rc = znormalise((long long)n, N2, V, st);
+    for (size_t c = 0; c < nb; ++c)
+        MPSB_REQUIRE(hn[c * kk].x > 0.0 && std::isfinite(hn[c * kk].x), "lanczos_ground: start vector of chain %zu has norm^2 = %g",
+                     c, hn[c * kk].x);
+    if (batch == 1) MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    else MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(cplx), th, (size_t)s_theta * sizeof(cplx), n * sizeof(cplx), nb,
+                                           cudaMemcpyDeviceToDevice, st));
+    rc = znormalise((long long)n, N2, V, st, bat(0, sV, sN));
     if (rc) return rc;
 
     int j0 = 0;                 // first basis index whose product has not been formed yet
-    bool converged = false;
     const bool dbg = getenv("MPSB_LANCZOS_DEBUG") != nullptr;
     double t_enq = 0.0, t_wait = 0.0, t_host = 0.0;
     auto now = [] { return std::chrono::high_resolution_clock::now(); };
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     // Convergence is also polled inside the FIRST cycle (after 4 steps, then every 8: one small download and a host
-    // eigen-solve of the projected matrix, ~0.1 ms).  A start vector that is already the answer - finite-DMRG sweeps
-    // after the first - then costs a few products instead of a whole 24-step cycle.  Later cycles run to their end:
+    // eigen-solve of the projected matrices).  A start vector that is already the answer - finite-DMRG sweeps after
+    // the first - then costs a few products instead of a whole 24-step cycle.  Later cycles run to their end:
     // stopping them the moment the tolerance is met was measured to cost more products over an iDMRG run (each step
     // then starts from a slightly less converged prediction).
     static const int poll_env = getenv("MPSB_LANCZOS_POLL") ? atoi(getenv("MPSB_LANCZOS_POLL")) : 1;
-    int mm = m;
-    double beta_last = 0.0;
-    std::vector<int> idx;
-    // Ritz data of the basis V[0 .. formed): fills T (eigenvalues on the diagonal), Y, idx (ascending), E, resid, mm.
+    auto small_enough = [&](const Chain& c) { return c.resid <= tol * (std::fabs(c.E) > 1.0 ? std::fabs(c.E) : 1.0); };
+    // Ritz data of the bases V[chain][0 .. formed): per live chain T (eigenvalues on the diagonal), Y, idx (ascending),
+    // E, resid, mm.
     auto evaluate = [&](int formed) -> int {
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(h1.data(), C1, sizeof(cplx) * kk * formed, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(h2.data(), C2, sizeof(cplx) * kk * formed, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx) * formed, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h1.data(), kk * kk * sizeof(cplx), C1, kk * kk * sizeof(cplx),
+                                          sizeof(cplx) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h2.data(), kk * kk * sizeof(cplx), C2, kk * kk * sizeof(cplx),
+                                          sizeof(cplx) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(cplx), N2, kk * sizeof(cplx), sizeof(cplx) * formed, nb,
+                                          cudaMemcpyDeviceToHost, st));
         auto tb = now();
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
         auto tc = now();
         t_wait += us(tb, tc);
-        mm = formed;
-        beta_last = 0.0;
-        for (int j = j0; j < formed; ++j) {
-            for (int i = 0; i <= j; ++i) {
-                const double v = h1[(size_t)j * kk + i].x + h2[(size_t)j * kk + i].x;
-                Hp[(size_t)i * m + j] = v;
-                Hp[(size_t)j * m + i] = v;
+        for (size_t ci = 0; ci < nb; ++ci) {
+            Chain& c = ch[ci];
+            if (c.frozen) continue;
+            const cplx* a1 = h1.data() + ci * kk * kk;
+            const cplx* a2 = h2.data() + ci * kk * kk;
+            const cplx* an = hn.data() + ci * kk;
+            c.mm = formed;
+            c.beta_last = 0.0;
+            double hscale = 0.0;                      // largest |h_ij| seen: scale of the breakdown test
+            for (int j = j0; j < formed; ++j) {
+                for (int i = 0; i <= j; ++i) {
+                    const double v = a1[(size_t)j * kk + i].x + a2[(size_t)j * kk + i].x;
+                    c.Hp[(size_t)i * m + j] = v;
+                    c.Hp[(size_t)j * m + i] = v;
+                    hscale = std::max(hscale, std::fabs(v));
+                }
+                const double bj = std::sqrt(an[j].x > 0.0 ? an[j].x : 0.0);
+                c.beta_last = bj;
+                if (j + 1 < m) { c.Hp[(size_t)(j + 1) * m + j] = bj; c.Hp[(size_t)j * m + j + 1] = bj; }
+                hscale = std::max(hscale, std::fabs(c.Hp[0]));
+                if (!(bj > 1e-14 * (hscale + 1e-300)) || !std::isfinite(bj)) { c.mm = j + 1; break; }
             }
-            const double bj = std::sqrt(hn[j].x > 0.0 ? hn[j].x : 0.0);
-            beta_last = bj;
-            if (j + 1 < m) { Hp[(size_t)(j + 1) * m + j] = bj; Hp[(size_t)j * m + j + 1] = bj; }
-            if (!(bj > 1e-14 * (std::fabs(Hp[0]) + 1e-300)) || !std::isfinite(bj)) { mm = j + 1; break; }
+            const int mm = c.mm;
+            c.T.assign((size_t)mm * mm, 0.0);
+            for (int i = 0; i < mm; ++i)
+                for (int q = 0; q < mm; ++q) c.T[(size_t)i * mm + q] = c.Hp[(size_t)i * m + q];
+            sym_eig_host(mm, c.T, c.Y);
+            c.idx.resize(mm);
+            for (int i = 0; i < mm; ++i) c.idx[i] = i;
+            std::sort(c.idx.begin(), c.idx.end(), [&](int a, int b) { return c.T[(size_t)a * mm + a] < c.T[(size_t)b * mm + b]; });
+            const int best = c.idx[0];
+            c.E = c.T[(size_t)best * mm + best];
+            c.resid = std::fabs(c.beta_last * c.Y[(size_t)(mm - 1) * mm + best]);
         }
-        T.assign((size_t)mm * mm, 0.0);
-        for (int i = 0; i < mm; ++i)
-            for (int q = 0; q < mm; ++q) T[(size_t)i * mm + q] = Hp[(size_t)i * m + q];
-        sym_eig_host(mm, T, Y);
-        idx.resize(mm);
-        for (int i = 0; i < mm; ++i) idx[i] = i;
-        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return T[(size_t)a * mm + a] < T[(size_t)b * mm + b]; });
-        const int best = idx[0];
-        E = T[(size_t)best * mm + best];
-        resid = std::fabs(beta_last * Y[(size_t)(mm - 1) * mm + best]);
         t_host += us(tc, now());
         return 0;
     };
-    auto small_enough = [&] { return resid <= tol * (std::fabs(E) > 1.0 ? std::fabs(E) : 1.0); };
-    for (int restart = 0; restart < max_restarts && !converged; ++restart) {
+    bool all_done = false;
+    for (int restart = 0; restart < max_restarts && !all_done; ++restart) {
         auto ta = now();
         int formed = m;
         bool evaluated = false;
         for (int j = j0; j < m; ++j) {
+            cplx* vj = V + (size_t)j * vstride;
             cplx* wv = V + (size_t)(j + 1) * vstride;
-            rc = heff_apply(h, V + (size_t)j * vstride, wv, st);
+            rc = heff_apply(h, vj, wv, st, sV, sV);
             if (rc) return rc;
             ++n_mv;
             for (int pass = 0; pass < 2; ++pass) {
                 cplx* c = (pass == 0 ? C1 : C2) + (size_t)j * kk;
-                rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, (int)kk, st);
+                rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, (int)kk, st, bat(sV, sV, sC));
                 if (rc) return rc;
-                rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c, -1.0, wv, st);
+                rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c, -1.0, wv, st, bat(sV, sV, sC));
                 if (rc) return rc;
             }
-            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, N2 + j, part, nchunk, (int)kk, st);
+            rc = zdotc_multi(wv, 0, 1, (long long)n, wv, N2 + j, part, nchunk, (int)kk, st, bat(sV, sV, sN));
             if (rc) return rc;
-            rc = znormalise((long long)n, N2 + j, wv, st);
+            rc = znormalise((long long)n, N2 + j, wv, st, bat(0, sV, sN));
             if (rc) return rc;
             const int done_now = j + 1 - j0;
             if (poll_env && restart == 0 && j + 1 < m && (done_now == 4 || (done_now > 4 && (done_now - 4) % 8 == 0))) {
@@ -374,7 +449,9 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
                 rc = evaluate(j + 1);
                 if (rc) return rc;
                 ta = now();
-                if (small_enough() || mm < j + 1) { formed = j + 1; evaluated = true; break; }
+                bool all = true;
+                for (const Chain& c : ch) all = all && (c.frozen || small_enough(c) || c.mm < j + 1);
+                if (all) { formed = j + 1; evaluated = true; break; }
             }
         }
         t_enq += us(ta, now());
@@ -383,53 +460,97 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
             if (rc) return rc;
         }
         auto tc = now();
-        converged = small_enough() || mm < m || restart + 1 == max_restarts;
-        const int keep = converged ? 1 : std::min(LANCZOS_KEEP, mm - 1);
-        // Ritz vectors Vk[i] = sum_q Y[q][idx[i]] V[q]
-        for (int i = 0; i < keep; ++i)
-            for (int q = 0; q < mm; ++q) hc[(size_t)i * kk + q] = make_double2(Y[(size_t)q * mm + idx[i]], 0.0);
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(cplx) * kk * keep, cudaMemcpyHostToDevice, st));
-        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, al(n * sizeof(cplx)) * keep, st));
+        const bool last = restart + 1 == max_restarts;
+        all_done = true;
+        std::vector<char> finish(nb, 0);
+        for (size_t ci = 0; ci < nb; ++ci) {
+            Chain& c = ch[ci];
+            if (c.frozen) continue;
+            if (small_enough(c) || c.mm < formed || formed < m || last) finish[ci] = 1;
+            else all_done = false;
+        }
+        const int keep = all_done ? 1 : std::min(LANCZOS_KEEP, m - 1);
+        // Ritz vectors Vk[chain][i] = sum_q Y[q][idx[i]] V[chain][q]   (zero coefficients beyond a chain's own mm)
+        std::fill(hc.begin(), hc.end(), make_double2(0.0, 0.0));
+        for (size_t ci = 0; ci < nb; ++ci) {
+            const Chain& c = ch[ci];
+            if (c.frozen) continue;
+            const int kc = std::min(keep, c.mm);
+            for (int i = 0; i < kc; ++i)
+                for (int q = 0; q < c.mm; ++q)
+                    hc[ci * kk * LANCZOS_KEEP + (size_t)i * kk + q] = make_double2(c.Y[(size_t)q * c.mm + c.idx[i]], 0.0);
+        }
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(cplx) * nb * kk * LANCZOS_KEEP, cudaMemcpyHostToDevice, st));
+        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, nb * al(n * sizeof(cplx)) * LANCZOS_KEEP, st));
         for (int i = 0; i < keep; ++i) {
-            rc = zaxpy_multi(V, (long long)vstride, mm, (long long)n, Yd + (size_t)i * kk, 1.0, Vk + (size_t)i * vstride, st);
+            rc = zaxpy_multi(V, (long long)vstride, formed, (long long)n, Yd + (size_t)i * kk, 1.0, Vk + (size_t)i * vstride, st,
+                             bat(sV, sVk, sY));
             if (rc) return rc;
         }
+        for (size_t ci = 0; ci < nb; ++ci) {          // freeze the chains that finished in this cycle
+            if (!finish[ci]) continue;
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(th + ci * (size_t)s_theta, Vk + ci * (size_t)sVk, n * sizeof(cplx),
+                                            cudaMemcpyDeviceToDevice, st));
+            ch[ci].frozen = true;
+        }
         t_host += us(tc, now());
-        if (converged) break;
-        // new basis: kept Ritz vectors, then the residual direction v_m (already orthogonal to all of them)
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(V + (size_t)keep * vstride, V + (size_t)m * vstride, n * sizeof(cplx),
-                                        cudaMemcpyDeviceToDevice, st));
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(V, Vk, al(n * sizeof(cplx)) * keep, cudaMemcpyDeviceToDevice, st));
-        std::fill(Hp.begin(), Hp.end(), 0.0);
-        for (int i = 0; i < keep; ++i) Hp[(size_t)i * m + i] = T[(size_t)idx[i] * mm + idx[i]];
+        if (all_done) break;
+        // new bases: kept Ritz vectors, then the residual direction v_m (already orthogonal to all of them)
+        if (batch == 1) {
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(V + (size_t)keep * vstride, V + (size_t)m * vstride, n * sizeof(cplx),
+                                            cudaMemcpyDeviceToDevice, st));
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(V, Vk, al(n * sizeof(cplx)) * keep, cudaMemcpyDeviceToDevice, st));
+        } else {
+            MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V + (size_t)keep * vstride, (size_t)sV * sizeof(cplx), V + (size_t)m * vstride,
+                                              (size_t)sV * sizeof(cplx), n * sizeof(cplx), nb, cudaMemcpyDeviceToDevice, st));
+            MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(cplx), Vk, (size_t)sVk * sizeof(cplx),
+                                              al(n * sizeof(cplx)) * keep, nb, cudaMemcpyDeviceToDevice, st));
+        }
+        for (Chain& c : ch) {
+            if (c.frozen) continue;
+            std::vector<double> diag(keep);
+            for (int i = 0; i < keep; ++i) diag[i] = c.T[(size_t)c.idx[i] * c.mm + c.idx[i]];
+            std::fill(c.Hp.begin(), c.Hp.end(), 0.0);
+            for (int i = 0; i < keep; ++i) c.Hp[(size_t)i * m + i] = diag[i];
+        }
         j0 = keep;
     }
-    if (dbg) fprintf(stderr, "[mpsb] lanczos: %d matvecs, enqueue %.0f us, wait %.0f us, host ritz %.0f us\n", n_mv, t_enq, t_wait, t_host);
-    // returned vector: lowest Ritz vector, renormalised; Rayleigh quotient and true residual with one more product
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(th, Vk, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st);
+    if (dbg) fprintf(stderr, "[mpsb] lanczos: %d chains, %d matvecs, enqueue %.0f us, wait %.0f us, host ritz %.0f us\n", batch,
+                     n_mv, t_enq, t_wait, t_host);
+    // returned vectors: lowest Ritz vectors, renormalised; Rayleigh quotients and true residuals with one more product
+    rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st, bat(s_theta, s_theta, sN));
     if (rc) return rc;
-    rc = znormalise((long long)n, N2, th, st);
+    rc = znormalise((long long)n, N2, th, st, bat(0, s_theta, sN));
     if (rc) return rc;
     cplx* hv = V + (size_t)1 * vstride;
-    rc = heff_apply(h, th, hv, st);
+    rc = heff_apply(h, th, hv, st, s_theta, sV);
     if (rc) return rc;
     ++n_mv;
-    rc = zdotc_multi(th, 0, 1, (long long)n, hv, C1, part, nchunk, (int)kk, st);
+    rc = zdotc_multi(th, 0, 1, (long long)n, hv, C1, part, nchunk, (int)kk, st, bat(s_theta, sV, sC));
     if (rc) return rc;
-    rc = zaxpy_multi(th, 0, 1, (long long)n, C1, -1.0, hv, st);
+    rc = zaxpy_multi(th, 0, 1, (long long)n, C1, -1.0, hv, st, bat(s_theta, sV, sC));
     if (rc) return rc;
-    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, N2, part, nchunk, (int)kk, st);
+    rc = zdotc_multi(hv, 0, 1, (long long)n, hv, N2, part, nchunk, (int)kk, st, bat(sV, sV, sN));
     if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(hc.data(), C1, sizeof(cplx), cudaMemcpyDeviceToHost, st));
-    MPSB_CHECK_CUDA(cudaMemcpyAsync(hn.data(), N2, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hc.data(), sizeof(cplx), C1, kk * kk * sizeof(cplx), sizeof(cplx), nb,
+                                      cudaMemcpyDeviceToHost, st));
+    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), sizeof(cplx), N2, kk * sizeof(cplx), sizeof(cplx), nb, cudaMemcpyDeviceToHost,
+                                      st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
-    E = hc[0].x;
-    resid = std::sqrt(hn[0].x > 0.0 ? hn[0].x : 0.0);
-    if (energy_host) *energy_host = E;
-    if (resid_host) *resid_host = resid;
+    for (size_t ci = 0; ci < nb; ++ci) {
+        if (energy_host) energy_host[ci] = hc[ci].x;
+        if (resid_host) resid_host[ci] = std::sqrt(hn[ci].x > 0.0 ? hn[ci].x : 0.0);
+    }
     if (n_matvec_host) *n_matvec_host = n_mv;
     return 0;
+}
+
+int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
+                        int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
+                        int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
+    const long long n = (long long)chil * d * d * chir;
+    return mpsb_lanczos_ground_batched(1, chil, chir, d, w, L, 0, W, 0, R, 0, theta, n, krylov, max_restarts, tol,
+                                       energy_host, resid_host, n_matvec_host, ws, ws_bytes, stream);
 }
 
 size_t mpsb_predict_workspace(int chi, int chip, int d) {
@@ -457,28 +578,35 @@ int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, c
     return zgemm(g, st);
 }
 
-size_t mpsb_env_workspace(int chi, int chin, int d, int w) {
-    return al((size_t)w * chi * chi * sizeof(cplx)) + al((size_t)w * chi * d * chin * sizeof(cplx)) * 2 +
-           al((size_t)w * chin * chin * sizeof(cplx));
+size_t mpsb_env_batched_workspace(int batch, int chi, int chin, int d, int w) {
+    const size_t b = (size_t)batch;
+    return al(b * w * chi * chi * sizeof(cplx)) + al(b * w * chi * d * chin * sizeof(cplx)) * 2 +
+           al(b * w * chin * chin * sizeof(cplx));
 }
+size_t mpsb_env_workspace(int chi, int chin, int d, int w) { return mpsb_env_batched_workspace(1, chi, chin, d, w); }
 
-static int env_common(int right, int chi, int chin, int d, int w, const void* E, const void* UV, const void* W,
-                      int swap_conj, void* E_out, void* ws, size_t ws_bytes, void* stream) {
+// E [batch][chi][chi][w] (stride sE), UV [batch][...] (sUV), W [w][w][d][d] per chain (sW) or shared (sW = 0),
+// E_out [batch][chin][chin][w] (sEo)
+static int env_common(int right, int batch, int chi, int chin, int d, int w, const void* E, long long sE, const void* UV,
+                      long long sUV, const void* W, long long sW, int swap_conj, void* E_out, long long sEo, void* ws,
+                      size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(chi >= 1 && chin >= 1 && d >= 1 && w >= 1, "env: bad dims");
-    const size_t need = mpsb_env_workspace(chi, chin, d, w);
+    MPSB_REQUIRE(batch >= 1 && chi >= 1 && chin >= 1 && d >= 1 && w >= 1, "env: bad dims");
+    const size_t need = mpsb_env_batched_workspace(batch, chi, chin, d, w);
     MPSB_REQUIRE(ws && ws_bytes >= need, "env: workspace %zu B < required %zu B", ws_bytes, need);
+    const size_t b = (size_t)batch;
     unsigned char* p = static_cast<unsigned char*>(ws);
-    cplx* Et = reinterpret_cast<cplx*>(p); p += al((size_t)w * chi * chi * sizeof(cplx));
-    cplx* T1 = reinterpret_cast<cplx*>(p); p += al((size_t)w * chi * d * chin * sizeof(cplx));
-    cplx* T2 = reinterpret_cast<cplx*>(p); p += al((size_t)w * chi * d * chin * sizeof(cplx));
+    cplx* Et = reinterpret_cast<cplx*>(p); p += al(b * w * chi * chi * sizeof(cplx));
+    cplx* T1 = reinterpret_cast<cplx*>(p); p += al(b * w * chi * d * chin * sizeof(cplx));
+    cplx* T2 = reinterpret_cast<cplx*>(p); p += al(b * w * chi * d * chin * sizeof(cplx));
     cplx* Ot = reinterpret_cast<cplx*>(p);
     const cplx* X = static_cast<const cplx*>(UV);
+    const long long sEt = (long long)w * chi * chi, sT = (long long)w * chi * d * chin, sOt = (long long)w * chin * chin;
     // Et[k][i][j] = E[i][j][k]
-    int rc = perm_last_to_first(static_cast<const cplx*>(E), chi * chi, w, Et, st);
+    int rc = transpose_conj(static_cast<const cplx*>(E), w, chi * chi, w, Et, chi * chi, 0, st, batch, sE, sEt);
     if (rc) return rc;
     GemmArgs g;
-    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    g.batch1 = batch; g.batch2 = 1; g.sA1 = sEt; g.sB1 = sUV; g.sC1 = sT; g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
     // ket leg (index j of the environment) meets the un-conjugated tensor unless swap_conj
     if (!right) {
         // T1[(k,i)][(m,B)] = sum_j Et[(k,i)][j] U[j][(m,B)]
@@ -492,13 +620,15 @@ static int env_common(int right, int chi, int chin, int d, int w, const void* E,
     rc = zgemm(g, st);
     if (rc) return rc;
     const long long total = (long long)w * chi * d * chin;
-    env_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(right, chi, chin, d, w, static_cast<const cplx*>(W),
-                                                                  T1, T2);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    env_w_kernel<<<grid, 256, 0, st>>>(right, chi, chin, d, w, static_cast<const cplx*>(W), sW, T1, T2);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
-    // bra leg:  Ot[C][A][B] = sum_{K} op(X)[A][K] T2[C][K][B]
+    // bra leg:  Ot[C][A][B] = sum_{K} op(X)[A][K] T2[C][K][B]      (batch level 1: chains, level 2: C)
     g.B = T2; g.C = Ot; g.M = chin; g.N = chin; g.K = chi * d; g.ldb = chin; g.ldc = chin;
-    g.batch1 = w; g.sA1 = 0; g.sB1 = (long long)chi * d * chin; g.sC1 = (long long)chin * chin;
+    g.batch1 = batch; g.batch2 = w;
+    g.sA1 = sUV; g.sB1 = sT; g.sC1 = sOt;
+    g.sA2 = 0; g.sB2 = (long long)chi * d * chin; g.sC2 = (long long)chin * chin;
     g.A = X;
     if (!right) { g.lda = chin; g.opA = swap_conj ? 1 : 2; }      // U as [(i,l)][A]
     else        { g.lda = chi * d; g.opA = swap_conj ? 0 : 3; }   // V as [A][(l,i)]
@@ -506,16 +636,26 @@ static int env_common(int right, int chi, int chin, int d, int w, const void* E,
     rc = zgemm(g, st);
     if (rc) return rc;
     // E_out[A][B][C] = Ot[C][A][B]
-    return perm_first_to_last(Ot, w, chin * chin, static_cast<cplx*>(E_out), st);
+    return transpose_conj(Ot, chin * chin, w, chin * chin, static_cast<cplx*>(E_out), w, 0, st, batch, sOt, sEo);
 }
 
 int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U, const void* W, int swap_conj,
                   void* L_out, void* ws, size_t ws_bytes, void* stream) {
-    return env_common(0, chi, chin, d, w, L, U, W, swap_conj, L_out, ws, ws_bytes, stream);
+    return env_common(0, 1, chi, chin, d, w, L, 0, U, 0, W, 0, swap_conj, L_out, 0, ws, ws_bytes, stream);
 }
 int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
                    void* R_out, void* ws, size_t ws_bytes, void* stream) {
-    return env_common(1, chi, chin, d, w, R, V, W, swap_conj, R_out, ws, ws_bytes, stream);
+    return env_common(1, 1, chi, chin, d, w, R, 0, V, 0, W, 0, swap_conj, R_out, 0, ws, ws_bytes, stream);
+}
+int mpsb_env_left_batched(int batch, int chi, int chin, int d, int w, const void* L, long long sL, const void* U, long long sU,
+                          const void* W, long long sW, int swap_conj, void* L_out, long long sLo, void* ws, size_t ws_bytes,
+                          void* stream) {
+    return env_common(0, batch, chi, chin, d, w, L, sL, U, sU, W, sW, swap_conj, L_out, sLo, ws, ws_bytes, stream);
+}
+int mpsb_env_right_batched(int batch, int chi, int chin, int d, int w, const void* R, long long sR, const void* V, long long sV,
+                           const void* W, long long sW, int swap_conj, void* R_out, long long sRo, void* ws, size_t ws_bytes,
+                           void* stream) {
+    return env_common(1, batch, chi, chin, d, w, R, sR, V, sV, W, sW, swap_conj, R_out, sRo, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

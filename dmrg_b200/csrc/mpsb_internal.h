@@ -114,15 +114,21 @@ int scale_rows(int rows, int cols, const cplx* in, int ldi, const double* s, int
 // out[c][a][b] = in[a][b][c]  (n_ab = a*b merged)   and the inverse
 int perm_last_to_first(const cplx* in, int n_ab, int n_c, cplx* out, cudaStream_t st);
 int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_t st);
+// The BLAS-1 helpers below take `batch` independent problems in one launch (the chains of a batched Lanczos run):
+// problem b uses V + b sV, w + b sw, the coefficient / result vector + b sc and the scratch + b spart.
+struct BlasBatch {
+    int batch = 1;
+    long long sV = 0, sw = 0, sc = 0, spart = 0;
+};
 // y[j] = sum_i conj(V[j][i]) w[i]  for j < m (deterministic, single launch).  part: m_cap * nchunk partial sums
 // followed by m_cap ticket counters (unsigned int) that must be zero on entry; they are zero again on exit.
 int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
-                int m_cap, cudaStream_t st);
+                int m_cap, cudaStream_t st, BlasBatch bb = BlasBatch());
 // w[i] += sign * sum_j c[j] V[j][i]   (c on device, m entries)
 int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
-                cudaStream_t st);
+                cudaStream_t st, BlasBatch bb = BlasBatch());
 // w *= 1/sqrt(nrm2[0].x) with nrm2 on the device (zero vector if the norm vanishes)
-int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st);
+int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st, BlasBatch bb = BlasBatch());
 // w[i] = alpha * w[i]  (alpha real, on host)
 int zdscal(long long n, double alpha, cplx* w, cudaStream_t st);
 

@@ -117,6 +117,7 @@ def ground_state(Ld, Md, Rd, seed=0, theta0=None):
                                        MAX_RESTARTS, TOL, ctypes.byref(E), ctypes.byref(resid), ctypes.byref(nmv), ws,
                                        wsn, _lib.stream_ptr()), "mpsb_lanczos_ground")
     last_info.update(n_matvec=nmv.value, residual=resid.value)
+    _warn_if_residual_large(E.value, resid.value)
     return E.value, theta
 
 
@@ -250,6 +251,156 @@ class Chain:
         mps = MPS([a, _lib.to_host(self.B)], trun=max(int(self.trunc), len(self.S)), err=0.0)
         mps.canon()
         return mps
+
+
+# ---- many independent chains in lock step (BASELINE config 4: coupling sweeps over h/J) -------------------------------
+def _transpose_batched(a, conj=True):
+    """[n, rows, cols] device tensor -> [n, cols, rows] (conjugated) through the library's tile-transpose kernel."""
+    n, rows, cols = (int(v) for v in a.shape)
+    out = _lib.empty((n, cols, rows))
+    _lib.check(_lib.load().mpsb_transpose_batched(n, rows, cols, _lib.ptr(a), cols, rows * cols, _lib.ptr(out), rows,
+                                                  rows * cols, int(conj), _lib.stream_ptr()), "mpsb_transpose_batched")
+    return out
+
+
+def _svd_batched(A, trunc, want_u):
+    """`halve`'s SVD (no eps cut, raw singular values) of n matrices [n, rows, cols] in one call: (Uh | None, S_all, Vh)
+    with Uh [n, k, rows] = U^H, Vh [n, k, cols], k = min(trunc, rows, cols) for every chain."""
+    lib = _lib.load()
+    n, rows, cols = (int(v) for v in A.shape)
+    k = max(1, min(rows, cols, int(trunc)))
+    vh = _lib.empty((n, k, cols))
+    uh = _lib.empty((n, k, rows)) if want_u else None
+    s = _lib.empty((n, k), "f64")
+    sraw = _lib.empty((n, min(rows, cols)), "f64")
+    rank = _lib.empty((n,), "i32")
+    ws, wsn = _lib.workspace(lib.mpsb_svd_trunc_workspace(n, rows, cols, int(want_u)))
+    _lib.check(lib.mpsb_svd_trunc(n, rows, cols, _lib.ptr(A), cols, rows * cols, int(trunc), 0.0, 0, k, _lib.ptr(vh),
+                                  _lib.ptr(uh), _lib.ptr(s), _lib.ptr(sraw), _lib.ptr(rank), ws, wsn, _lib.stream_ptr()),
+               "mpsb_svd_trunc")
+    _lib.warn_if_unconverged("halve (batched)")
+    return uh, sraw, vh
+
+
+def halve_batched(theta, trunc):
+    """`halve` (DMRG/iDMRG.py:17-35) for n two-site tensors [n, xl, d, d, xr] at once: U [n, xl, d, k], S_all [n, .],
+    V [n, k, d, xr] (device tensors; every chain keeps k = min(trunc, S.size) states, so the shapes stay common)."""
+    n, xl, d, _, xr = (int(v) for v in theta.shape)
+    A = theta.reshape(n, xl * d, d * xr)
+    if xl * d <= 256:                                       # carried-identity SVD: U and V from one decomposition
+        uh, s_all, vh = _svd_batched(A, trunc, True)
+        U = _transpose_batched(uh)
+    else:                                                   # two row-orthogonalisations (see _halve_split)
+        _, s_all, vh = _svd_batched(A, trunc, False)
+        _, _, uh = _svd_batched(_transpose_batched(A), trunc, False)
+        U = _transpose_batched(uh)
+    k = int(vh.shape[1])
+    return U.reshape(n, xl, d, k), s_all, vh.reshape(n, k, d, xr)
+
+
+def ground_state_batched(Ld, Md, Rd, seed=0, theta0=None):
+    """Lowest eigenpairs of n effective Hamiltonians in lock step: Ld [n, xl, xl, w], Rd [n, xr, xr, w], Md
+    [w, w, d, d] (one MPO for all chains) or [n, w, w, d, d] (one per chain).  Returns (E [n] numpy, theta
+    [n, xl, d, d, xr] device, normalised per chain)."""
+    import ctypes
+    lib = _lib.load()
+    n, xl, xr, w = int(Ld.shape[0]), int(Ld.shape[1]), int(Rd.shape[1]), int(Ld.shape[3])
+    d = int(Md.shape[-1])
+    sW = w * w * d * d if Md.dim() == 5 else 0
+    nel = xl * d * d * xr
+    if theta0 is None:
+        t = _lib.torch()
+        gen = t.Generator(device=_lib.device())
+        gen.manual_seed(int(seed))
+        theta0 = t.view_as_complex(t.randn((n, xl, d, d, xr, 2), dtype=t.float64, device=_lib.device(), generator=gen))
+    theta = theta0.clone()
+    E = (ctypes.c_double * n)()
+    resid = (ctypes.c_double * n)()
+    nmv = ctypes.c_int(0)
+    ws, wsn = _lib.workspace(lib.mpsb_lanczos_batched_workspace(n, xl, xr, d, w, KRYLOV))
+    _lib.check(lib.mpsb_lanczos_ground_batched(n, xl, xr, d, w, _lib.ptr(Ld), xl * xl * w, _lib.ptr(Md), sW, _lib.ptr(Rd),
+                                               xr * xr * w, _lib.ptr(theta), nel, KRYLOV, MAX_RESTARTS, TOL, E, resid,
+                                               ctypes.byref(nmv), ws, wsn, _lib.stream_ptr()), "mpsb_lanczos_ground_batched")
+    E, resid = np.array(E[:]), np.array(resid[:])
+    last_info.update(n_matvec=nmv.value, residual=float(resid.max()))
+    _warn_if_residual_large(E, resid)
+    return E, theta
+
+
+def _warn_if_residual_large(E, resid):
+    """The reference's ARPACK raises ArpackNoConvergence; here an eigenpair whose true residual ||H v - E v|| is far from
+    the target after MAX_RESTARTS cycles is reported instead of flowing silently into the split."""
+    bad = np.atleast_1d(resid) > 1e3 * TOL * np.maximum(1.0, np.abs(np.atleast_1d(E)))
+    if bad.any():
+        import warnings
+        warnings.warn(f"Lanczos ground state: residual {float(np.max(resid)):.2e} exceeds 1e3 x TOL for {int(bad.sum())} "
+                      f"chain(s) after {MAX_RESTARTS} restarts")
+
+
+def _env_batched(left, Ed, Td, Md, swap_conj):
+    lib = _lib.load()
+    n, chi, w = int(Ed.shape[0]), int(Ed.shape[1]), int(Ed.shape[3])
+    d = int(Md.shape[-1])
+    chin = int(Td.shape[3]) if left else int(Td.shape[1])
+    sW = w * w * d * d if Md.dim() == 5 else 0
+    out = _lib.empty((n, chin, chin, w))
+    ws, wsn = _lib.workspace(lib.mpsb_env_batched_workspace(n, chi, chin, d, w))
+    fn = lib.mpsb_env_left_batched if left else lib.mpsb_env_right_batched
+    _lib.check(fn(n, chi, chin, d, w, _lib.ptr(Ed), chi * chi * w, _lib.ptr(Td), chi * d * chin, _lib.ptr(Md), sW,
+                  int(swap_conj), _lib.ptr(out), chin * chin * w, ws, wsn, _lib.stream_ptr()), "mpsb_env_batched")
+    return out
+
+
+class ChainBatch:
+    """n independent iDMRG runs in lock step on one GPU - the coupling sweep of BASELINE config 4 (e.g. TFIM with
+    g / J on np.linspace(0.2, 2.0, n)).  The reference would run `next_LR` (DMRG/iDMRG.py:49-61) once per
+    parameter in separate processes; here every Lanczos product, the split and the environment growth are single
+    batched launches over all chains.  All chains share (w, d) and, because `halve` keeps min(trunc, S.size) states
+    without an eps cut, the same bond dimension at every step.
+
+        W = np.stack([(-g * MPO('sx') - MPO('sz') ** 2).tomatrix() for g in gs])     # [n, w, w, d, d]
+        run = ChainBatch(W, trunc=128)
+        for _ in range(steps):
+            E = run.step()            # total energies of the enlarged chains, array [n]
+    """
+
+    def __init__(self, W, trunc=10, left_index=None, right_index=0, swap_conj=False):
+        W = np.asarray(W)
+        assert W.ndim == 5, "W: one MPO per chain, [n, w, w, d, d]"
+        self.n, self.w, self.d = int(W.shape[0]), int(W.shape[1]), int(W.shape[3])
+        self.trunc, self.swap_conj = int(trunc), bool(swap_conj)
+        self.W = _lib.to_device(W)
+        L = np.zeros((self.n, 1, 1, self.w), dtype=complex)
+        R = np.zeros((self.n, 1, 1, self.w), dtype=complex)
+        L[:, 0, 0, self.w - 1 if left_index is None else left_index] = 1     # boundary vectors of the lower-triangular MPO
+        R[:, 0, 0, right_index] = 1
+        self.L, self.R = _lib.to_device(L), _lib.to_device(R)
+        self.energies, self.n_matvec, self.S = [], [], None
+        self.sites = 0
+
+    def step(self, seed=0):
+        """One growth step for every chain; returns the total energies [n]."""
+        E, theta = ground_state_batched(self.L, self.W, self.R, seed=seed + self.sites)
+        U, S, V = halve_batched(theta, self.trunc)
+        self.L = _env_batched(True, self.L, U.contiguous(), self.W, self.swap_conj)
+        self.R = _env_batched(False, self.R, V.contiguous(), self.W, self.swap_conj)
+        self.S = _lib.to_host(S)
+        self.sites += 2
+        self.energies.append(E)
+        self.n_matvec.append(last_info["n_matvec"])
+        return E
+
+    def energy_per_site(self):
+        """Energy per site from the last two growth steps (bond energy of the infinite chain), array [n]."""
+        assert len(self.energies) >= 2
+        return (self.energies[-1] - self.energies[-2]) / 2
+
+    def entropies(self):
+        """Entanglement entropy (nats) of the kept spectrum of the last split, array [n]."""
+        s = self.S[:, :self.trunc]
+        p = s ** 2 / np.sum(s ** 2, axis=1, keepdims=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return -np.where(p > 0, p * np.log(p), 0.0).sum(axis=1)
 
 
 def next_LR(L, R, M, trunc=None, swap_conj=False, seed=0):

@@ -131,6 +131,14 @@ size_t mpsb_heff_workspace(int chil, int chir, int d, int w);
 int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
                      void* out, void* ws, size_t ws_bytes, void* stream);
 
+/* `batch` independent chains of equal shape in one call (coupling sweeps over h/J, BASELINE config 4; the reference
+ * runs one next_LR chain per Python process, DMRG/iDMRG.py:64-76).  s* = element strides between chains; sW = 0
+ * shares one MPO between all chains. */
+size_t mpsb_heff_batched_workspace(int batch, int chil, int chir, int d, int w);
+int mpsb_heff_matvec_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                             long long sW, const void* R, long long sR, const void* theta, long long s_theta, void* out,
+                             long long s_out, void* ws, size_t ws_bytes, void* stream);
+
 /* Lowest eigenpair of the effective Hamiltonian by Lanczos with full reorthogonalisation and
  * restarts (replaces eigsh(k=1, which='SA'), DMRG/iDMRG.py:57).  theta holds the start vector on
  * entry (must be non-zero) and the normalised ground vector on exit.  Results (host pointers):
@@ -139,6 +147,15 @@ size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov);
 int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
                         int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
                         int* n_matvec_host, void* ws, size_t ws_bytes, void* stream);
+
+/* The same for `batch` chains in lock step: every product, orthogonalisation pass and update is one batched launch;
+ * a chain that has converged is frozen (its vector is final) while the others finish.  energy_host and resid_host
+ * receive `batch` values, n_matvec_host the common number of products. */
+size_t mpsb_lanczos_batched_workspace(int batch, int chil, int chir, int d, int w, int krylov);
+int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                                long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
+                                int max_restarts, double tol, double* energy_host, double* resid_host, int* n_matvec_host,
+                                void* ws, size_t ws_bytes, void* stream);
 
 /* Environment growth (DMRG/iDMRG.py:59-60, with the conjugation on the bra leg — SURVEY App. B1):
  *     L'[A,B,C] = sum L[i,j,k] conj(U[i,l,A]) U[j,m,B] W[k,C,l,m]        U [chi][d][chin]
@@ -149,6 +166,14 @@ int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U,
                   void* L_out, void* ws, size_t ws_bytes, void* stream);
 int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
                    void* R_out, void* ws, size_t ws_bytes, void* stream);
+
+size_t mpsb_env_batched_workspace(int batch, int chi, int chin, int d, int w);
+int mpsb_env_left_batched(int batch, int chi, int chin, int d, int w, const void* L, long long sL, const void* U, long long sU,
+                          const void* W, long long sW, int swap_conj, void* L_out, long long sLo, void* ws, size_t ws_bytes,
+                          void* stream);
+int mpsb_env_right_batched(int batch, int chi, int chin, int d, int w, const void* R, long long sR, const void* V, long long sV,
+                           const void* W, long long sW, int swap_conj, void* R_out, long long sRo, void* ws, size_t ws_bytes,
+                           void* stream);
 
 /* Start vector for the next growth step from the tensors of the last one (new; the reference restarts ARPACK from a
  * random vector at DMRG/iDMRG.py:57).  With theta_n = A S B from the last split (A [chip][d][chi] left-orthonormal,
@@ -169,6 +194,8 @@ int mpsb_scale_rows(int rows, int cols, const void* in, int ldi, const double* s
 
 /* out[j * ldo + i] = conj?(in[i * ldi + j]) for i < rows, j < cols (layout helper of the shim). */
 int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int ldo, int conj, void* stream);
+int mpsb_transpose_batched(int batch, int rows, int cols, const void* in, int ldi, long long s_in, void* out, int ldo,
+                           long long s_out, int conj, void* stream);
 
 /* Diagnostics of the last SVD call on this thread: number of Jacobi sweeps of the slowest problem. */
 int mpsb_last_svd_sweeps(void);
