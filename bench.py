@@ -169,6 +169,34 @@ def idmrg_leg(with_cpu):
     return out
 
 
+def idmrg_batch_leg(n_chains=256, chi=128):
+    """BASELINE config 4 on the iDMRG side: a TFIM coupling sweep (g / J on np.linspace(0.2, 2.0, n)) of
+    n_chains independent chains grown in lock step by dmrg_b200.iDMRG.ChainBatch; ms per growth step at bond
+    dimension chi and the contraction rate of the whole step on SURVEY 8(d)'s F_iDMRG-step formula (complex flops)."""
+    import torch
+    from dmrg_b200 import iDMRG
+    from dmrg_b200.MPO import MPO
+    gs = np.linspace(0.2, 2.0, n_chains)
+    Ws = np.stack([(-g * MPO('sx') - MPO('sz') ** 2).tomatrix() for g in gs])
+    run = iDMRG.ChainBatch(Ws, trunc=chi)
+    times = []
+    while True:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        run.step()
+        torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+        if int(run.L.shape[1]) >= chi and len(times) >= int(np.log2(chi)) + 3:
+            break
+    w, d = 3, 2
+    nmv = statistics.mean(run.n_matvec[-2:])
+    sec = statistics.mean(times[-2:])
+    flop = n_chains * 8.0 * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
+    e = run.energy_per_site()
+    return {"workload": f"{n_chains} TFIM chains, g/J = 0.2 .. 2.0, chi = {chi}, d = 2, w = 3, complex128, lock-step growth",
+            "ms_per_growth_step": 1e3 * sec, "chain_steps_per_s": n_chains / sec, "matvecs_per_step": nmv,
+            "contraction_tflops": flop / sec / 1e12, "e_site_g0.2": float(e[0]), "e_site_g2.0": float(e[-1]),
+            "e_site_g1_exact": -4.0 / np.pi}
+
+
 def tebd_chain_leg():
     """BASELINE config 3 shape: ONE chain, L = 128, chi = 128, d = 2 - every half sweep is a batch of 63/64 saturated
     bonds through MPS.iTEBD_double (random canonical state, TFIM gate); ms per Trotter step = two half sweeps."""
@@ -463,6 +491,7 @@ def main():
             "hbm_peak_gbs": peaks.get("hbm_gbs")}
     if world == 1 and not args.no_idmrg:
         line["idmrg"] = idmrg_leg(not args.no_cpu)
+        line["idmrg_batch"] = idmrg_batch_leg()
         line["tebd_chain"] = tebd_chain_leg()
         line["finite_dmrg"] = finite_dmrg_leg()
     if world == 1 and not args.no_cpu:

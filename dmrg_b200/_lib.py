@@ -35,6 +35,8 @@ SIGNATURES = {
     "mpsb_mpo_site": (_i, [_i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),
     "mpsb_predict_workspace": (_sz, [_i, _i, _i]),
     "mpsb_predict_theta": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mpsb_predict_batched_workspace": (_sz, [_i, _i, _i, _i]),
+    "mpsb_predict_theta_batched": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_scale_rows": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "mpsb_transpose": (_i, [_i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "mpsb_transpose_batched": (_i, [_i, _i, _i, _vp, _i, _ll, _vp, _i, _ll, _i, _vp]),

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include "../../include/mpsb.h"
 #include "common.cuh"
@@ -132,6 +133,9 @@ predict_scale_kernel(int chi, int chip, int d, const cplx* __restrict__ B, const
     const long long total = (long long)chi * d * chip;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
+    B += (size_t)blockIdx.y * total; A += (size_t)blockIdx.y * total;         // chain of the batch
+    XL += (size_t)blockIdx.y * total; XR += (size_t)blockIdx.y * total;
+    S += (size_t)blockIdx.y * chi; Sinv += (size_t)blockIdx.y * chip;
     {   // B[a][s][c]
         const int c = (int)(e % chip);
         const int a = (int)(e / ((long long)d * chip));
@@ -384,9 +388,9 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
         auto tc = now();
         t_wait += us(tb, tc);
-        for (size_t ci = 0; ci < nb; ++ci) {
+        auto solve_chain = [&](size_t ci) {
             Chain& c = ch[ci];
-            if (c.frozen) continue;
+            if (c.frozen) return;
             const cplx* a1 = h1.data() + ci * kk * kk;
             const cplx* a2 = h2.data() + ci * kk * kk;
             const cplx* an = hn.data() + ci * kk;
@@ -417,6 +421,16 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
             const int best = c.idx[0];
             c.E = c.T[(size_t)best * mm + best];
             c.resid = std::fabs(c.beta_last * c.Y[(size_t)(mm - 1) * mm + best]);
+        };
+        // the projected eigenproblems of the chains are independent: spread them over a few host threads
+        const unsigned nthr = (unsigned)std::max<size_t>(1, std::min<size_t>({nb / 8, (size_t)16, (size_t)std::thread::hardware_concurrency()}));
+        if (nthr <= 1) {
+            for (size_t ci = 0; ci < nb; ++ci) solve_chain(ci);
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nthr; ++t)
+                pool.emplace_back([&, t] { for (size_t ci = t; ci < nb; ci += nthr) solve_chain(ci); });
+            for (auto& th_ : pool) th_.join();
         }
         t_host += us(tc, now());
         return 0;
@@ -553,29 +567,39 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
                                        energy_host, resid_host, n_matvec_host, ws, ws_bytes, stream);
 }
 
-size_t mpsb_predict_workspace(int chi, int chip, int d) {
-    return 2 * al((size_t)chi * d * chip * sizeof(cplx));
+size_t mpsb_predict_batched_workspace(int batch, int chi, int chip, int d) {
+    return 2 * al((size_t)batch * chi * d * chip * sizeof(cplx));
 }
+size_t mpsb_predict_workspace(int chi, int chip, int d) { return mpsb_predict_batched_workspace(1, chi, chip, d); }
 
-int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
-                       void* theta, void* ws, size_t ws_bytes, void* stream) {
+// A, B, S, S_prev_inv, theta: contiguous per chain ([batch][...])
+int mpsb_predict_theta_batched(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
+                               const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(chi >= 1 && chip >= 1 && d >= 1 && A && B && S && S_prev_inv && theta, "predict_theta: bad arguments");
-    const size_t need = mpsb_predict_workspace(chi, chip, d);
+    MPSB_REQUIRE(batch >= 1 && chi >= 1 && chip >= 1 && d >= 1 && A && B && S && S_prev_inv && theta,
+                 "predict_theta: bad arguments");
+    const size_t need = mpsb_predict_batched_workspace(batch, chi, chip, d);
     MPSB_REQUIRE(ws && ws_bytes >= need, "predict_theta: workspace %zu B < required %zu B", ws_bytes, need);
     cplx* XL = static_cast<cplx*>(ws);
     cplx* XR = reinterpret_cast<cplx*>(static_cast<unsigned char*>(ws) + need / 2);
     const long long total = (long long)chi * d * chip;
-    predict_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(chi, chip, d, static_cast<const cplx*>(B),
-                                                                          static_cast<const cplx*>(A), S, S_prev_inv, XL, XR);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    predict_scale_kernel<<<grid, 256, 0, st>>>(chi, chip, d, static_cast<const cplx*>(B), static_cast<const cplx*>(A), S,
+                                               S_prev_inv, XL, XR);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     GemmArgs g;
-    g.batch1 = 1; g.batch2 = 1; g.sA1 = g.sA2 = g.sB1 = g.sB2 = g.sC1 = g.sC2 = 0; g.accumulate = 0;
+    g.batch1 = batch; g.batch2 = 1; g.sA1 = total; g.sB1 = total; g.sC1 = (long long)chi * d * d * chi;
+    g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
     g.A = XL; g.B = XR; g.C = static_cast<cplx*>(theta);
     g.M = chi * d; g.N = d * chi; g.K = chip;
     g.lda = chip; g.ldb = d * chi; g.ldc = d * chi; g.opA = 0; g.opB = 0;
     return zgemm(g, st);
+}
+
+int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
+                       void* theta, void* ws, size_t ws_bytes, void* stream) {
+    return mpsb_predict_theta_batched(1, chi, chip, d, A, B, S, S_prev_inv, theta, ws, ws_bytes, stream);
 }
 
 size_t mpsb_env_batched_workspace(int batch, int chi, int chin, int d, int w) {

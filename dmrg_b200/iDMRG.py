@@ -364,11 +364,13 @@ class ChainBatch:
             E = run.step()            # total energies of the enlarged chains, array [n]
     """
 
-    def __init__(self, W, trunc=10, left_index=None, right_index=0, swap_conj=False):
+    def __init__(self, W, trunc=10, left_index=None, right_index=0, swap_conj=False, predict=True, cutoff=1e-12):
         W = np.asarray(W)
         assert W.ndim == 5, "W: one MPO per chain, [n, w, w, d, d]"
         self.n, self.w, self.d = int(W.shape[0]), int(W.shape[1]), int(W.shape[3])
         self.trunc, self.swap_conj = int(trunc), bool(swap_conj)
+        self.predict, self.cutoff = bool(predict), float(cutoff)
+        self.A = self.B = self.Sn = self.Sn_prev = None
         self.W = _lib.to_device(W)
         L = np.zeros((self.n, 1, 1, self.w), dtype=complex)
         R = np.zeros((self.n, 1, 1, self.w), dtype=complex)
@@ -378,13 +380,36 @@ class ChainBatch:
         self.energies, self.n_matvec, self.S = [], [], None
         self.sites = 0
 
+    def _prediction(self):
+        """Start vectors (S B) S_prev^-1 (A S) of all chains from the tensors of the last two splits (`Chain._prediction`
+        batched; needs U and V of one SVD, i.e. chi d <= 256, and a bond dimension that has stopped growing)."""
+        if not self.predict or self.Sn_prev is None or self.A is None:
+            return None
+        n, chip, d, chi = (int(v) for v in self.A.shape)
+        if self.Sn_prev.shape[1] != chip or self.Sn.shape[1] != chi or chi * d > 256:
+            return None
+        lib = _lib.load()
+        inv = np.where(self.Sn_prev > self.cutoff * self.Sn_prev[:, :1], 1.0 / np.maximum(self.Sn_prev, 1e-300), 0.0)
+        cur = np.where(self.Sn > self.cutoff * self.Sn[:, :1], self.Sn, 0.0)
+        theta = _lib.empty((n, chi, d, d, chi))
+        S, Sinv = _lib.to_device(cur, np.float64), _lib.to_device(inv, np.float64)
+        ws, wsn = _lib.workspace(lib.mpsb_predict_batched_workspace(n, chi, chip, d))
+        _lib.check(lib.mpsb_predict_theta_batched(n, chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S),
+                                                  _lib.ptr(Sinv), _lib.ptr(theta), ws, wsn, _lib.stream_ptr()),
+                   "mpsb_predict_theta_batched")
+        return theta
+
     def step(self, seed=0):
         """One growth step for every chain; returns the total energies [n]."""
-        E, theta = ground_state_batched(self.L, self.W, self.R, seed=seed + self.sites)
+        E, theta = ground_state_batched(self.L, self.W, self.R, seed=seed + self.sites, theta0=self._prediction())
         U, S, V = halve_batched(theta, self.trunc)
         self.L = _env_batched(True, self.L, U.contiguous(), self.W, self.swap_conj)
         self.R = _env_batched(False, self.R, V.contiguous(), self.W, self.swap_conj)
         self.S = _lib.to_host(S)
+        k = int(U.shape[3])
+        sk = self.S[:, :k]
+        self.Sn_prev, self.Sn = self.Sn, sk / np.linalg.norm(sk, axis=1, keepdims=True)
+        self.A, self.B = U.contiguous(), V.contiguous()
         self.sites += 2
         self.energies.append(E)
         self.n_matvec.append(last_info["n_matvec"])

@@ -186,6 +186,10 @@ size_t mpsb_predict_workspace(int chi, int chip, int d);
 int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
                        void* theta, void* ws, size_t ws_bytes, void* stream);
 
+size_t mpsb_predict_batched_workspace(int batch, int chi, int chip, int d);
+int mpsb_predict_theta_batched(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
+                               const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream);
+
 /* out[i * ldo + j] = s[i / group] * in[i * ldi + j]: the Lambda_l scaling `self.Sl[i][:, newaxis, ...] * theta`
  * (DMRG/MPS.py:446) of a tensor viewed as a (chi_l * group) x cols matrix.  Used by the multi-site update
  * (MPS.update_k, DMRG/MPS.py:459-461), whose splits have unequal local dimensions on the two sides. */
