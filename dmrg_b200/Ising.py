@@ -16,7 +16,9 @@ def nearest(n, *ops, coef=1, sparse=False):
     k = len(ops)
     one = np.eye(ops[0].shape[0])
     weight = coef * np.ones(n)
-    kron = sps.kron if sparse else np.kron
+    # sparse: the first factor is wrapped as a sparse MATRIX, which keeps scipy.sparse.kron on the spmatrix interface
+    # the reference relies on (and silences scipy's "switching to the sparse array interface" deprecation)
+    kron = (lambda a, b: sps.kron(sps.coo_matrix(a), b)) if sparse else np.kron
     total = 0
     for start in range(n - k + 1):
         factors = [one] * start + list(ops) + [one] * (n - k - start)

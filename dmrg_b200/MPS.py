@@ -296,8 +296,10 @@ class MPS:
         t = self._dev[i]
         xl, d, xr = (int(v) for v in t.shape)
         U = _lib.to_device(np.eye(d) * factor)
-        _lib.check(_lib.load().mpsb_one_site(1, xl, xr, d, _lib.ptr(t), 0, _lib.ptr(U), 0, _lib.ptr(t), 0, _lib.stream_ptr()),
-                   "mpsb_one_site")
+        out = t if d <= 16 else _lib.empty(tuple(t.shape))       # the in-place kernel covers d <= 16, larger d go through GEMM
+        _lib.check(_lib.load().mpsb_one_site(1, xl, xr, d, _lib.ptr(t), 0, _lib.ptr(U), 0, _lib.ptr(out), 0,
+                                             _lib.stream_ptr()), "mpsb_one_site")
+        self._dev[i] = out
 
     def unify_end(self):
         """Divide the phases parked in the dummy boundary tensors back in (DMRG/MPS.py:286-293)."""
@@ -380,8 +382,10 @@ class MPS:
         for i in sites:
             t = self._dev[i]
             xl, d, xr = (int(v) for v in t.shape)
-            _lib.check(lib.mpsb_one_site(1, xl, xr, d, _lib.ptr(t), 0, _lib.ptr(U_dev), 0, _lib.ptr(t), 0,
+            out = t if d <= 16 else _lib.empty(tuple(t.shape))
+            _lib.check(lib.mpsb_one_site(1, xl, xr, d, _lib.ptr(t), 0, _lib.ptr(U_dev), 0, _lib.ptr(out), 0,
                                          _lib.stream_ptr()), "mpsb_one_site")
+            self._dev[i] = out
 
     def update_double(self, U, i, unitary=True):
         """Two-site gate on sites (i, i+1) with SVD truncation (DMRG/MPS.py:428-457)."""

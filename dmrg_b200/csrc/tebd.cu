@@ -129,10 +129,20 @@ int gate_scale(int batch, int chil, int chir, int d, const cplx* theta0, long lo
 
 int one_site(int batch, int chil, int chir, int d, const cplx* M, long long sM, const cplx* U, long long sU, cplx* Mo,
              long long sMo, cudaStream_t st) {
-    MPSB_REQUIRE(d >= 1 && d <= ONE_SITE_DMAX, "one_site: local dimension %d not in [1, %d]", d, ONE_SITE_DMAX);
+    MPSB_REQUIRE(d >= 1, "one_site: local dimension %d", d);
     MPSB_REQUIRE(batch <= 65535, "one_site: batch %d exceeds grid.y", batch);
     const long long total = (long long)chil * chir;
     if (total == 0 || batch == 0) return 0;
+    if (d > ONE_SITE_DMAX) {        // large local spaces (boson chains, fused sites): one d x d GEMM per left index
+        MPSB_REQUIRE(M != Mo, "one_site: the in-place form needs d <= %d (d = %d)", ONE_SITE_DMAX, d);
+        GemmArgs g;
+        g.A = U; g.B = M; g.C = Mo;
+        g.M = d; g.N = chir; g.K = d; g.lda = d; g.ldb = chir; g.ldc = chir; g.opA = 0; g.opB = 0;
+        g.batch1 = batch; g.batch2 = chil;
+        g.sA1 = sU; g.sB1 = sM; g.sC1 = sMo; g.sA2 = 0; g.sB2 = (long long)d * chir; g.sC2 = (long long)d * chir;
+        g.accumulate = 0;
+        return zgemm(g, st);
+    }
     dim3 grid((unsigned)((total + 255) / 256), batch);
     one_site_kernel<<<grid, 256, 0, st>>>(chil, chir, d, M, sM, U, sU, Mo, sMo);
     MPSB_COUNT_LAUNCH();

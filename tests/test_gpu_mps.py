@@ -452,3 +452,16 @@ def _random_canonical_chain(seed, Lc, chi):
     o = OracleMPS([rs.randn(x[i], 2, x[i + 1]) + 1j * rs.randn(x[i], 2, x[i + 1]) for i in range(Lc)], trun=chi, err=1e-12)
     o.canon()
     return [m.copy() for m in o.M[:Lc]], [np.array(v) for v in o.s]
+
+
+def test_update_single_large_local_dimension(lib):
+    """`update_single` for d > 16 (the reference accepts any d, DMRG/MPS.py:413-425): the GEMM path of mpsb_one_site."""
+    from dmrg_b200.MPS import MPS
+    rs = np.random.RandomState(12)
+    d = 20
+    Ms = [rs.randn(1, d, 3) + 1j * rs.randn(1, d, 3), rs.randn(3, d, 1) + 1j * rs.randn(3, d, 1)]
+    A = rs.randn(d, d) + 1j * rs.randn(d, d)
+    U = la.expm(0.1j * (A + A.conj().T))
+    s = MPS([m.copy() for m in Ms], d, trun=8, err=1e-12)
+    s.update_single(U, 0)
+    np.testing.assert_allclose(np.asarray(s.M[0]), np.einsum('lcr, dc->ldr', Ms[0], U), atol=1e-12)
