@@ -441,10 +441,13 @@ def main():
     nrow, ncol = CHI * D, D * CHI
     npairs = nrow * (nrow - 1) // 2
     k_steps = args.steps
-    # Algorithmic flops of the Jacobi phase.  Lean model = what one-sided Jacobi must do per visited
-    # pair with cached row norms and scaled rotations: the cross inner product (4 FMA = 8 flops per column) and,
-    # if the pair is rotated, the 2x2 update of two complex rows in scaled form (8 FMA = 16 flops per column).
-    # The textbook count (three inner products, unscaled rotation: 16 and 24 flops per column) is given beside it.
+    # Algorithmic flops of the SVD phase.  Primary figure: SURVEY 8(d)'s count for one truncated SVD with vectors,
+    # 4 * 21 n^3 real flops at n = d chi = 256 -> 1.409 GFLOP, over the time of the WHOLE SVD phase (QR preconditioning
+    # + Jacobi sweeps) - it does not grow with the number of sweeps.  Second figure ("lean"): what one-sided Jacobi has
+    # to do per visited pair with cached norms and scaled rotations (inner product 8 flops per column; 2 x 2 update of
+    # two complex rows 16 flops per column), from the library's own sweep / rotation counters, over the Jacobi time.
+    svd_flop = k_steps * n * 4.0 * 21.0 * float(nrow) ** 3
+    svd_s = (phases[2] + phases[3]) * 1e-3
     jac_flop = sweeps * npairs * 8.0 * ncol + rot * 16.0 * ncol
     jac_flop_textbook = sweeps * npairs * 16.0 * ncol + rot * 24.0 * ncol
     jac_s = phases[3] * 1e-3
@@ -457,18 +460,23 @@ def main():
         pass
     traffic = None
     try:   # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
-    except (OSError, ValueError):
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
         pass
-    roofline = {"kernel": "jacobi_cross_kernel (all Jacobi sweeps of one step, modulus ordering; self tasks ride in the same launches)", "bound": "fp64",
-                "achieved": jac_flop / jac_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": jac_flop / jac_s / 1e12 / fp64_peak,
+    peak_note = ("cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; profiles/r2_fp64_peak.json "
+                 "holds the DFMA / DMMA / mixed micro-benchmark of this pool: 35.5 / 37.1 / 33.8 TFLOP/s - DMMA and DFMA "
+                 "share one execution unit on this part)")
+    roofline = {"kernel": "jacobi_cross_kernel (all Jacobi sweeps of one step, modulus ordering; self tasks ride in the same launches)",
+                "bound": "fp64",
+                "achieved": svd_flop / svd_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": svd_flop / svd_s / 1e12 / fp64_peak,
                 "traffic": traffic,
-                "flop_model": "lean: 8*L per visited pair + 16*L per rotation (L = 256 columns)",
-                "achieved_textbook": jac_flop_textbook / jac_s / 1e12,
-                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); B200 FP64 "
-                               "vector and tensor peaks are nominally equal, so one denominator serves both",
-                "share_of_step": float(phases[3] / phases.sum())}
+                "flop_model": "SURVEY 8(d): 4*21*n^3 = 1.409 GFLOP per truncated SVD (n = 256), over QR + Jacobi time",
+                "lean": {"achieved": jac_flop / jac_s / 1e12, "frac": jac_flop / jac_s / 1e12 / fp64_peak,
+                         "flop_model": "8*L per visited pair + 16*L per rotation (L = 256 columns), library counters, Jacobi time only",
+                         "achieved_textbook": jac_flop_textbook / jac_s / 1e12},
+                "peak_source": peak_note,
+                "share_of_step": float((phases[2] + phases[3]) / phases.sum())}
     roof_gemm = {"kernel": "zgemm_kernel (theta formation + back-projection, DMMA m8n8k4)", "bound": "tensor",
                  "achieved": gemm_flop / gemm_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                  "frac": gemm_flop / gemm_s / 1e12 / fp64_peak, "traffic": None,

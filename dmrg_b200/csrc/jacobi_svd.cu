@@ -1042,24 +1042,13 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
     const double cs = newton_rsqrt(wv, newton_rsqrt(wv, rsqrt_approx(wv)));
     const double cs2 = cs * cs;
     const double delta = k * ac2;                                            // t |c|
-    const double an = r.a - delta, bn = bq + delta;
-    const double dpn = r.d * cs, epn = r.e * cs2, dqn = dq * cs, eqn = eq * cs2;
+    r.d *= cs;
+    r.e *= cs2;
+    r.a -= delta;
     r.dirty = true;
-    if (sort && an < bn) {                                                   // identical in every lane
-        r.d = dqn; r.e = eqn; r.a = bn;
-        dq = dpn; eq = epn; bq = an;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const cplx xo = r.x[j], yo = y[j];
-            y[j].x = fma(-tpr, yo.x, fma(tpi, yo.y, xo.x));
-            y[j].y = fma(-tpr, yo.y, fma(-tpi, yo.x, xo.y));
-            r.x[j].x = fma(sqr, xo.x, fma(-sqi, xo.y, yo.x));
-            r.x[j].y = fma(sqr, xo.y, fma(sqi, xo.x, yo.y));
-        }
-        return 1;
-    }
-    r.d = dpn; r.e = epn; r.a = an;
-    dq = dqn; eq = eqn; bq = bn;
+    dq *= cs;
+    eq *= cs2;
+    bq += delta;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const cplx xo = r.x[j], yo = y[j];
@@ -1068,7 +1057,34 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
         y[j].x = fma(sqr, xo.x, fma(-sqi, xo.y, yo.x));
         y[j].y = fma(sqr, xo.y, fma(sqi, xo.x, yo.y));
     }
+    // de Rijk's rule: the register row (lower block) keeps the larger norm.  With rows that start sorted (pivoted QR)
+    // this fires for well under 1 % of the rotations of the first sweeps and never later; the caller then exchanges
+    // the two rows through the shared-memory slot of y (return value 2), here only the bookkeeping trades places.
+    if (sort && r.a < bq) {
+        double t;
+        t = r.d; r.d = dq; dq = t;
+        t = r.e; r.e = eq; eq = t;
+        t = r.a; r.a = bq; bq = t;
+        return 2;
+    }
     return 1;
+}
+
+// Exchange the register row with the streamed row y (cold path of de Rijk's rule): through y's shared-memory slot, so
+// that no temporary registers are needed in a kernel that sits at its register limit.
+template <bool FULL>
+__device__ __forceinline__ void swap_rows_via_smem(RegRow& r, cplx (&y)[8], cplx* rq, int ltot_r, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (FULL || c < ltot_r) { rq[c] = r.x[j]; r.x[j] = y[j]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (FULL || c < ltot_r) y[j] = rq[c];
+    }
 }
 
 template <bool FULL>
@@ -1077,19 +1093,6 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
                     int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
                     unsigned long long* __restrict__ phase_clk, int* __restrict__ stamps, int stamp_stride,
                     int launch_id, int modulus) {
-    // modulus ordering, even steps: the CTA after the cross pairs plays the two self tasks of the step
-    if (modulus && blockIdx.x >= mod_cross_pairs(nblk, round)) {
-        const int mat = mat0 + blockIdx.y;
-        if (done[mat]) return;
-        cplx* X = Xall + (size_t)mat * strideX;
-        int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
-        const int bA = round >> 1, bB = bA + (nblk >> 1), unit = stamp_self_index(nblk, bA);
-        if (FULL) selftask_body<4, true>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
-        else if (ltot_r > 128) selftask_body<4, false>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
-        else if (ltot_r > 64) selftask_body<2, false>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
-        else selftask_body<1, false>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, unit, launch_id);
-        return;
-    }
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [8][ltot_r]
     __shared__ double nq[8], dqs[8], eqs[8];                  // true norm^2, scale d and d^2 of the rows of block J
@@ -1169,8 +1172,10 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
             y[j] = (FULL || c < ltot_r) ? rq[c] : make_double2(0.0, 0.0);
         }
         double dq = dqs[q], eq = eqs[q], bq = nq[q];
-        const int n0 = cross_pair<FULL>(r0, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
-        const int n1 = cross_pair<FULL>(r1, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
+        int n0 = cross_pair<FULL>(r0, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
+        if (n0 == 2) { swap_rows_via_smem<FULL>(r0, y, rq, ltot_r, lane); n0 = 1; }
+        int n1 = cross_pair<FULL>(r1, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
+        if (n1 == 2) { swap_rows_via_smem<FULL>(r1, y, rq, ltot_r, lane); n1 = 1; }
         nrot += n0 + n1;
         // Even rows of block J are visited in even steps, odd rows in odd steps, so steps 6 and 7 are the last
         // visits: fold the accumulated scale back into the row there.
@@ -1233,6 +1238,23 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
             atomicAdd(&phase_clk[3], 1ull);
         }
     }
+}
+
+// ---- self tasks of the modulus ordering (jacobi_selftask.cuh) --------------------------------------------------------
+// Even steps: blocks round/2 and round/2 + nblk/2 meet nobody, one 128-thread CTA per problem orthogonalises the pairs
+// inside them.  A kernel of its own: compiled into jacobi_cross_kernel its 4.5 k straight-line instructions cost the
+// cross CTAs registers (spills in the hot loop) and instruction-cache hits (no-instruction stalls 0.08 -> 0.47 per issue).
+template <int CPL, bool EXACT>
+__global__ void __launch_bounds__(128, 3)
+jacobi_self_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk, int round,
+                   int* __restrict__ rot, const int* __restrict__ done, double tol2, int* __restrict__ stamps,
+                   int stamp_stride, int launch_id) {
+    const int mat = mat0 + blockIdx.x;
+    if (done[mat]) return;
+    cplx* X = Xall + (size_t)mat * strideX;
+    int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
+    const int bA = round >> 1, bB = bA + (nblk >> 1);
+    selftask_body<CPL, EXACT>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, stamp_self_index(nblk, bA), launch_id);
 }
 
 // ---- Gram-assisted round (block of 16 rows per CTA, FP64 tensor cores) -------------------------------
@@ -1983,8 +2005,8 @@ int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, i
     return 0;
 }
 
-// Modulus ordering (rows of <= 256 columns, 8-row blocks): step `round` in [0, nblk) = ONE launch of the register-
-// resident cross kernel over the step's cross pairs; on even steps one more CTA per problem plays the two self tasks
+// Modulus ordering (rows of <= 256 columns, 8-row blocks): step `round` in [0, nblk) = one launch of the register-
+// resident cross kernel over the step's cross pairs; on even steps a second, small launch plays the two self tasks
 // (pairs inside blocks round/2 and round/2 + nblk/2, which no cross pair of the step touches).
 bool use_modulus_order(const SvdPlan& pl) {
     const int nblk = pl.n_pad / 8, ltot_r = round_up(pl.ltot, 32);
@@ -2001,7 +2023,7 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
     if (int rc = ensure_dynamic_smem(full ? reinterpret_cast<const void*>(jacobi_cross_kernel<true>)
                                           : reinterpret_cast<const void*>(jacobi_cross_kernel<false>), smem))
         return rc;
-    dim3 grid(mod_cross_pairs(nblk, round) + ((round & 1) ? 0 : 1), count);
+    dim3 grid(mod_cross_pairs(nblk, round), count);
     if (full)
         jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
                                                                      s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride,
@@ -2012,6 +2034,18 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
                                                                       launch_id, 1);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
+    if ((round & 1) == 0) {
+#define MPSB_SELF(CPL, EXACT)                                                                                              \
+    jacobi_self_kernel<CPL, EXACT><<<count, 128, 0, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, \
+                                                          tol2, s.stamps, s.stamp_stride, launch_id)
+        if (full) MPSB_SELF(4, true);
+        else if (ltot_r > 128) MPSB_SELF(4, false);
+        else if (ltot_r > 64) MPSB_SELF(2, false);
+        else MPSB_SELF(1, false);
+#undef MPSB_SELF
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
