@@ -174,7 +174,7 @@ def idmrg_batch_leg(n_chains=256, chi=128):
     n_chains independent chains grown in lock step by dmrg_b200.iDMRG.ChainBatch; ms per growth step at bond
     dimension chi and the contraction rate of the whole step on SURVEY 8(d)'s F_iDMRG-step formula (complex flops)."""
     import torch
-    from dmrg_b200 import iDMRG
+    from dmrg_b200 import iDMRG, _lib as L_
     from dmrg_b200.MPO import MPO
     gs = np.linspace(0.2, 2.0, n_chains)
     Ws = np.stack([(-g * MPO('sx') - MPO('sz') ** 2).tomatrix() for g in gs])
@@ -187,13 +187,37 @@ def idmrg_batch_leg(n_chains=256, chi=128):
         if int(run.L.shape[1]) >= chi and len(times) >= int(np.log2(chi)) + 3:
             break
     w, d = 3, 2
+    # the batched H_eff product alone (DMRG/iDMRG.py:38-40 + the dense matvec inside eigsh, :57), CUDA events
+    lib = L_.load()
+    theta = torch.randn((n_chains, chi, d, d, chi), dtype=torch.complex128, device=run.L.device)
+    out = torch.empty_like(theta)
+    nel = chi * d * d * chi
+    ws, wsn = L_.workspace(lib.mpsb_heff_batched_workspace(n_chains, chi, chi, d, w))
+
+    def matvec():
+        L_.check(lib.mpsb_heff_matvec_batched(n_chains, chi, chi, d, w, L_.ptr(run.L), chi * chi * w, L_.ptr(run.W), w * w * d * d,
+                                              L_.ptr(run.R), chi * chi * w, L_.ptr(theta), nel, L_.ptr(out), nel, ws, wsn,
+                                              L_.stream_ptr()), "mpsb_heff_matvec_batched")
+    for _ in range(3):
+        matvec()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        matvec()
+    e1.record(); torch.cuda.synchronize()
+    mv_ms = e0.elapsed_time(e1) / 20
+    mv_flop = n_chains * 8.0 * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2)
     nmv = statistics.mean(run.n_matvec[-2:])
     sec = statistics.mean(times[-2:])
     flop = n_chains * 8.0 * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
     e = run.energy_per_site()
     return {"workload": f"{n_chains} TFIM chains, g/J = 0.2 .. 2.0, chi = {chi}, d = 2, w = 3, complex128, lock-step growth",
             "ms_per_growth_step": 1e3 * sec, "chain_steps_per_s": n_chains / sec, "matvecs_per_step": nmv,
-            "contraction_tflops": flop / sec / 1e12, "e_site_g0.2": float(e[0]), "e_site_g2.0": float(e[-1]),
+            "contraction_tflops": flop / sec / 1e12,
+            "matvec_only": {"ms": mv_ms, "tflops": mv_flop / (mv_ms * 1e-3) / 1e12,
+                            "note": "mpsb_heff_matvec_batched alone (incl. its per-call MPO / environment preparation), "
+                                    "SURVEY 8(d) flops 8 (2 w d^2 chi^3 + 2 w^2 d^3 chi^2) per chain"},
+            "e_site_g0.2": float(e[0]), "e_site_g2.0": float(e[-1]),
             "e_site_g1_exact": -4.0 / np.pi}
 
 
