@@ -49,8 +49,51 @@ __global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, long l
 }
 
 // T3[A][B][C][dr][k] = sum_{i,b,c} WW[i][k][B][C][b][c] T1[i][A][b][c][dr]
-// One thread per (A, B, C, dr) producing the w values of k (contiguous store).  Zero blocks of the
-// (lower-triangular, mostly empty) MPO are skipped; the test is uniform across the warp.
+// One thread per (A, dr): it reads its w d^2 inputs once and produces all d^2 w outputs (instantiated for d = 2 with
+// w = 3 and w = 5; other MPOs take one (B, C) per thread, below), so T1 and T3 cross the memory system exactly once.  Zero blocks of
+// the (lower-triangular, mostly empty) MPO are skipped; the test is uniform across the warp.
+template <int W, int D>
+__global__ void __launch_bounds__(128)
+ww_apply_fused_kernel(int chil, int chir, const cplx* __restrict__ WW, long long sWW, const cplx* __restrict__ T1,
+                      cplx* __restrict__ T3) {
+    constexpr int DD = D * D;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)chil * chir;
+    if (e >= total) return;
+    const long long per_chain = (long long)chil * DD * chir * W;
+    WW += (size_t)blockIdx.y * sWW;
+    T1 += (size_t)blockIdx.y * per_chain;
+    T3 += (size_t)blockIdx.y * per_chain;
+    const int dr = (int)(e % chir), A = (int)(e / chir);
+    cplx x[W][DD];
+    const size_t t1_row = (size_t)DD * chir;             // elements per (i, A)
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+#pragma unroll
+        for (int bc = 0; bc < DD; ++bc) x[i][bc] = T1[((size_t)i * chil + A) * t1_row + (size_t)bc * chir + dr];
+#pragma unroll
+    for (int BC = 0; BC < DD; ++BC) {
+        cplx* out = T3 + (((size_t)A * DD + BC) * chir + dr) * W;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            double re = 0.0, im = 0.0;
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                const cplx* g0 = WW + (((size_t)i * W + k) * DD + BC) * DD;
+#pragma unroll
+                for (int bc = 0; bc < DD; ++bc) {
+                    const cplx g = g0[bc];
+                    if (g.x == 0.0 && g.y == 0.0) continue;
+                    re = fma(g.x, x[i][bc].x, fma(-g.y, x[i][bc].y, re));
+                    im = fma(g.x, x[i][bc].y, fma(g.y, x[i][bc].x, im));
+                }
+            }
+            out[k] = make_double2(re, im);
+        }
+    }
+}
+
+// General form: one thread per (A, B, C, dr) producing the w values of k (contiguous store).
 __global__ void __launch_bounds__(256)
 ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, long long sWW,
                 const cplx* __restrict__ T1, cplx* __restrict__ T3) {
@@ -190,8 +233,15 @@ int heff_apply(const Heff& h, const cplx* theta, cplx* out, cudaStream_t st, lon
     g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
     int rc = zgemm(g, st);
     if (rc) return rc;
-    dim3 grid((unsigned)((h.n + 255) / 256), h.batch);
-    ww_apply_kernel<<<grid, 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.sWW, h.T1, h.T3);
+    dim3 fgrid((unsigned)(((long long)h.chil * h.chir + 127) / 128), h.batch);
+    if (h.d == 2 && h.w == 3) {            // TFIM-like MPOs: the inputs of a thread fit its registers
+        ww_apply_fused_kernel<3, 2><<<fgrid, 128, 0, st>>>(h.chil, h.chir, h.WW, h.sWW, h.T1, h.T3);
+    } else if (h.d == 2 && h.w == 5) {     // Heisenberg / XXZ
+        ww_apply_fused_kernel<5, 2><<<fgrid, 128, 0, st>>>(h.chil, h.chir, h.WW, h.sWW, h.T1, h.T3);
+    } else {
+        dim3 grid((unsigned)((h.n + 255) / 256), h.batch);
+        ww_apply_kernel<<<grid, 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.sWW, h.T1, h.T3);
+    }
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     // out[(A,B,C)][D] = sum_{(dr,k)} T3[(A,B,C)][(dr,k)] R[D][(dr,k)]
@@ -440,14 +490,28 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         auto ta = now();
         int formed = m;
         bool evaluated = false;
+        MPSB_CHECK_CUDA(cudaMemsetAsync(C1, 0, al(nb * kk * kk * sizeof(cplx)), st));     // pass 1 fills only part of a row
         for (int j = j0; j < m; ++j) {
             cplx* vj = V + (size_t)j * vstride;
             cplx* wv = V + (size_t)(j + 1) * vstride;
             rc = heff_apply(h, vj, wv, st, sV, sV);
             if (rc) return rc;
             ++n_mv;
-            for (int pass = 0; pass < 2; ++pass) {
-                cplx* c = (pass == 0 ? C1 : C2) + (size_t)j * kk;
+            // Gram-Schmidt in two passes.  Pass 1 is the Lanczos recurrence itself: it removes the large components
+            // along v_j and v_{j-1} (right after a (re)start: along every basis vector, the kept Ritz vectors all couple
+            // to the continued one), so that pass 2 - the full reorthogonalisation - subtracts only rounding-level
+            // coefficients and needs no repetition.  Traffic per step: 3 + j vectors instead of 2 (j + 1).
+            const int lo = (j == j0) ? 0 : std::max(0, j - 1);
+            {
+                cplx* c = C1 + (size_t)j * kk + lo;
+                const cplx* Vlo = V + (size_t)lo * vstride;
+                rc = zdotc_multi(Vlo, (long long)vstride, j + 1 - lo, (long long)n, wv, c, part, nchunk, (int)kk, st, bat(sV, sV, sC));
+                if (rc) return rc;
+                rc = zaxpy_multi(Vlo, (long long)vstride, j + 1 - lo, (long long)n, c, -1.0, wv, st, bat(sV, sV, sC));
+                if (rc) return rc;
+            }
+            {
+                cplx* c = C2 + (size_t)j * kk;
                 rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, (int)kk, st, bat(sV, sV, sC));
                 if (rc) return rc;
                 rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c, -1.0, wv, st, bat(sV, sV, sC));
