@@ -26,6 +26,7 @@ SIGNATURES = {
     "mpsb_profile_enable": (None, [_i]),
     "mpsb_profile_read": (_i, [_pd, _c.POINTER(_c.c_ulonglong), _c.POINTER(_c.c_ulonglong)]),
     "mpsb_zgemm": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _i, _vp]),
+    "mpsb_dgemm": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _i, _vp]),
     "mpsb_svd_trunc_workspace": (_sz, [_i, _i, _i, _i]),
     "mpsb_svd_trunc": (_i, [_i, _i, _i, _vp, _i, _ll, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_tebd_two_site_workspace": (_sz, [_i, _i, _i, _i, _i]),
@@ -42,6 +43,14 @@ SIGNATURES = {
     "mpsb_transpose_batched": (_i, [_i, _i, _i, _vp, _i, _ll, _vp, _i, _ll, _i, _vp]),
     "mpsb_heff_batched_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "mpsb_heff_matvec_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz, _vp]),
+    "mpsb_heff_matvec_batched_real": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz,
+                                           _vp]),
+    "mpsb_lanczos_ground_batched_real": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _pd, _pd,
+                                              _pi, _vp, _sz, _vp]),
+    "mpsb_env_left_batched_real": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz, _vp]),
+    "mpsb_env_right_batched_real": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz, _vp]),
+    "mpsb_predict_theta_batched_real": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mpsb_transpose_batched_real": (_i, [_i, _i, _i, _vp, _i, _ll, _vp, _i, _ll, _vp]),
     "mpsb_lanczos_batched_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mpsb_lanczos_ground_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _pd, _pd, _pi,
                                          _vp, _sz, _vp]),
@@ -228,6 +237,12 @@ def zgemm(A, B, C, M, N, K, lda, ldb, ldc, opA=OP_N, opB=OP_N, batch1=1, batch2=
           accumulate=False):
     check(load().mpsb_zgemm(opA, opB, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, batch1, batch2, sA[0], sA[1],
                             sB[0], sB[1], sC[0], sC[1], int(accumulate), stream_ptr()), "mpsb_zgemm")
+
+
+def dgemm(A, B, C, M, N, K, lda, ldb, ldc, opA=OP_N, opB=OP_N, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0),
+          accumulate=False):
+    check(load().mpsb_dgemm(opA, opB, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, batch1, batch2, sA[0], sA[1],
+                            sB[0], sB[1], sC[0], sC[1], int(accumulate), stream_ptr()), "mpsb_dgemm")
 
 
 def matmul(A, B, opA=OP_N, opB=OP_N):

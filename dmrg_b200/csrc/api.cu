@@ -142,6 +142,22 @@ int mpsb_zgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, co
     return zgemm(p, static_cast<cudaStream_t>(stream));
 }
 
+int mpsb_dgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+               int ldc, int batch1, int batch2, long long sA1, long long sA2, long long sB1, long long sB2,
+               long long sC1, long long sC2, int accumulate, void* stream) {
+    GemmArgsT<double> p;
+    p.A = static_cast<const double*>(A);
+    p.B = static_cast<const double*>(B);
+    p.C = static_cast<double*>(C);
+    p.M = M; p.N = N; p.K = K;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.opA = opA; p.opB = opB;
+    p.batch1 = batch1; p.batch2 = batch2;
+    p.sA1 = sA1; p.sA2 = sA2; p.sB1 = sB1; p.sB2 = sB2; p.sC1 = sC1; p.sC2 = sC2;
+    p.accumulate = accumulate;
+    return dgemm(p, static_cast<cudaStream_t>(stream));
+}
+
 // ---- svd_truncate / halve ---------------------------------------------------------------------------
 size_t mpsb_svd_trunc_workspace(int batch, int rows, int cols, int want_u) {
     SvdLayout L;
@@ -252,6 +268,12 @@ int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int l
 int mpsb_transpose_batched(int batch, int rows, int cols, const void* in, int ldi, long long s_in, void* out, int ldo,
                            long long s_out, int conj, void* stream) {
     return transpose_conj(static_cast<const cplx*>(in), ldi, rows, cols, static_cast<cplx*>(out), ldo, conj,
+                          static_cast<cudaStream_t>(stream), batch, s_in, s_out);
+}
+
+int mpsb_transpose_batched_real(int batch, int rows, int cols, const void* in, int ldi, long long s_in, void* out, int ldo,
+                                long long s_out, void* stream) {
+    return transpose_conj(static_cast<const double*>(in), ldi, rows, cols, static_cast<double*>(out), ldo, 0,
                           static_cast<cudaStream_t>(stream), batch, s_in, s_out);
 }
 

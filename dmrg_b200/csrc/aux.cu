@@ -38,10 +38,11 @@ pack_kernel(cplx* __restrict__ X, int n_pad, int ld, int rows, int ldot, int lto
 }
 
 // 32x32 tile transpose through shared memory (padded against bank conflicts).
+template <typename T>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const cplx* __restrict__ in, int ldi, int rows, int cols, cplx* __restrict__ out, int ldo,
+transpose_kernel(const T* __restrict__ in, int ldi, int rows, int cols, T* __restrict__ out, int ldo,
                  int conj, long long s_in, long long s_out) {
-    __shared__ cplx tile[32][33];
+    __shared__ T tile[32][33];
     in += (size_t)blockIdx.z * s_in;
     out += (size_t)blockIdx.z * s_out;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -54,21 +55,29 @@ transpose_kernel(const cplx* __restrict__ in, int ldi, int rows, int cols, cplx*
     for (int r = ty; r < 32; r += 8) {
         const int j = j0 + r, i = i0 + tx;
         if (i < rows && j < cols) {
-            cplx v = tile[tx][r];
-            if (conj) v.y = -v.y;
+            T v = tile[tx][r];
+            if (conj) v = Sc<T>::conj(v);
             out[(size_t)j * ldo + i] = v;
         }
     }
 }
 
+__device__ __forceinline__ double warp_sum_t(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx warp_sum_t(cplx v) { return make_double2(warp_sum_t(v.x), warp_sum_t(v.y)); }
+
 constexpr int DOT_THREADS = 256;
 // y[j] = sum_i conj(V[j][i]) w[i]: every block reduces one chunk of one vector into part[j][chunk]; the block that
 // draws the last ticket of vector j adds the partials in a fixed order (deterministic) and re-arms the ticket.
 // `part` holds m * nchunk partial sums followed by m ticket counters (zero on entry, zero again on exit).
+template <typename T>
 __global__ void __launch_bounds__(DOT_THREADS)
-dot_fused_kernel(const cplx* __restrict__ V, long long ldv, long long n, const cplx* __restrict__ w,
-                 cplx* __restrict__ part, int nchunk, int m_cap, cplx* __restrict__ y, BlasBatch bb) {
-    __shared__ double sr[DOT_THREADS / 32], si[DOT_THREADS / 32];
+dot_fused_kernel(const T* __restrict__ V, long long ldv, long long n, const T* __restrict__ w,
+                 T* __restrict__ part, int nchunk, int m_cap, T* __restrict__ y, BlasBatch bb) {
+    __shared__ T sred[DOT_THREADS / 32];
     __shared__ int is_last;
     const int j = blockIdx.y, ch = blockIdx.x;
     V += (size_t)blockIdx.z * bb.sV; w += (size_t)blockIdx.z * bb.sw;
@@ -76,77 +85,53 @@ dot_fused_kernel(const cplx* __restrict__ V, long long ldv, long long n, const c
     unsigned int* tickets = reinterpret_cast<unsigned int*>(part + (size_t)m_cap * nchunk);
     const long long per = (n + nchunk - 1) / nchunk;
     const long long lo = (long long)ch * per, hi = lo + per < n ? lo + per : n;
-    const cplx* v = V + (size_t)j * ldv;
-    double re = 0.0, im = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += DOT_THREADS) {
-        const cplx a = v[i], b = w[i];
-        re = fma(a.x, b.x, fma(a.y, b.y, re));
-        im = fma(a.x, b.y, fma(-a.y, b.x, im));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        re += __shfl_xor_sync(0xffffffffu, re, o);
-        im += __shfl_xor_sync(0xffffffffu, im, o);
-    }
-    if ((threadIdx.x & 31) == 0) { sr[threadIdx.x >> 5] = re; si[threadIdx.x >> 5] = im; }
+    const T* v = V + (size_t)j * ldv;
+    T acc = Sc<T>::zero();
+    for (long long i = lo + threadIdx.x; i < hi; i += DOT_THREADS) Sc<T>::macc(acc, v[i], w[i]);
+    acc = warp_sum_t(acc);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int q = 0; q < DOT_THREADS / 32; ++q) { a += sr[q]; b += si[q]; }
-        part[(size_t)j * nchunk + ch] = make_double2(a, b);
+        T a = Sc<T>::zero();
+        for (int q = 0; q < DOT_THREADS / 32; ++q) a = Sc<T>::add(a, sred[q]);
+        part[(size_t)j * nchunk + ch] = a;
         __threadfence();
         is_last = (atomicAdd(&tickets[j], 1u) == (unsigned)(nchunk - 1));
     }
     __syncthreads();
     if (is_last && threadIdx.x < 32) {
-        double a = 0.0, b = 0.0;
-        for (int q = threadIdx.x; q < nchunk; q += 32) {
-            const cplx t = __ldcg(&part[(size_t)j * nchunk + q]);
-            a += t.x;
-            b += t.y;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-        }
+        T a = Sc<T>::zero();
+        for (int q = threadIdx.x; q < nchunk; q += 32) a = Sc<T>::add(a, __ldcg(&part[(size_t)j * nchunk + q]));
+        a = warp_sum_t(a);
         if (threadIdx.x == 0) {
-            y[j] = make_double2(a, b);
+            y[j] = a;
             tickets[j] = 0u;
         }
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-axpy_multi_kernel(const cplx* __restrict__ V, long long ldv, int m, long long n, const cplx* __restrict__ c,
-                  double sign, cplx* __restrict__ w, BlasBatch bb) {
+axpy_multi_kernel(const T* __restrict__ V, long long ldv, int m, long long n, const T* __restrict__ c,
+                  double sign, T* __restrict__ w, BlasBatch bb) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     V += (size_t)blockIdx.y * bb.sV; w += (size_t)blockIdx.y * bb.sw; c += (size_t)blockIdx.y * bb.sc;
-    cplx acc = w[i];
-    for (int j = 0; j < m; ++j) {
-        cplx cj = c[j];
-        cj.x *= sign;
-        cj.y *= sign;
-        const cplx v = V[(size_t)j * ldv + i];
-        acc.x = fma(cj.x, v.x, fma(-cj.y, v.y, acc.x));
-        acc.y = fma(cj.x, v.y, fma(cj.y, v.x, acc.y));
-    }
+    T acc = w[i];
+    for (int j = 0; j < m; ++j) Sc<T>::mac(acc, Sc<T>::scale(c[j], sign), V[(size_t)j * ldv + i]);
     w[i] = acc;
 }
 
-// w *= 1/sqrt(nrm2[0].x); a vanishing norm (Lanczos breakdown) zeroes the vector instead of producing NaNs
-__global__ void __launch_bounds__(256) normalise_kernel(long long n, const cplx* __restrict__ nrm2, cplx* __restrict__ w,
+// w *= 1/sqrt(re(nrm2[0])); a vanishing norm (Lanczos breakdown) zeroes the vector instead of producing NaNs
+template <typename T>
+__global__ void __launch_bounds__(256) normalise_kernel(long long n, const T* __restrict__ nrm2, T* __restrict__ w,
                                                         BlasBatch bb) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     nrm2 += (size_t)blockIdx.y * bb.sc; w += (size_t)blockIdx.y * bb.sw;
-    const double v2 = nrm2[0].x;
+    const double v2 = Sc<T>::re(nrm2[0]);
     const double sc = v2 > 0.0 ? rsqrt(v2) : 0.0;
-    cplx v = w[i];
-    v.x *= sc;
-    v.y *= sc;
-    w[i] = v;
+    w[i] = Sc<T>::scale(w[i], sc);
 }
 
 __global__ void __launch_bounds__(256) dscal_kernel(long long n, double alpha, cplx* __restrict__ w) {
@@ -171,15 +156,24 @@ int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, c
     return 0;
 }
 
-int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st,
-                   int batch, long long s_in, long long s_out) {
+template <typename T>
+static int transpose_t(const T* in, int ldi, int rows, int cols, T* out, int ldo, int conj, cudaStream_t st,
+                       int batch, long long s_in, long long s_out) {
     if (rows == 0 || cols == 0) return 0;
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
     MPSB_REQUIRE(grid.y <= 65535 && batch >= 1 && batch <= 65535, "transpose: %d rows / batch %d exceed the grid", rows, batch);
-    transpose_kernel<<<grid, 256, 0, st>>>(in, ldi, rows, cols, out, ldo, conj, s_in, s_out);
+    transpose_kernel<T><<<grid, 256, 0, st>>>(in, ldi, rows, cols, out, ldo, conj, s_in, s_out);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st,
+                   int batch, long long s_in, long long s_out) {
+    return transpose_t(in, ldi, rows, cols, out, ldo, conj, st, batch, s_in, s_out);
+}
+int transpose_conj(const double* in, int ldi, int rows, int cols, double* out, int ldo, int conj, cudaStream_t st,
+                   int batch, long long s_in, long long s_out) {
+    return transpose_t(in, ldi, rows, cols, out, ldo, conj, st, batch, s_in, s_out);
 }
 
 // out[i][j] = s[i / group] * in[i][j]: the Lambda_l scaling of a (chi_l * group) x cols matrix view (DMRG/MPS.py:446).
@@ -212,36 +206,57 @@ int perm_first_to_last(const cplx* in, int n_c, int n_ab, cplx* out, cudaStream_
     return transpose_conj(in, n_ab, n_c, n_ab, out, n_c, 0, st);
 }
 
-int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
-                int m_cap, cudaStream_t st, BlasBatch bb) {
+template <typename T>
+static int dotc_t(const T* V, long long ldv, int m, long long n, const T* w, T* y, T* part, int nchunk, int m_cap,
+                  cudaStream_t st, BlasBatch bb) {
     if (m == 0) return 0;
     MPSB_REQUIRE(m <= 65535 && m <= m_cap && nchunk >= 1 && bb.batch >= 1 && bb.batch <= 65535,
                  "zdotc_multi: bad m=%d (cap %d) nchunk=%d batch=%d", m, m_cap, nchunk, bb.batch);
     dim3 grid(nchunk, m, bb.batch);
-    dot_fused_kernel<<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk, m_cap, y, bb);
+    dot_fused_kernel<T><<<grid, DOT_THREADS, 0, st>>>(V, ldv, n, w, part, nchunk, m_cap, y, bb);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
+                int m_cap, cudaStream_t st, BlasBatch bb) {
+    return dotc_t(V, ldv, m, n, w, y, part, nchunk, m_cap, st, bb);
+}
+int zdotc_multi(const double* V, long long ldv, int m, long long n, const double* w, double* y, double* part, int nchunk,
+                int m_cap, cudaStream_t st, BlasBatch bb) {
+    return dotc_t(V, ldv, m, n, w, y, part, nchunk, m_cap, st, bb);
+}
 
-int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
-                cudaStream_t st, BlasBatch bb) {
+template <typename T>
+static int axpy_t(const T* V, long long ldv, int m, long long n, const T* c, double sign, T* w, cudaStream_t st,
+                  BlasBatch bb) {
     if (m == 0 || n == 0) return 0;
     dim3 grid((unsigned)((n + 255) / 256), bb.batch);
-    axpy_multi_kernel<<<grid, 256, 0, st>>>(V, ldv, m, n, c, sign, w, bb);
+    axpy_multi_kernel<T><<<grid, 256, 0, st>>>(V, ldv, m, n, c, sign, w, bb);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
+                cudaStream_t st, BlasBatch bb) {
+    return axpy_t(V, ldv, m, n, c, sign, w, st, bb);
+}
+int zaxpy_multi(const double* V, long long ldv, int m, long long n, const double* c, double sign, double* w,
+                cudaStream_t st, BlasBatch bb) {
+    return axpy_t(V, ldv, m, n, c, sign, w, st, bb);
 }
 
-int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st, BlasBatch bb) {
+template <typename T>
+static int normalise_t(long long n, const T* nrm2, T* w, cudaStream_t st, BlasBatch bb) {
     if (n == 0) return 0;
     dim3 grid((unsigned)((n + 255) / 256), bb.batch);
-    normalise_kernel<<<grid, 256, 0, st>>>(n, nrm2, w, bb);
+    normalise_kernel<T><<<grid, 256, 0, st>>>(n, nrm2, w, bb);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st, BlasBatch bb) { return normalise_t(n, nrm2, w, st, bb); }
+int znormalise(long long n, const double* nrm2, double* w, cudaStream_t st, BlasBatch bb) { return normalise_t(n, nrm2, w, st, bb); }
 
 int zdscal(long long n, double alpha, cplx* w, cudaStream_t st) {
     if (n == 0) return 0;

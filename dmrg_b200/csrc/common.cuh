@@ -142,6 +142,38 @@ __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); 
 __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {  // a*b + c
     return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
+
+// Scalar traits: the iDMRG kernels are written once for complex128 (cplx) and for real doubles - the reference's
+// real path, MPO.tomatrix(dtype='double'), DMRG/MPO.py:68-76.
+template <typename T> struct Sc;
+template <> struct Sc<cplx> {
+    static __host__ __device__ __forceinline__ cplx zero() { return make_double2(0.0, 0.0); }
+    static __host__ __device__ __forceinline__ cplx from_re(double v) { return make_double2(v, 0.0); }
+    static __host__ __device__ __forceinline__ double re(cplx a) { return a.x; }
+    static __device__ __forceinline__ bool is_zero(cplx g) { return g.x == 0.0 && g.y == 0.0; }
+    static __device__ __forceinline__ void mac(cplx& acc, cplx g, cplx x) {          // acc += g x
+        acc.x = fma(g.x, x.x, fma(-g.y, x.y, acc.x));
+        acc.y = fma(g.x, x.y, fma(g.y, x.x, acc.y));
+    }
+    static __device__ __forceinline__ void macc(cplx& acc, cplx a, cplx b) {         // acc += conj(a) b
+        acc.x = fma(a.x, b.x, fma(a.y, b.y, acc.x));
+        acc.y = fma(a.x, b.y, fma(-a.y, b.x, acc.y));
+    }
+    static __device__ __forceinline__ cplx add(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+    static __device__ __forceinline__ cplx scale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+    static __device__ __forceinline__ cplx conj(cplx a) { return make_double2(a.x, -a.y); }
+};
+template <> struct Sc<double> {
+    static __host__ __device__ __forceinline__ double zero() { return 0.0; }
+    static __host__ __device__ __forceinline__ double from_re(double v) { return v; }
+    static __host__ __device__ __forceinline__ double re(double a) { return a; }
+    static __device__ __forceinline__ bool is_zero(double g) { return g == 0.0; }
+    static __device__ __forceinline__ void mac(double& acc, double g, double x) { acc = fma(g, x, acc); }
+    static __device__ __forceinline__ void macc(double& acc, double a, double b) { acc = fma(a, b, acc); }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double scale(double a, double s) { return a * s; }
+    static __device__ __forceinline__ double conj(double a) { return a; }
+};
 #endif  // __CUDACC__
 
 }  // namespace mpsb

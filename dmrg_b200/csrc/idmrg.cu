@@ -25,7 +25,8 @@ namespace {
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 // WW[i][k][B][C][b][c] = sum_j W[i][j][B][b] W[j][k][C][c]
-__global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, long long sW, cplx* __restrict__ WW) {
+template <typename T>
+__global__ void ww_build_kernel(int w, int d, const T* __restrict__ W, long long sW, T* __restrict__ WW) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = w * w * d * d * d * d;
     if (e >= total) return;
@@ -38,24 +39,20 @@ __global__ void ww_build_kernel(int w, int d, const cplx* __restrict__ W, long l
     const int B = r % d; r /= d;
     const int k = r % w;
     const int i = r / w;
-    double re = 0.0, im = 0.0;
-    for (int j = 0; j < w; ++j) {
-        const cplx x = W[((size_t)(i * w + j) * d + B) * d + b];
-        const cplx y = W[((size_t)(j * w + k) * d + C) * d + c];
-        re += x.x * y.x - x.y * y.y;
-        im += x.x * y.y + x.y * y.x;
-    }
-    WW[e] = make_double2(re, im);
+    T acc = Sc<T>::zero();
+    for (int j = 0; j < w; ++j)
+        Sc<T>::mac(acc, W[((size_t)(i * w + j) * d + B) * d + b], W[((size_t)(j * w + k) * d + C) * d + c]);
+    WW[e] = acc;
 }
 
 // T3[A][B][C][dr][k] = sum_{i,b,c} WW[i][k][B][C][b][c] T1[i][A][b][c][dr]
 // One thread per (A, dr): it reads its w d^2 inputs once and produces all d^2 w outputs (instantiated for d = 2 with
 // w = 3 and w = 5; other MPOs take one (B, C) per thread, below), so T1 and T3 cross the memory system exactly once.  Zero blocks of
 // the (lower-triangular, mostly empty) MPO are skipped; the test is uniform across the warp.
-template <int W, int D>
+template <typename T, int W, int D>
 __global__ void __launch_bounds__(128)
-ww_apply_fused_kernel(int chil, int chir, const cplx* __restrict__ WW, long long sWW, const cplx* __restrict__ T1,
-                      cplx* __restrict__ T3) {
+ww_apply_fused_kernel(int chil, int chir, const T* __restrict__ WW, long long sWW, const T* __restrict__ T1,
+                      T* __restrict__ T3) {
     constexpr int DD = D * D;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)chil * chir;
@@ -65,7 +62,7 @@ ww_apply_fused_kernel(int chil, int chir, const cplx* __restrict__ WW, long long
     T1 += (size_t)blockIdx.y * per_chain;
     T3 += (size_t)blockIdx.y * per_chain;
     const int dr = (int)(e % chir), A = (int)(e / chir);
-    cplx x[W][DD];
+    T x[W][DD];
     const size_t t1_row = (size_t)DD * chir;             // elements per (i, A)
 #pragma unroll
     for (int i = 0; i < W; ++i)
@@ -73,30 +70,30 @@ ww_apply_fused_kernel(int chil, int chir, const cplx* __restrict__ WW, long long
         for (int bc = 0; bc < DD; ++bc) x[i][bc] = T1[((size_t)i * chil + A) * t1_row + (size_t)bc * chir + dr];
 #pragma unroll
     for (int BC = 0; BC < DD; ++BC) {
-        cplx* out = T3 + (((size_t)A * DD + BC) * chir + dr) * W;
+        T* out = T3 + (((size_t)A * DD + BC) * chir + dr) * W;
 #pragma unroll
         for (int k = 0; k < W; ++k) {
-            double re = 0.0, im = 0.0;
+            T acc = Sc<T>::zero();
 #pragma unroll
             for (int i = 0; i < W; ++i) {
-                const cplx* g0 = WW + (((size_t)i * W + k) * DD + BC) * DD;
+                const T* g0 = WW + (((size_t)i * W + k) * DD + BC) * DD;
 #pragma unroll
                 for (int bc = 0; bc < DD; ++bc) {
-                    const cplx g = g0[bc];
-                    if (g.x == 0.0 && g.y == 0.0) continue;
-                    re = fma(g.x, x[i][bc].x, fma(-g.y, x[i][bc].y, re));
-                    im = fma(g.x, x[i][bc].y, fma(g.y, x[i][bc].x, im));
+                    const T g = g0[bc];
+                    if (Sc<T>::is_zero(g)) continue;
+                    Sc<T>::mac(acc, g, x[i][bc]);
                 }
             }
-            out[k] = make_double2(re, im);
+            out[k] = acc;
         }
     }
 }
 
 // General form: one thread per (A, B, C, dr) producing the w values of k (contiguous store).
+template <typename T>
 __global__ void __launch_bounds__(256)
-ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, long long sWW,
-                const cplx* __restrict__ T1, cplx* __restrict__ T3) {
+ww_apply_kernel(int chil, int chir, int d, int w, const T* __restrict__ WW, long long sWW,
+                const T* __restrict__ T1, T* __restrict__ T3) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)chil * d * d * chir;
     if (e >= total) return;
@@ -110,28 +107,27 @@ ww_apply_kernel(int chil, int chir, int d, int w, const cplx* __restrict__ WW, l
     const int A = (int)(r / d);
     const size_t t1_row = (size_t)d * d * chir;          // elements per (i, A)
     for (int k = 0; k < w; ++k) {
-        double re = 0.0, im = 0.0;
+        T acc = Sc<T>::zero();
         for (int i = 0; i < w; ++i) {
-            const cplx* t1 = T1 + ((size_t)i * chil + A) * t1_row + dr;
-            const cplx* g0 = WW + ((((size_t)i * w + k) * d + B) * d + C) * d * d;
+            const T* t1 = T1 + ((size_t)i * chil + A) * t1_row + dr;
+            const T* g0 = WW + ((((size_t)i * w + k) * d + B) * d + C) * d * d;
             for (int b = 0; b < d; ++b)
                 for (int c = 0; c < d; ++c) {
-                    const cplx g = g0[b * d + c];
-                    if (g.x == 0.0 && g.y == 0.0) continue;
-                    const cplx x = t1[(size_t)(b * d + c) * chir];
-                    re = fma(g.x, x.x, fma(-g.y, x.y, re));
-                    im = fma(g.x, x.y, fma(g.y, x.x, im));
+                    const T g = g0[b * d + c];
+                    if (Sc<T>::is_zero(g)) continue;
+                    Sc<T>::mac(acc, g, t1[(size_t)(b * d + c) * chir]);
                 }
         }
-        T3[(size_t)e * w + k] = make_double2(re, im);
+        T3[(size_t)e * w + k] = acc;
     }
 }
 
 // Left environment:  T2[C][i][l][B] = sum_{k,m} W[k][C][l][m] T1[k][i][m][B]
 // Right environment: T2[C][l][i][B] = sum_{k,m} W[C][k][l][m] T1[k][i][B][m]
+template <typename T>
 __global__ void __launch_bounds__(256)
-env_w_kernel(int right, int chi, int chin, int d, int w, const cplx* __restrict__ W, long long sW,
-             const cplx* __restrict__ T1, cplx* __restrict__ T2) {
+env_w_kernel(int right, int chi, int chin, int d, int w, const T* __restrict__ W, long long sW,
+             const T* __restrict__ T1, T* __restrict__ T2) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)w * chi * d * chin;
     if (e >= total) return;
@@ -144,35 +140,35 @@ env_w_kernel(int right, int chi, int chin, int d, int w, const cplx* __restrict_
     if (!right) { l = (int)(r % d); r /= d; i = (int)(r % chi); r /= chi; }
     else        { i = (int)(r % chi); r /= chi; l = (int)(r % d); r /= d; }
     const int C = (int)r;
-    double re = 0.0, im = 0.0;
+    T acc = Sc<T>::zero();
     for (int k = 0; k < w; ++k)
         for (int m = 0; m < d; ++m) {
-            const cplx g = right ? W[((size_t)(C * w + k) * d + l) * d + m] : W[((size_t)(k * w + C) * d + l) * d + m];
-            if (g.x == 0.0 && g.y == 0.0) continue;
-            const cplx x = right ? T1[(((size_t)k * chi + i) * chin + B) * d + m]
-                                 : T1[(((size_t)k * chi + i) * d + m) * chin + B];
-            re = fma(g.x, x.x, fma(-g.y, x.y, re));
-            im = fma(g.x, x.y, fma(g.y, x.x, im));
+            const T g = right ? W[((size_t)(C * w + k) * d + l) * d + m] : W[((size_t)(k * w + C) * d + l) * d + m];
+            if (Sc<T>::is_zero(g)) continue;
+            Sc<T>::mac(acc, g, right ? T1[(((size_t)k * chi + i) * chin + B) * d + m]
+                                     : T1[(((size_t)k * chi + i) * d + m) * chin + B]);
         }
-    T2[e] = make_double2(re, im);
+    T2[e] = acc;
 }
 
+template <typename T>
 struct Heff {
     int chil, chir, d, w;
     int batch;          // independent chains, every tensor below has a leading chain index
-    const cplx* R;      // as given: [D][dr][k]
+    const T* R;         // as given: [D][dr][k]
     long long sR;       // chain stride of R
     long long sWW;      // chain stride of WW (0: one MPO shared by all chains)
-    cplx *Lt, *WW, *T1, *T3;
+    T *Lt, *WW, *T1, *T3;
     size_t n;           // chil*d*d*chir
 };
 // Wavefunction prediction (new; no counterpart in the reference, which restarts ARPACK from a random vector):
 //   XL[a,s,c] = S[a] B[a,s,c] Sinv[c]        XR[c,t,b] = A[c,t,b] S[b]
 // so that theta_trial[a,s,t,b] = sum_c XL[a,s,c] XR[c,t,b] = (S B) Sprev^-1 (A S).  Element-wise, HBM-bound.
+template <typename T>
 __global__ void __launch_bounds__(256)
-predict_scale_kernel(int chi, int chip, int d, const cplx* __restrict__ B, const cplx* __restrict__ A,
-                     const double* __restrict__ S, const double* __restrict__ Sinv, cplx* __restrict__ XL,
-                     cplx* __restrict__ XR) {
+predict_scale_kernel(int chi, int chip, int d, const T* __restrict__ B, const T* __restrict__ A,
+                     const double* __restrict__ S, const double* __restrict__ Sinv, T* __restrict__ XL,
+                     T* __restrict__ XR) {
     const long long total = (long long)chi * d * chip;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -182,65 +178,63 @@ predict_scale_kernel(int chi, int chip, int d, const cplx* __restrict__ B, const
     {   // B[a][s][c]
         const int c = (int)(e % chip);
         const int a = (int)(e / ((long long)d * chip));
-        const double f = S[a] * Sinv[c];
-        const cplx x = B[e];
-        XL[e] = make_double2(f * x.x, f * x.y);
+        XL[e] = Sc<T>::scale(B[e], S[a] * Sinv[c]);
     }
     {   // A[c][t][b]
         const int b = (int)(e % chi);
-        const double f = S[b];
-        const cplx x = A[e];
-        XR[e] = make_double2(f * x.x, f * x.y);
+        XR[e] = Sc<T>::scale(A[e], S[b]);
     }
 }
 
-size_t heff_bytes(int chil, int chir, int d, int w, int batch = 1) {
+size_t heff_bytes(int chil, int chir, int d, int w, int batch = 1, size_t esz = sizeof(cplx)) {
     const size_t n = (size_t)chil * d * d * chir;
-    return al((size_t)batch * w * chil * chil * sizeof(cplx)) + al((size_t)batch * w * w * d * d * d * d * sizeof(cplx)) +
-           al((size_t)batch * n * w * sizeof(cplx)) * 2;
+    return al((size_t)batch * w * chil * chil * esz) + al((size_t)batch * w * w * d * d * d * d * esz) +
+           al((size_t)batch * n * w * esz) * 2;
 }
 // L, R: one environment per chain (strides sL, sR in elements); W: one MPO per chain (sW) or a shared one (sW = 0).
-int heff_prepare(Heff& h, int chil, int chir, int d, int w, const cplx* L, const cplx* W, const cplx* R, void* ws,
+template <typename T>
+int heff_prepare(Heff<T>& h, int chil, int chir, int d, int w, const T* L, const T* W, const T* R, void* ws,
                  cudaStream_t st, int batch = 1, long long sL = 0, long long sW = 0, long long sR = 0) {
     h.chil = chil; h.chir = chir; h.d = d; h.w = w; h.R = R; h.batch = batch; h.sR = sR;
     h.n = (size_t)chil * d * d * chir;
     const int ww = w * w * d * d * d * d;
     unsigned char* p = static_cast<unsigned char*>(ws);
-    h.Lt = reinterpret_cast<cplx*>(p); p += al((size_t)batch * w * chil * chil * sizeof(cplx));
-    h.WW = reinterpret_cast<cplx*>(p); p += al((size_t)batch * ww * sizeof(cplx));
-    h.T1 = reinterpret_cast<cplx*>(p); p += al((size_t)batch * h.n * w * sizeof(cplx));
-    h.T3 = reinterpret_cast<cplx*>(p);
+    h.Lt = reinterpret_cast<T*>(p); p += al((size_t)batch * w * chil * chil * sizeof(T));
+    h.WW = reinterpret_cast<T*>(p); p += al((size_t)batch * ww * sizeof(T));
+    h.T1 = reinterpret_cast<T*>(p); p += al((size_t)batch * h.n * w * sizeof(T));
+    h.T3 = reinterpret_cast<T*>(p);
     // Lt[i][A][a] = L[A][a][i]
     int rc = transpose_conj(L, w, chil * chil, w, h.Lt, chil * chil, 0, st, batch, sL, (long long)w * chil * chil);
     if (rc) return rc;
     const int nww = (sW == 0) ? 1 : batch;
     h.sWW = (sW == 0) ? 0 : ww;
     dim3 grid((ww + 127) / 128, nww);
-    ww_build_kernel<<<grid, 128, 0, st>>>(w, d, W, sW, h.WW);
+    ww_build_kernel<T><<<grid, 128, 0, st>>>(w, d, W, sW, h.WW);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 // theta / out: [batch][n] with chain strides s_theta / s_out
-int heff_apply(const Heff& h, const cplx* theta, cplx* out, cudaStream_t st, long long s_theta = 0, long long s_out = 0) {
+template <typename T>
+int heff_apply(const Heff<T>& h, const T* theta, T* out, cudaStream_t st, long long s_theta = 0, long long s_out = 0) {
     const int ncol = h.d * h.d * h.chir;
-    GemmArgs g;
+    GemmArgsT<T> g;
     // T1[(i,A)][(b,c,dr)] = sum_a Lt[(i,A)][a] theta[a][(b,c,dr)]
     g.A = h.Lt; g.B = theta; g.C = h.T1;
     g.M = h.w * h.chil; g.N = ncol; g.K = h.chil; g.lda = h.chil; g.ldb = ncol; g.ldc = ncol; g.opA = 0; g.opB = 0;
     g.batch1 = h.batch; g.batch2 = 1;
     g.sA1 = (long long)h.w * h.chil * h.chil; g.sB1 = s_theta; g.sC1 = (long long)h.n * h.w;
     g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
-    int rc = zgemm(g, st);
+    int rc = gemm(g, st);
     if (rc) return rc;
     dim3 fgrid((unsigned)(((long long)h.chil * h.chir + 127) / 128), h.batch);
     if (h.d == 2 && h.w == 3) {            // TFIM-like MPOs: the inputs of a thread fit its registers
-        ww_apply_fused_kernel<3, 2><<<fgrid, 128, 0, st>>>(h.chil, h.chir, h.WW, h.sWW, h.T1, h.T3);
+        ww_apply_fused_kernel<T, 3, 2><<<fgrid, 128, 0, st>>>(h.chil, h.chir, h.WW, h.sWW, h.T1, h.T3);
     } else if (h.d == 2 && h.w == 5) {     // Heisenberg / XXZ
-        ww_apply_fused_kernel<5, 2><<<fgrid, 128, 0, st>>>(h.chil, h.chir, h.WW, h.sWW, h.T1, h.T3);
+        ww_apply_fused_kernel<T, 5, 2><<<fgrid, 128, 0, st>>>(h.chil, h.chir, h.WW, h.sWW, h.T1, h.T3);
     } else {
         dim3 grid((unsigned)((h.n + 255) / 256), h.batch);
-        ww_apply_kernel<<<grid, 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.sWW, h.T1, h.T3);
+        ww_apply_kernel<T><<<grid, 256, 0, st>>>(h.chil, h.chir, h.d, h.w, h.WW, h.sWW, h.T1, h.T3);
     }
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
@@ -249,7 +243,7 @@ int heff_apply(const Heff& h, const cplx* theta, cplx* out, cudaStream_t st, lon
     g.M = h.chil * h.d * h.d; g.N = h.chir; g.K = h.chir * h.w; g.lda = g.K; g.ldb = g.K; g.ldc = h.chir;
     g.opA = 0; g.opB = 1;
     g.sA1 = (long long)h.n * h.w; g.sB1 = h.sR; g.sC1 = s_out;
-    return zgemm(g, st);
+    return gemm(g, st);
 }
 
 // Symmetric eigenproblem of a small dense real matrix by cyclic Jacobi (host; m <= a few dozen).
@@ -287,50 +281,33 @@ void sym_eig_host(int m, std::vector<double>& a, std::vector<double>& v) {
     }
 }
 
-}  // namespace
-}  // namespace mpsb
 
-using namespace mpsb;
-
-extern "C" {
-
-size_t mpsb_heff_batched_workspace(int batch, int chil, int chir, int d, int w) {
-    return heff_bytes(chil, chir, d, w, batch);
-}
-size_t mpsb_heff_workspace(int chil, int chir, int d, int w) { return heff_bytes(chil, chir, d, w); }
-
-int mpsb_heff_matvec_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
-                             long long sW, const void* R, long long sR, const void* theta, long long s_theta, void* out,
-                             long long s_out, void* ws, size_t ws_bytes, void* stream) {
+template <typename T>
+int heff_matvec_impl(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                     long long sW, const void* R, long long sR, const void* theta, long long s_theta, void* out,
+                     long long s_out, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MPSB_REQUIRE(batch >= 1 && chil >= 1 && chir >= 1 && d >= 1 && w >= 1, "heff_matvec: bad dims");
-    const size_t need = heff_bytes(chil, chir, d, w, batch);
+    const size_t need = heff_bytes(chil, chir, d, w, batch, sizeof(T));
     MPSB_REQUIRE(ws && ws_bytes >= need, "heff_matvec: workspace %zu B < required %zu B", ws_bytes, need);
-    Heff h;
-    int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
-                          static_cast<const cplx*>(R), ws, st, batch, sL, sW, sR);
+    Heff<T> h;
+    int rc = heff_prepare<T>(h, chil, chir, d, w, static_cast<const T*>(L), static_cast<const T*>(W),
+                             static_cast<const T*>(R), ws, st, batch, sL, sW, sR);
     if (rc) return rc;
-    return heff_apply(h, static_cast<const cplx*>(theta), static_cast<cplx*>(out), st, s_theta, s_out);
+    return heff_apply<T>(h, static_cast<const T*>(theta), static_cast<T*>(out), st, s_theta, s_out);
 }
 
-int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
-                     void* out, void* ws, size_t ws_bytes, void* stream) {
-    return mpsb_heff_matvec_batched(1, chil, chir, d, w, L, 0, W, 0, R, 0, theta, 0, out, 0, ws, ws_bytes, stream);
-}
 
 constexpr int LANCZOS_KEEP = 8;        // Ritz vectors carried across a (thick) restart
 constexpr int LANCZOS_NCHUNK = 64;
 
-size_t mpsb_lanczos_batched_workspace(int batch, int chil, int chir, int d, int w, int krylov) {
+size_t lanczos_bytes(int batch, int chil, int chir, int d, int w, int krylov, size_t esz) {
     const size_t n = (size_t)chil * d * d * chir;
     const size_t kk = (size_t)krylov + 2;
     const size_t b = (size_t)batch;
-    return heff_bytes(chil, chir, d, w, batch) + b * al(n * sizeof(cplx)) * (kk + LANCZOS_KEEP) +
-           al(b * kk * (LANCZOS_NCHUNK + 1) * sizeof(cplx)) + al(b * kk * kk * sizeof(cplx)) * 2 + al(b * kk * sizeof(cplx)) +
-           al(b * kk * LANCZOS_KEEP * sizeof(cplx));
-}
-size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
-    return mpsb_lanczos_batched_workspace(1, chil, chir, d, w, krylov);
+    return heff_bytes(chil, chir, d, w, batch, esz) + b * al(n * esz) * (kk + LANCZOS_KEEP) +
+           al(b * kk * (LANCZOS_NCHUNK + 1) * esz) + al(b * kk * kk * esz) * 2 + al(b * kk * esz) +
+           al(b * kk * LANCZOS_KEEP * esz);
 }
 
 // Thick-restart Lanczos with full (twice-applied) reorthogonalisation for `batch` independent chains in lock step
@@ -347,14 +324,15 @@ size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
 //  * A chain that has converged (or whose Krylov space closed) has its Ritz vector copied to theta and is FROZEN: it
 //    keeps riding along in the batched launches, its later numbers are ignored.  The call ends when every chain is
 //    frozen or max_restarts is reached.
-int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
-                                long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
-                                int max_restarts, double tol, double* energy_host, double* resid_host, int* n_matvec_host,
-                                void* ws, size_t ws_bytes, void* stream) {
+template <typename T>
+int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                 long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
+                 int max_restarts, double tol, double* energy_host, double* resid_host, int* n_matvec_host,
+                 void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MPSB_REQUIRE(batch >= 1 && chil >= 1 && chir >= 1 && d >= 1 && w >= 1 && krylov >= 2 && max_restarts >= 1,
                  "lanczos_ground: bad arguments");
-    const size_t need = mpsb_lanczos_batched_workspace(batch, chil, chir, d, w, krylov);
+    const size_t need = lanczos_bytes(batch, chil, chir, d, w, krylov, sizeof(T));
     MPSB_REQUIRE(ws && ws_bytes >= need, "lanczos_ground: workspace %zu B < required %zu B", ws_bytes, need);
     const size_t n = (size_t)chil * d * d * chir;
     const int nchunk = LANCZOS_NCHUNK;
@@ -363,30 +341,30 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
     const size_t kk = (size_t)krylov + 2;
     const size_t nb = (size_t)batch;
     unsigned char* p = static_cast<unsigned char*>(ws);
-    Heff h;
-    int rc = heff_prepare(h, chil, chir, d, w, static_cast<const cplx*>(L), static_cast<const cplx*>(W),
-                          static_cast<const cplx*>(R), p, st, batch, sL, sW, sR);
+    Heff<T> h;
+    int rc = heff_prepare<T>(h, chil, chir, d, w, static_cast<const T*>(L), static_cast<const T*>(W),
+                             static_cast<const T*>(R), p, st, batch, sL, sW, sR);
     if (rc) return rc;
-    p += heff_bytes(chil, chir, d, w, batch);
-    const size_t vstride = al(n * sizeof(cplx)) / sizeof(cplx);
+    p += heff_bytes(chil, chir, d, w, batch, sizeof(T));
+    const size_t vstride = al(n * sizeof(T)) / sizeof(T);
     const long long sV = (long long)(vstride * kk), sVk = (long long)(vstride * LANCZOS_KEEP);
     const long long sPart = (long long)(kk * (nchunk + 1)), sC = (long long)(kk * kk), sN = (long long)kk,
                     sY = (long long)(kk * LANCZOS_KEEP);
-    cplx* V = reinterpret_cast<cplx*>(p);                 p += nb * al(n * sizeof(cplx)) * kk;             // [chain][kk][vstride]
-    cplx* Vk = reinterpret_cast<cplx*>(p);                p += nb * al(n * sizeof(cplx)) * LANCZOS_KEEP;   // Ritz vectors
-    cplx* part = reinterpret_cast<cplx*>(p);              p += al(nb * kk * (nchunk + 1) * sizeof(cplx));   // partials + tickets
-    cplx* C1 = reinterpret_cast<cplx*>(p);                p += al(nb * kk * kk * sizeof(cplx));   // pass-1 coefficients, row j
-    cplx* C2 = reinterpret_cast<cplx*>(p);                p += al(nb * kk * kk * sizeof(cplx));   // pass-2 coefficients
-    cplx* N2 = reinterpret_cast<cplx*>(p);                p += al(nb * kk * sizeof(cplx));        // ||w_j||^2
-    cplx* Yd = reinterpret_cast<cplx*>(p);                                                          // [chain][keep][kk]
-    cplx* th = static_cast<cplx*>(theta);
+    T* V = reinterpret_cast<T*>(p);                 p += nb * al(n * sizeof(T)) * kk;             // [chain][kk][vstride]
+    T* Vk = reinterpret_cast<T*>(p);                p += nb * al(n * sizeof(T)) * LANCZOS_KEEP;   // Ritz vectors
+    T* part = reinterpret_cast<T*>(p);              p += al(nb * kk * (nchunk + 1) * sizeof(T));   // partials + tickets
+    T* C1 = reinterpret_cast<T*>(p);                p += al(nb * kk * kk * sizeof(T));   // pass-1 coefficients, row j
+    T* C2 = reinterpret_cast<T*>(p);                p += al(nb * kk * kk * sizeof(T));   // pass-2 coefficients
+    T* N2 = reinterpret_cast<T*>(p);                p += al(nb * kk * sizeof(T));        // ||w_j||^2
+    T* Yd = reinterpret_cast<T*>(p);                                                          // [chain][keep][kk]
+    T* th = static_cast<T*>(theta);
     auto bat = [&](long long sv, long long sw, long long sc) {
         BlasBatch b;
         b.batch = batch; b.sV = sv; b.sw = sw; b.sc = sc; b.spart = sPart;
         return b;
     };
     struct Chain {
-        std::vector<double> Hp, T, Y;
+        std::vector<double> Hp, Tm, Y;
         std::vector<int> idx;
         double E = 0.0, resid = 0.0, beta_last = 0.0;
         int mm = 0;
@@ -394,21 +372,21 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
     };
     std::vector<Chain> ch(nb);
     for (auto& c : ch) c.Hp.assign((size_t)m * m, 0.0);
-    std::vector<cplx> h1(nb * kk * kk), h2(nb * kk * kk), hn(nb * kk), hc(nb * kk * LANCZOS_KEEP);
+    std::vector<T> h1(nb * kk * kk), h2(nb * kk * kk), hn(nb * kk), hc(nb * kk * LANCZOS_KEEP);
     int n_mv = 0;
 
-    MPSB_CHECK_CUDA(cudaMemsetAsync(part, 0, al(nb * kk * (nchunk + 1) * sizeof(cplx)), st));
+    MPSB_CHECK_CUDA(cudaMemsetAsync(part, 0, al(nb * kk * (nchunk + 1) * sizeof(T)), st));
     // normalise the start vectors into V[chain][0]
     rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st, bat(s_theta, s_theta, sN));
     if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(cplx), N2, kk * sizeof(cplx), sizeof(cplx), nb,
+    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(T), N2, kk * sizeof(T), sizeof(T), nb,
                                       cudaMemcpyDeviceToHost, st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
     for (size_t c = 0; c < nb; ++c)
-        MPSB_REQUIRE(hn[c * kk].x > 0.0 && std::isfinite(hn[c * kk].x), "lanczos_ground: start vector of chain %zu has norm^2 = %g",
-                     c, hn[c * kk].x);
-    if (batch == 1) MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-    else MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(cplx), th, (size_t)s_theta * sizeof(cplx), n * sizeof(cplx), nb,
+        MPSB_REQUIRE(Sc<T>::re(hn[c * kk]) > 0.0 && std::isfinite(Sc<T>::re(hn[c * kk])), "lanczos_ground: start vector of chain %zu has norm^2 = %g",
+                     c, Sc<T>::re(hn[c * kk]));
+    if (batch == 1) MPSB_CHECK_CUDA(cudaMemcpyAsync(V, th, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    else MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(T), th, (size_t)s_theta * sizeof(T), n * sizeof(T), nb,
                                            cudaMemcpyDeviceToDevice, st));
     rc = znormalise((long long)n, N2, V, st, bat(0, sV, sN));
     if (rc) return rc;
@@ -428,11 +406,11 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
     // Ritz data of the bases V[chain][0 .. formed): per live chain T (eigenvalues on the diagonal), Y, idx (ascending),
     // E, resid, mm.
     auto evaluate = [&](int formed) -> int {
-        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h1.data(), kk * kk * sizeof(cplx), C1, kk * kk * sizeof(cplx),
-                                          sizeof(cplx) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h2.data(), kk * kk * sizeof(cplx), C2, kk * kk * sizeof(cplx),
-                                          sizeof(cplx) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(cplx), N2, kk * sizeof(cplx), sizeof(cplx) * formed, nb,
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h1.data(), kk * kk * sizeof(T), C1, kk * kk * sizeof(T),
+                                          sizeof(T) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h2.data(), kk * kk * sizeof(T), C2, kk * kk * sizeof(T),
+                                          sizeof(T) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(T), N2, kk * sizeof(T), sizeof(T) * formed, nb,
                                           cudaMemcpyDeviceToHost, st));
         auto tb = now();
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -441,35 +419,35 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         auto solve_chain = [&](size_t ci) {
             Chain& c = ch[ci];
             if (c.frozen) return;
-            const cplx* a1 = h1.data() + ci * kk * kk;
-            const cplx* a2 = h2.data() + ci * kk * kk;
-            const cplx* an = hn.data() + ci * kk;
+            const T* a1 = h1.data() + ci * kk * kk;
+            const T* a2 = h2.data() + ci * kk * kk;
+            const T* an = hn.data() + ci * kk;
             c.mm = formed;
             c.beta_last = 0.0;
             double hscale = 0.0;                      // largest |h_ij| seen: scale of the breakdown test
             for (int j = j0; j < formed; ++j) {
                 for (int i = 0; i <= j; ++i) {
-                    const double v = a1[(size_t)j * kk + i].x + a2[(size_t)j * kk + i].x;
+                    const double v = Sc<T>::re(a1[(size_t)j * kk + i]) + Sc<T>::re(a2[(size_t)j * kk + i]);
                     c.Hp[(size_t)i * m + j] = v;
                     c.Hp[(size_t)j * m + i] = v;
                     hscale = std::max(hscale, std::fabs(v));
                 }
-                const double bj = std::sqrt(an[j].x > 0.0 ? an[j].x : 0.0);
+                const double bj = std::sqrt(Sc<T>::re(an[j]) > 0.0 ? Sc<T>::re(an[j]) : 0.0);
                 c.beta_last = bj;
                 if (j + 1 < m) { c.Hp[(size_t)(j + 1) * m + j] = bj; c.Hp[(size_t)j * m + j + 1] = bj; }
                 hscale = std::max(hscale, std::fabs(c.Hp[0]));
                 if (!(bj > 1e-14 * (hscale + 1e-300)) || !std::isfinite(bj)) { c.mm = j + 1; break; }
             }
             const int mm = c.mm;
-            c.T.assign((size_t)mm * mm, 0.0);
+            c.Tm.assign((size_t)mm * mm, 0.0);
             for (int i = 0; i < mm; ++i)
-                for (int q = 0; q < mm; ++q) c.T[(size_t)i * mm + q] = c.Hp[(size_t)i * m + q];
-            sym_eig_host(mm, c.T, c.Y);
+                for (int q = 0; q < mm; ++q) c.Tm[(size_t)i * mm + q] = c.Hp[(size_t)i * m + q];
+            sym_eig_host(mm, c.Tm, c.Y);
             c.idx.resize(mm);
             for (int i = 0; i < mm; ++i) c.idx[i] = i;
-            std::sort(c.idx.begin(), c.idx.end(), [&](int a, int b) { return c.T[(size_t)a * mm + a] < c.T[(size_t)b * mm + b]; });
+            std::sort(c.idx.begin(), c.idx.end(), [&](int a, int b) { return c.Tm[(size_t)a * mm + a] < c.Tm[(size_t)b * mm + b]; });
             const int best = c.idx[0];
-            c.E = c.T[(size_t)best * mm + best];
+            c.E = c.Tm[(size_t)best * mm + best];
             c.resid = std::fabs(c.beta_last * c.Y[(size_t)(mm - 1) * mm + best]);
         };
         // the projected eigenproblems of the chains are independent: spread them over a few host threads
@@ -490,10 +468,10 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         auto ta = now();
         int formed = m;
         bool evaluated = false;
-        MPSB_CHECK_CUDA(cudaMemsetAsync(C1, 0, al(nb * kk * kk * sizeof(cplx)), st));     // pass 1 fills only part of a row
+        MPSB_CHECK_CUDA(cudaMemsetAsync(C1, 0, al(nb * kk * kk * sizeof(T)), st));     // pass 1 fills only part of a row
         for (int j = j0; j < m; ++j) {
-            cplx* vj = V + (size_t)j * vstride;
-            cplx* wv = V + (size_t)(j + 1) * vstride;
+            T* vj = V + (size_t)j * vstride;
+            T* wv = V + (size_t)(j + 1) * vstride;
             rc = heff_apply(h, vj, wv, st, sV, sV);
             if (rc) return rc;
             ++n_mv;
@@ -503,15 +481,15 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
             // coefficients and needs no repetition.  Traffic per step: 3 + j vectors instead of 2 (j + 1).
             const int lo = (j == j0) ? 0 : std::max(0, j - 1);
             {
-                cplx* c = C1 + (size_t)j * kk + lo;
-                const cplx* Vlo = V + (size_t)lo * vstride;
+                T* c = C1 + (size_t)j * kk + lo;
+                const T* Vlo = V + (size_t)lo * vstride;
                 rc = zdotc_multi(Vlo, (long long)vstride, j + 1 - lo, (long long)n, wv, c, part, nchunk, (int)kk, st, bat(sV, sV, sC));
                 if (rc) return rc;
                 rc = zaxpy_multi(Vlo, (long long)vstride, j + 1 - lo, (long long)n, c, -1.0, wv, st, bat(sV, sV, sC));
                 if (rc) return rc;
             }
             {
-                cplx* c = C2 + (size_t)j * kk;
+                T* c = C2 + (size_t)j * kk;
                 rc = zdotc_multi(V, (long long)vstride, j + 1, (long long)n, wv, c, part, nchunk, (int)kk, st, bat(sV, sV, sC));
                 if (rc) return rc;
                 rc = zaxpy_multi(V, (long long)vstride, j + 1, (long long)n, c, -1.0, wv, st, bat(sV, sV, sC));
@@ -549,17 +527,17 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         }
         const int keep = all_done ? 1 : std::min(LANCZOS_KEEP, m - 1);
         // Ritz vectors Vk[chain][i] = sum_q Y[q][idx[i]] V[chain][q]   (zero coefficients beyond a chain's own mm)
-        std::fill(hc.begin(), hc.end(), make_double2(0.0, 0.0));
+        std::fill(hc.begin(), hc.end(), Sc<T>::zero());
         for (size_t ci = 0; ci < nb; ++ci) {
             const Chain& c = ch[ci];
             if (c.frozen) continue;
             const int kc = std::min(keep, c.mm);
             for (int i = 0; i < kc; ++i)
                 for (int q = 0; q < c.mm; ++q)
-                    hc[ci * kk * LANCZOS_KEEP + (size_t)i * kk + q] = make_double2(c.Y[(size_t)q * c.mm + c.idx[i]], 0.0);
+                    hc[ci * kk * LANCZOS_KEEP + (size_t)i * kk + q] = Sc<T>::from_re(c.Y[(size_t)q * c.mm + c.idx[i]]);
         }
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(cplx) * nb * kk * LANCZOS_KEEP, cudaMemcpyHostToDevice, st));
-        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, nb * al(n * sizeof(cplx)) * LANCZOS_KEEP, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(T) * nb * kk * LANCZOS_KEEP, cudaMemcpyHostToDevice, st));
+        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, nb * al(n * sizeof(T)) * LANCZOS_KEEP, st));
         for (int i = 0; i < keep; ++i) {
             rc = zaxpy_multi(V, (long long)vstride, formed, (long long)n, Yd + (size_t)i * kk, 1.0, Vk + (size_t)i * vstride, st,
                              bat(sV, sVk, sY));
@@ -567,7 +545,7 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         }
         for (size_t ci = 0; ci < nb; ++ci) {          // freeze the chains that finished in this cycle
             if (!finish[ci]) continue;
-            MPSB_CHECK_CUDA(cudaMemcpyAsync(th + ci * (size_t)s_theta, Vk + ci * (size_t)sVk, n * sizeof(cplx),
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(th + ci * (size_t)s_theta, Vk + ci * (size_t)sVk, n * sizeof(T),
                                             cudaMemcpyDeviceToDevice, st));
             ch[ci].frozen = true;
         }
@@ -575,19 +553,19 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
         if (all_done) break;
         // new bases: kept Ritz vectors, then the residual direction v_m (already orthogonal to all of them)
         if (batch == 1) {
-            MPSB_CHECK_CUDA(cudaMemcpyAsync(V + (size_t)keep * vstride, V + (size_t)m * vstride, n * sizeof(cplx),
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(V + (size_t)keep * vstride, V + (size_t)m * vstride, n * sizeof(T),
                                             cudaMemcpyDeviceToDevice, st));
-            MPSB_CHECK_CUDA(cudaMemcpyAsync(V, Vk, al(n * sizeof(cplx)) * keep, cudaMemcpyDeviceToDevice, st));
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(V, Vk, al(n * sizeof(T)) * keep, cudaMemcpyDeviceToDevice, st));
         } else {
-            MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V + (size_t)keep * vstride, (size_t)sV * sizeof(cplx), V + (size_t)m * vstride,
-                                              (size_t)sV * sizeof(cplx), n * sizeof(cplx), nb, cudaMemcpyDeviceToDevice, st));
-            MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(cplx), Vk, (size_t)sVk * sizeof(cplx),
-                                              al(n * sizeof(cplx)) * keep, nb, cudaMemcpyDeviceToDevice, st));
+            MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V + (size_t)keep * vstride, (size_t)sV * sizeof(T), V + (size_t)m * vstride,
+                                              (size_t)sV * sizeof(T), n * sizeof(T), nb, cudaMemcpyDeviceToDevice, st));
+            MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(T), Vk, (size_t)sVk * sizeof(T),
+                                              al(n * sizeof(T)) * keep, nb, cudaMemcpyDeviceToDevice, st));
         }
         for (Chain& c : ch) {
             if (c.frozen) continue;
             std::vector<double> diag(keep);
-            for (int i = 0; i < keep; ++i) diag[i] = c.T[(size_t)c.idx[i] * c.mm + c.idx[i]];
+            for (int i = 0; i < keep; ++i) diag[i] = c.Tm[(size_t)c.idx[i] * c.mm + c.idx[i]];
             std::fill(c.Hp.begin(), c.Hp.end(), 0.0);
             for (int i = 0; i < keep; ++i) c.Hp[(size_t)i * m + i] = diag[i];
         }
@@ -600,7 +578,7 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
     if (rc) return rc;
     rc = znormalise((long long)n, N2, th, st, bat(0, s_theta, sN));
     if (rc) return rc;
-    cplx* hv = V + (size_t)1 * vstride;
+    T* hv = V + (size_t)1 * vstride;
     rc = heff_apply(h, th, hv, st, s_theta, sV);
     if (rc) return rc;
     ++n_mv;
@@ -610,19 +588,159 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
     if (rc) return rc;
     rc = zdotc_multi(hv, 0, 1, (long long)n, hv, N2, part, nchunk, (int)kk, st, bat(sV, sV, sN));
     if (rc) return rc;
-    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hc.data(), sizeof(cplx), C1, kk * kk * sizeof(cplx), sizeof(cplx), nb,
+    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hc.data(), sizeof(T), C1, kk * kk * sizeof(T), sizeof(T), nb,
                                       cudaMemcpyDeviceToHost, st));
-    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), sizeof(cplx), N2, kk * sizeof(cplx), sizeof(cplx), nb, cudaMemcpyDeviceToHost,
+    MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), sizeof(T), N2, kk * sizeof(T), sizeof(T), nb, cudaMemcpyDeviceToHost,
                                       st));
     MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
     for (size_t ci = 0; ci < nb; ++ci) {
-        if (energy_host) energy_host[ci] = hc[ci].x;
-        if (resid_host) resid_host[ci] = std::sqrt(hn[ci].x > 0.0 ? hn[ci].x : 0.0);
+        if (energy_host) energy_host[ci] = Sc<T>::re(hc[ci]);
+        if (resid_host) resid_host[ci] = std::sqrt(Sc<T>::re(hn[ci]) > 0.0 ? Sc<T>::re(hn[ci]) : 0.0);
     }
     if (n_matvec_host) *n_matvec_host = n_mv;
     return 0;
 }
 
+
+// A, B, S, S_prev_inv, theta: contiguous per chain ([batch][...])
+template <typename T>
+int predict_impl(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
+                 const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(batch >= 1 && chi >= 1 && chip >= 1 && d >= 1 && A && B && S && S_prev_inv && theta,
+                 "predict_theta: bad arguments");
+    const size_t need = 2 * al((size_t)batch * chi * d * chip * sizeof(T));
+    MPSB_REQUIRE(ws && ws_bytes >= need, "predict_theta: workspace %zu B < required %zu B", ws_bytes, need);
+    T* XL = static_cast<T*>(ws);
+    T* XR = reinterpret_cast<T*>(static_cast<unsigned char*>(ws) + need / 2);
+    const long long total = (long long)chi * d * chip;
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    predict_scale_kernel<T><<<grid, 256, 0, st>>>(chi, chip, d, static_cast<const T*>(B), static_cast<const T*>(A), S,
+                                                  S_prev_inv, XL, XR);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    GemmArgsT<T> g;
+    g.batch1 = batch; g.batch2 = 1; g.sA1 = total; g.sB1 = total; g.sC1 = (long long)chi * d * d * chi;
+    g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
+    g.A = XL; g.B = XR; g.C = static_cast<T*>(theta);
+    g.M = chi * d; g.N = d * chi; g.K = chip;
+    g.lda = chip; g.ldb = d * chi; g.ldc = d * chi; g.opA = 0; g.opB = 0;
+    return gemm(g, st);
+}
+
+
+size_t env_bytes(int batch, int chi, int chin, int d, int w, size_t esz) {
+    const size_t b = (size_t)batch;
+    return al(b * w * chi * chi * esz) + al(b * w * chi * d * chin * esz) * 2 + al(b * w * chin * chin * esz);
+}
+
+// E [batch][chi][chi][w] (stride sE), UV [batch][...] (sUV), W [w][w][d][d] per chain (sW) or shared (sW = 0),
+// E_out [batch][chin][chin][w] (sEo)
+template <typename T>
+int env_common(int right, int batch, int chi, int chin, int d, int w, const void* E, long long sE, const void* UV,
+                      long long sUV, const void* W, long long sW, int swap_conj, void* E_out, long long sEo, void* ws,
+                      size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(batch >= 1 && chi >= 1 && chin >= 1 && d >= 1 && w >= 1, "env: bad dims");
+    const size_t need = env_bytes(batch, chi, chin, d, w, sizeof(T));
+    MPSB_REQUIRE(ws && ws_bytes >= need, "env: workspace %zu B < required %zu B", ws_bytes, need);
+    const size_t b = (size_t)batch;
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    T* Et = reinterpret_cast<T*>(p); p += al(b * w * chi * chi * sizeof(T));
+    T* T1 = reinterpret_cast<T*>(p); p += al(b * w * chi * d * chin * sizeof(T));
+    T* T2 = reinterpret_cast<T*>(p); p += al(b * w * chi * d * chin * sizeof(T));
+    T* Ot = reinterpret_cast<T*>(p);
+    const T* X = static_cast<const T*>(UV);
+    const long long sEt = (long long)w * chi * chi, sT = (long long)w * chi * d * chin, sOt = (long long)w * chin * chin;
+    // Et[k][i][j] = E[i][j][k]
+    int rc = transpose_conj(static_cast<const T*>(E), w, chi * chi, w, Et, chi * chi, 0, st, batch, sE, sEt);
+    if (rc) return rc;
+    GemmArgsT<T> g;
+    g.batch1 = batch; g.batch2 = 1; g.sA1 = sEt; g.sB1 = sUV; g.sC1 = sT; g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
+    // ket leg (index j of the environment) meets the un-conjugated tensor unless swap_conj
+    if (!right) {
+        // T1[(k,i)][(m,B)] = sum_j Et[(k,i)][j] U[j][(m,B)]
+        g.A = Et; g.B = X; g.C = T1; g.M = w * chi; g.N = d * chin; g.K = chi;
+        g.lda = chi; g.ldb = d * chin; g.ldc = d * chin; g.opA = 0; g.opB = swap_conj ? 3 : 0;
+    } else {
+        // T1[(k,i)][(B,m)] = sum_j Et[(k,i)][j] V[(B,m)][j]
+        g.A = Et; g.B = X; g.C = T1; g.M = w * chi; g.N = chin * d; g.K = chi;
+        g.lda = chi; g.ldb = chi; g.ldc = chin * d; g.opA = 0; g.opB = swap_conj ? 2 : 1;
+    }
+    rc = gemm(g, st);
+    if (rc) return rc;
+    const long long total = (long long)w * chi * d * chin;
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    env_w_kernel<T><<<grid, 256, 0, st>>>(right, chi, chin, d, w, static_cast<const T*>(W), sW, T1, T2);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    // bra leg:  Ot[C][A][B] = sum_{K} op(X)[A][K] T2[C][K][B]      (batch level 1: chains, level 2: C)
+    g.B = T2; g.C = Ot; g.M = chin; g.N = chin; g.K = chi * d; g.ldb = chin; g.ldc = chin;
+    g.batch1 = batch; g.batch2 = w;
+    g.sA1 = sUV; g.sB1 = sT; g.sC1 = sOt;
+    g.sA2 = 0; g.sB2 = (long long)chi * d * chin; g.sC2 = (long long)chin * chin;
+    g.A = X;
+    if (!right) { g.lda = chin; g.opA = swap_conj ? 1 : 2; }      // U as [(i,l)][A]
+    else        { g.lda = chi * d; g.opA = swap_conj ? 0 : 3; }   // V as [A][(l,i)]
+    g.opB = 0;
+    rc = gemm(g, st);
+    if (rc) return rc;
+    // E_out[A][B][C] = Ot[C][A][B]
+    return transpose_conj(Ot, chin * chin, w, chin * chin, static_cast<T*>(E_out), w, 0, st, batch, sOt, sEo);
+}
+
+
+}  // namespace
+}  // namespace mpsb
+
+using namespace mpsb;
+
+extern "C" {
+
+// The *_real entry points take tensors of doubles with the same shapes, strides (in doubles) and workspace queries as
+// their complex twins (the queries return the complex size, an upper bound for the real call).
+size_t mpsb_heff_batched_workspace(int batch, int chil, int chir, int d, int w) {
+    return heff_bytes(chil, chir, d, w, batch);
+}
+size_t mpsb_heff_workspace(int chil, int chir, int d, int w) { return heff_bytes(chil, chir, d, w); }
+
+int mpsb_heff_matvec_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                             long long sW, const void* R, long long sR, const void* theta, long long s_theta, void* out,
+                             long long s_out, void* ws, size_t ws_bytes, void* stream) {
+    return heff_matvec_impl<cplx>(batch, chil, chir, d, w, L, sL, W, sW, R, sR, theta, s_theta, out, s_out, ws, ws_bytes,
+                                  stream);
+}
+int mpsb_heff_matvec_batched_real(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                                  long long sW, const void* R, long long sR, const void* theta, long long s_theta,
+                                  void* out, long long s_out, void* ws, size_t ws_bytes, void* stream) {
+    return heff_matvec_impl<double>(batch, chil, chir, d, w, L, sL, W, sW, R, sR, theta, s_theta, out, s_out, ws,
+                                    ws_bytes, stream);
+}
+int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, const void* theta,
+                     void* out, void* ws, size_t ws_bytes, void* stream) {
+    return mpsb_heff_matvec_batched(1, chil, chir, d, w, L, 0, W, 0, R, 0, theta, 0, out, 0, ws, ws_bytes, stream);
+}
+
+size_t mpsb_lanczos_batched_workspace(int batch, int chil, int chir, int d, int w, int krylov) {
+    return lanczos_bytes(batch, chil, chir, d, w, krylov, sizeof(cplx));
+}
+size_t mpsb_lanczos_workspace(int chil, int chir, int d, int w, int krylov) {
+    return mpsb_lanczos_batched_workspace(1, chil, chir, d, w, krylov);
+}
+int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                                long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
+                                int max_restarts, double tol, double* energy_host, double* resid_host, int* n_matvec_host,
+                                void* ws, size_t ws_bytes, void* stream) {
+    return lanczos_impl<cplx>(batch, chil, chir, d, w, L, sL, W, sW, R, sR, theta, s_theta, krylov, max_restarts, tol,
+                              energy_host, resid_host, n_matvec_host, ws, ws_bytes, stream);
+}
+int mpsb_lanczos_ground_batched_real(int batch, int chil, int chir, int d, int w, const void* L, long long sL,
+                                     const void* W, long long sW, const void* R, long long sR, void* theta,
+                                     long long s_theta, int krylov, int max_restarts, double tol, double* energy_host,
+                                     double* resid_host, int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
+    return lanczos_impl<double>(batch, chil, chir, d, w, L, sL, W, sW, R, sR, theta, s_theta, krylov, max_restarts, tol,
+                                energy_host, resid_host, n_matvec_host, ws, ws_bytes, stream);
+}
 int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const void* W, const void* R, void* theta,
                         int krylov, int max_restarts, double tol, double* energy_host, double* resid_host,
                         int* n_matvec_host, void* ws, size_t ws_bytes, void* stream) {
@@ -635,115 +753,50 @@ size_t mpsb_predict_batched_workspace(int batch, int chi, int chip, int d) {
     return 2 * al((size_t)batch * chi * d * chip * sizeof(cplx));
 }
 size_t mpsb_predict_workspace(int chi, int chip, int d) { return mpsb_predict_batched_workspace(1, chi, chip, d); }
-
-// A, B, S, S_prev_inv, theta: contiguous per chain ([batch][...])
 int mpsb_predict_theta_batched(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
                                const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(batch >= 1 && chi >= 1 && chip >= 1 && d >= 1 && A && B && S && S_prev_inv && theta,
-                 "predict_theta: bad arguments");
-    const size_t need = mpsb_predict_batched_workspace(batch, chi, chip, d);
-    MPSB_REQUIRE(ws && ws_bytes >= need, "predict_theta: workspace %zu B < required %zu B", ws_bytes, need);
-    cplx* XL = static_cast<cplx*>(ws);
-    cplx* XR = reinterpret_cast<cplx*>(static_cast<unsigned char*>(ws) + need / 2);
-    const long long total = (long long)chi * d * chip;
-    dim3 grid((unsigned)((total + 255) / 256), batch);
-    predict_scale_kernel<<<grid, 256, 0, st>>>(chi, chip, d, static_cast<const cplx*>(B), static_cast<const cplx*>(A), S,
-                                               S_prev_inv, XL, XR);
-    MPSB_COUNT_LAUNCH();
-    MPSB_CHECK_CUDA(cudaGetLastError());
-    GemmArgs g;
-    g.batch1 = batch; g.batch2 = 1; g.sA1 = total; g.sB1 = total; g.sC1 = (long long)chi * d * d * chi;
-    g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
-    g.A = XL; g.B = XR; g.C = static_cast<cplx*>(theta);
-    g.M = chi * d; g.N = d * chi; g.K = chip;
-    g.lda = chip; g.ldb = d * chi; g.ldc = d * chi; g.opA = 0; g.opB = 0;
-    return zgemm(g, st);
+    return predict_impl<cplx>(batch, chi, chip, d, A, B, S, S_prev_inv, theta, ws, ws_bytes, stream);
 }
-
+int mpsb_predict_theta_batched_real(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
+                                    const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream) {
+    return predict_impl<double>(batch, chi, chip, d, A, B, S, S_prev_inv, theta, ws, ws_bytes, stream);
+}
 int mpsb_predict_theta(int chi, int chip, int d, const void* A, const void* B, const double* S, const double* S_prev_inv,
                        void* theta, void* ws, size_t ws_bytes, void* stream) {
     return mpsb_predict_theta_batched(1, chi, chip, d, A, B, S, S_prev_inv, theta, ws, ws_bytes, stream);
 }
 
 size_t mpsb_env_batched_workspace(int batch, int chi, int chin, int d, int w) {
-    const size_t b = (size_t)batch;
-    return al(b * w * chi * chi * sizeof(cplx)) + al(b * w * chi * d * chin * sizeof(cplx)) * 2 +
-           al(b * w * chin * chin * sizeof(cplx));
+    return env_bytes(batch, chi, chin, d, w, sizeof(cplx));
 }
 size_t mpsb_env_workspace(int chi, int chin, int d, int w) { return mpsb_env_batched_workspace(1, chi, chin, d, w); }
-
-// E [batch][chi][chi][w] (stride sE), UV [batch][...] (sUV), W [w][w][d][d] per chain (sW) or shared (sW = 0),
-// E_out [batch][chin][chin][w] (sEo)
-static int env_common(int right, int batch, int chi, int chin, int d, int w, const void* E, long long sE, const void* UV,
-                      long long sUV, const void* W, long long sW, int swap_conj, void* E_out, long long sEo, void* ws,
-                      size_t ws_bytes, void* stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MPSB_REQUIRE(batch >= 1 && chi >= 1 && chin >= 1 && d >= 1 && w >= 1, "env: bad dims");
-    const size_t need = mpsb_env_batched_workspace(batch, chi, chin, d, w);
-    MPSB_REQUIRE(ws && ws_bytes >= need, "env: workspace %zu B < required %zu B", ws_bytes, need);
-    const size_t b = (size_t)batch;
-    unsigned char* p = static_cast<unsigned char*>(ws);
-    cplx* Et = reinterpret_cast<cplx*>(p); p += al(b * w * chi * chi * sizeof(cplx));
-    cplx* T1 = reinterpret_cast<cplx*>(p); p += al(b * w * chi * d * chin * sizeof(cplx));
-    cplx* T2 = reinterpret_cast<cplx*>(p); p += al(b * w * chi * d * chin * sizeof(cplx));
-    cplx* Ot = reinterpret_cast<cplx*>(p);
-    const cplx* X = static_cast<const cplx*>(UV);
-    const long long sEt = (long long)w * chi * chi, sT = (long long)w * chi * d * chin, sOt = (long long)w * chin * chin;
-    // Et[k][i][j] = E[i][j][k]
-    int rc = transpose_conj(static_cast<const cplx*>(E), w, chi * chi, w, Et, chi * chi, 0, st, batch, sE, sEt);
-    if (rc) return rc;
-    GemmArgs g;
-    g.batch1 = batch; g.batch2 = 1; g.sA1 = sEt; g.sB1 = sUV; g.sC1 = sT; g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
-    // ket leg (index j of the environment) meets the un-conjugated tensor unless swap_conj
-    if (!right) {
-        // T1[(k,i)][(m,B)] = sum_j Et[(k,i)][j] U[j][(m,B)]
-        g.A = Et; g.B = X; g.C = T1; g.M = w * chi; g.N = d * chin; g.K = chi;
-        g.lda = chi; g.ldb = d * chin; g.ldc = d * chin; g.opA = 0; g.opB = swap_conj ? 3 : 0;
-    } else {
-        // T1[(k,i)][(B,m)] = sum_j Et[(k,i)][j] V[(B,m)][j]
-        g.A = Et; g.B = X; g.C = T1; g.M = w * chi; g.N = chin * d; g.K = chi;
-        g.lda = chi; g.ldb = chi; g.ldc = chin * d; g.opA = 0; g.opB = swap_conj ? 2 : 1;
-    }
-    rc = zgemm(g, st);
-    if (rc) return rc;
-    const long long total = (long long)w * chi * d * chin;
-    dim3 grid((unsigned)((total + 255) / 256), batch);
-    env_w_kernel<<<grid, 256, 0, st>>>(right, chi, chin, d, w, static_cast<const cplx*>(W), sW, T1, T2);
-    MPSB_COUNT_LAUNCH();
-    MPSB_CHECK_CUDA(cudaGetLastError());
-    // bra leg:  Ot[C][A][B] = sum_{K} op(X)[A][K] T2[C][K][B]      (batch level 1: chains, level 2: C)
-    g.B = T2; g.C = Ot; g.M = chin; g.N = chin; g.K = chi * d; g.ldb = chin; g.ldc = chin;
-    g.batch1 = batch; g.batch2 = w;
-    g.sA1 = sUV; g.sB1 = sT; g.sC1 = sOt;
-    g.sA2 = 0; g.sB2 = (long long)chi * d * chin; g.sC2 = (long long)chin * chin;
-    g.A = X;
-    if (!right) { g.lda = chin; g.opA = swap_conj ? 1 : 2; }      // U as [(i,l)][A]
-    else        { g.lda = chi * d; g.opA = swap_conj ? 0 : 3; }   // V as [A][(l,i)]
-    g.opB = 0;
-    rc = zgemm(g, st);
-    if (rc) return rc;
-    // E_out[A][B][C] = Ot[C][A][B]
-    return transpose_conj(Ot, chin * chin, w, chin * chin, static_cast<cplx*>(E_out), w, 0, st, batch, sOt, sEo);
-}
-
 int mpsb_env_left(int chi, int chin, int d, int w, const void* L, const void* U, const void* W, int swap_conj,
                   void* L_out, void* ws, size_t ws_bytes, void* stream) {
-    return env_common(0, 1, chi, chin, d, w, L, 0, U, 0, W, 0, swap_conj, L_out, 0, ws, ws_bytes, stream);
+    return env_common<cplx>(0, 1, chi, chin, d, w, L, 0, U, 0, W, 0, swap_conj, L_out, 0, ws, ws_bytes, stream);
 }
 int mpsb_env_right(int chi, int chin, int d, int w, const void* R, const void* V, const void* W, int swap_conj,
                    void* R_out, void* ws, size_t ws_bytes, void* stream) {
-    return env_common(1, 1, chi, chin, d, w, R, 0, V, 0, W, 0, swap_conj, R_out, 0, ws, ws_bytes, stream);
+    return env_common<cplx>(1, 1, chi, chin, d, w, R, 0, V, 0, W, 0, swap_conj, R_out, 0, ws, ws_bytes, stream);
 }
 int mpsb_env_left_batched(int batch, int chi, int chin, int d, int w, const void* L, long long sL, const void* U, long long sU,
                           const void* W, long long sW, int swap_conj, void* L_out, long long sLo, void* ws, size_t ws_bytes,
                           void* stream) {
-    return env_common(0, batch, chi, chin, d, w, L, sL, U, sU, W, sW, swap_conj, L_out, sLo, ws, ws_bytes, stream);
+    return env_common<cplx>(0, batch, chi, chin, d, w, L, sL, U, sU, W, sW, swap_conj, L_out, sLo, ws, ws_bytes, stream);
 }
 int mpsb_env_right_batched(int batch, int chi, int chin, int d, int w, const void* R, long long sR, const void* V, long long sV,
                            const void* W, long long sW, int swap_conj, void* R_out, long long sRo, void* ws, size_t ws_bytes,
                            void* stream) {
-    return env_common(1, batch, chi, chin, d, w, R, sR, V, sV, W, sW, swap_conj, R_out, sRo, ws, ws_bytes, stream);
+    return env_common<cplx>(1, batch, chi, chin, d, w, R, sR, V, sV, W, sW, swap_conj, R_out, sRo, ws, ws_bytes, stream);
+}
+int mpsb_env_left_batched_real(int batch, int chi, int chin, int d, int w, const void* L, long long sL, const void* U,
+                               long long sU, const void* W, long long sW, void* L_out, long long sLo, void* ws,
+                               size_t ws_bytes, void* stream) {
+    return env_common<double>(0, batch, chi, chin, d, w, L, sL, U, sU, W, sW, 0, L_out, sLo, ws, ws_bytes, stream);
+}
+int mpsb_env_right_batched_real(int batch, int chi, int chin, int d, int w, const void* R, long long sR, const void* V,
+                                long long sV, const void* W, long long sW, void* R_out, long long sRo, void* ws,
+                                size_t ws_bytes, void* stream) {
+    return env_common<double>(1, batch, chi, chin, d, w, R, sR, V, sV, W, sW, 0, R_out, sRo, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -24,10 +24,11 @@ void prof_mark(int idx, cudaStream_t st);
 // ---- batched complex128 GEMM (zgemm.cu) ------------------------------------------------------
 // C[z1,z2] = op(A[z1,z2]) * op(B[z1,z2]) (+ C[z1,z2]); op: 0 = N, 1 = T, 2 = C (conj-transpose),
 // 3 = J (conjugate, no transpose).  M, N, K are the dimensions of the product (after op).
-struct GemmArgs {
-    const cplx* A;
-    const cplx* B;
-    cplx* C;
+template <typename T>
+struct GemmArgsT {
+    const T* A;
+    const T* B;
+    T* C;
     int M, N, K;
     int lda, ldb, ldc;
     int opA, opB;
@@ -35,7 +36,15 @@ struct GemmArgs {
     long long sA1, sA2, sB1, sB2, sC1, sC2;  // element strides of the two batch levels
     int accumulate;
 };
+typedef GemmArgsT<cplx> GemmArgs;
 int zgemm(const GemmArgs& p, cudaStream_t st);
+// ---- batched real (double) GEMM on the same DMMA tiles (dgemm.cu) --------------------------------
+// The real-arithmetic twin used when the MPO and the state are real (the reference's
+// MPO.tomatrix(dtype='double') path, DMRG/MPO.py:68-76): a quarter of the flops of the complex product.
+// op: 0 / 3 = N, 1 / 2 = T (conjugation is a no-op).
+int dgemm(const GemmArgsT<double>& p, cudaStream_t st);
+inline int gemm(const GemmArgsT<cplx>& p, cudaStream_t st) { return zgemm(p, st); }
+inline int gemm(const GemmArgsT<double>& p, cudaStream_t st) { return dgemm(p, st); }
 
 // ---- truncated SVD by QR-preconditioned one-sided Jacobi (jacobi_svd.cu) -----------------------
 // The work matrix X of one problem is n_pad x ld complex128, row-major.  Its first `ldot` columns
@@ -108,6 +117,8 @@ int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, c
 // out[j * ldo + i] = conj?(in[i * ldi + j]),  i < rows, j < cols; batched with element strides s_in / s_out
 int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st,
                    int batch = 1, long long s_in = 0, long long s_out = 0);
+int transpose_conj(const double* in, int ldi, int rows, int cols, double* out, int ldo, int conj, cudaStream_t st,
+                   int batch = 1, long long s_in = 0, long long s_out = 0);
 // out[i][j] = s[i / group] * in[i][j]
 int scale_rows(int rows, int cols, const cplx* in, int ldi, const double* s, int group, cplx* out, int ldo,
                cudaStream_t st);
@@ -124,11 +135,16 @@ struct BlasBatch {
 // followed by m_cap ticket counters (unsigned int) that must be zero on entry; they are zero again on exit.
 int zdotc_multi(const cplx* V, long long ldv, int m, long long n, const cplx* w, cplx* y, cplx* part, int nchunk,
                 int m_cap, cudaStream_t st, BlasBatch bb = BlasBatch());
+int zdotc_multi(const double* V, long long ldv, int m, long long n, const double* w, double* y, double* part, int nchunk,
+                int m_cap, cudaStream_t st, BlasBatch bb = BlasBatch());      // real twins of the three helpers
 // w[i] += sign * sum_j c[j] V[j][i]   (c on device, m entries)
 int zaxpy_multi(const cplx* V, long long ldv, int m, long long n, const cplx* c, double sign, cplx* w,
                 cudaStream_t st, BlasBatch bb = BlasBatch());
+int zaxpy_multi(const double* V, long long ldv, int m, long long n, const double* c, double sign, double* w,
+                cudaStream_t st, BlasBatch bb = BlasBatch());
 // w *= 1/sqrt(nrm2[0].x) with nrm2 on the device (zero vector if the norm vanishes)
 int znormalise(long long n, const cplx* nrm2, cplx* w, cudaStream_t st, BlasBatch bb = BlasBatch());
+int znormalise(long long n, const double* nrm2, double* w, cudaStream_t st, BlasBatch bb = BlasBatch());
 // w[i] = alpha * w[i]  (alpha real, on host)
 int zdscal(long long n, double alpha, cplx* w, cudaStream_t st);
 

@@ -18,6 +18,7 @@ from . import _lib
 from .MPO import MPO  # noqa: F401  (re-exported like the reference does)
 from .MPS import _device_svd
 
+REAL_PATH = True     # real L, W, R (MPO.tomatrix(dtype='double'), DMRG/MPO.py:68-76) run in real arithmetic (DGEMM on DMMA)
 KRYLOV = 24          # Lanczos basis size between restarts
 MAX_RESTARTS = 60
 TOL = 1e-13          # residual target relative to max(1, |E|)
@@ -33,6 +34,39 @@ def matrixify(A):
     """Reshape a (chi,d,d,chi,chi,d,d,chi) tensor into a square matrix (`DMRG/iDMRG.py:43-46`)."""
     n = np.rint(np.sqrt(A.size)).astype(int)
     return A.reshape([n, n])
+
+
+def _is_real_t(t):
+    return not t.is_complex()
+
+
+def _all_real(*arrays):
+    """True when every host array is real-valued (real dtype, or complex dtype with an exactly zero imaginary part)."""
+    if not REAL_PATH:
+        return False
+    for a in arrays:
+        a = np.asarray(a)
+        if np.iscomplexobj(a) and np.any(a.imag != 0):
+            return False
+    return True
+
+
+def _to_device_auto(real, *arrays):
+    if real:
+        return tuple(_lib.to_device(np.asarray(a).real, np.float64) for a in arrays)
+    return tuple(_lib.to_device(np.asarray(a)) for a in arrays)
+
+
+def _as_complex(x):
+    t = _lib.torch()
+    return t.complex(x, t.zeros_like(x)) if not x.is_complex() else x
+
+
+def _split_real(split, theta, sh, trunc):
+    """SVD split of a real two-site tensor: the Jacobi kernels are complex128, and complex arithmetic on data with a
+    zero imaginary part stays exactly real (every product with 0 is 0), so the factors are the real parts."""
+    U, S, V = split(_as_complex(theta), sh, trunc)
+    return U.real.contiguous(), S, V.real.contiguous()
 
 
 def halve(psi, sh, trunc=10):
@@ -70,16 +104,22 @@ _halve_public = halve
 def _heff_apply(L, M, R, theta):
     lib = _lib.load()
     xl, xr, w, d = L.shape[0], R.shape[0], M.shape[0], M.shape[2]
-    out = _lib.empty(tuple(theta.shape))
     ws, wsn = _lib.workspace(lib.mpsb_heff_workspace(xl, xr, d, w))
+    if _is_real_t(L):
+        out = _lib.empty(tuple(theta.shape), "f64")
+        _lib.check(lib.mpsb_heff_matvec_batched_real(1, xl, xr, d, w, _lib.ptr(L), 0, _lib.ptr(M), 0, _lib.ptr(R), 0,
+                                                     _lib.ptr(theta), 0, _lib.ptr(out), 0, ws, wsn, _lib.stream_ptr()),
+                   "mpsb_heff_matvec_batched_real")
+        return out
+    out = _lib.empty(tuple(theta.shape))
     _lib.check(lib.mpsb_heff_matvec(xl, xr, d, w, _lib.ptr(L), _lib.ptr(M), _lib.ptr(R), _lib.ptr(theta), _lib.ptr(out),
                                     ws, wsn, _lib.stream_ptr()), "mpsb_heff_matvec")
     return out
 
 
 def heff_matvec(L, M, R, theta):
-    """out = H_eff theta without forming H_eff (new; host arrays in and out)."""
-    Ld, Md, Rd, td = (_lib.to_device(a) for a in (L, M, R, theta))
+    """out = H_eff theta without forming H_eff (new; host arrays in and out; real arithmetic when all four are real)."""
+    Ld, Md, Rd, td = _to_device_auto(_all_real(L, M, R, theta), L, M, R, theta)
     return _lib.to_host(_heff_apply(Ld, Md, Rd, td))
 
 
@@ -103,19 +143,26 @@ def ground_state(Ld, Md, Rd, seed=0, theta0=None):
     """Lowest eigenpair of H_eff on device tensors: (E, theta) with theta normalised."""
     lib = _lib.load()
     xl, xr, w, d = Ld.shape[0], Rd.shape[0], Md.shape[0], Md.shape[2]
+    real = _is_real_t(Ld)
     if theta0 is None:      # seeded start vector, generated on the device (the reference's ARPACK start is random too)
         t = _lib.torch()
         gen = t.Generator(device=_lib.device())
         gen.manual_seed(int(seed))
         theta0 = t.randn((xl, d, d, xr, 2), dtype=t.float64, device=_lib.device(), generator=gen)
-        theta0 = t.view_as_complex(theta0)
+        theta0 = theta0[..., 0].contiguous() if real else t.view_as_complex(theta0)
     theta = theta0.clone()
     import ctypes
     E, resid, nmv = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
     ws, wsn = _lib.workspace(lib.mpsb_lanczos_workspace(xl, xr, d, w, KRYLOV))
-    _lib.check(lib.mpsb_lanczos_ground(xl, xr, d, w, _lib.ptr(Ld), _lib.ptr(Md), _lib.ptr(Rd), _lib.ptr(theta), KRYLOV,
-                                       MAX_RESTARTS, TOL, ctypes.byref(E), ctypes.byref(resid), ctypes.byref(nmv), ws,
-                                       wsn, _lib.stream_ptr()), "mpsb_lanczos_ground")
+    if real:
+        _lib.check(lib.mpsb_lanczos_ground_batched_real(1, xl, xr, d, w, _lib.ptr(Ld), 0, _lib.ptr(Md), 0, _lib.ptr(Rd), 0,
+                                                        _lib.ptr(theta), xl * d * d * xr, KRYLOV, MAX_RESTARTS, TOL,
+                                                        ctypes.byref(E), ctypes.byref(resid), ctypes.byref(nmv), ws, wsn,
+                                                        _lib.stream_ptr()), "mpsb_lanczos_ground_batched_real")
+    else:
+        _lib.check(lib.mpsb_lanczos_ground(xl, xr, d, w, _lib.ptr(Ld), _lib.ptr(Md), _lib.ptr(Rd), _lib.ptr(theta), KRYLOV,
+                                           MAX_RESTARTS, TOL, ctypes.byref(E), ctypes.byref(resid), ctypes.byref(nmv), ws,
+                                           wsn, _lib.stream_ptr()), "mpsb_lanczos_ground")
     last_info.update(n_matvec=nmv.value, residual=resid.value)
     _warn_if_residual_large(E.value, resid.value)
     return E.value, theta
@@ -126,8 +173,14 @@ def _env(left, Ed, Td, Md, swap_conj):
     w, d = Md.shape[0], Md.shape[2]
     chi = Ed.shape[0]
     chin = Td.shape[2] if left else Td.shape[0]
-    out = _lib.empty((chin, chin, w))
     ws, wsn = _lib.workspace(lib.mpsb_env_workspace(chi, chin, d, w))
+    if _is_real_t(Ed):
+        out = _lib.empty((chin, chin, w), "f64")
+        fn = lib.mpsb_env_left_batched_real if left else lib.mpsb_env_right_batched_real
+        _lib.check(fn(1, chi, chin, d, w, _lib.ptr(Ed), 0, _lib.ptr(Td), 0, _lib.ptr(Md), 0, _lib.ptr(out), 0, ws, wsn,
+                      _lib.stream_ptr()), "mpsb_env_real")
+        return out
+    out = _lib.empty((chin, chin, w))
     fn = lib.mpsb_env_left if left else lib.mpsb_env_right
     _lib.check(fn(chi, chin, d, w, _lib.ptr(Ed), _lib.ptr(Td), _lib.ptr(Md), int(swap_conj), _lib.ptr(out), ws, wsn,
                   _lib.stream_ptr()), "mpsb_env")
@@ -138,12 +191,15 @@ def next_LR_device(Ld, Rd, Md, trunc=None, swap_conj=False, seed=0):
     """`next_LR` on device-resident tensors (no host round trip): returns (L', R', E, S_all)."""
     E, theta = ground_state(Ld, Md, Rd, seed=seed)
     sh = tuple(theta.shape)
+    real = _is_real_t(theta)
     if trunc is None and halve is not _halve_public:       # somebody rebound the module-level halve (reference idiom)
         U, S, V = halve(theta, sh)
     elif sh[0] * sh[1] <= 256:                             # carried-identity SVD is faster while rows stay short
-        U, S, V = halve(theta, sh, 10 if trunc is None else trunc)
+        split, tr = halve, 10 if trunc is None else trunc
+        U, S, V = _split_real(split, theta, sh, tr) if real else split(theta, sh, tr)
     else:
-        U, S, V = _halve_split(theta, sh, 10 if trunc is None else trunc)
+        split, tr = _halve_split, 10 if trunc is None else trunc
+        U, S, V = _split_real(split, theta, sh, tr) if real else split(theta, sh, tr)
     Ln = _env(True, Ld, U.contiguous(), Md, swap_conj)
     Rn = _env(False, Rd, V.contiguous(), Md, swap_conj)
     last_info["S"] = _lib.to_host(S)
@@ -154,9 +210,10 @@ def _overlap(a, b):
     """<a|b> of two device tensors of equal shape: one batched 1x1 GEMM per row, summed on the host."""
     rows = int(a.shape[0]) * int(a.shape[1])
     cols = a.numel() // rows
-    part = _lib.empty((rows,))
-    _lib.zgemm(a.reshape(rows, cols), b.reshape(rows, cols), part, 1, 1, cols, cols, 1, 1, opA=_lib.OP_J, opB=_lib.OP_T,
-               batch1=rows, sA=(cols, 0), sB=(cols, 0), sC=(1, 0))
+    real = _is_real_t(a)
+    part = _lib.empty((rows,), "f64" if real else "c128")
+    (_lib.dgemm if real else _lib.zgemm)(a.reshape(rows, cols), b.reshape(rows, cols), part, 1, 1, cols, cols, 1, 1,
+                                         opA=_lib.OP_J, opB=_lib.OP_T, batch1=rows, sA=(cols, 0), sB=(cols, 0), sC=(1, 0))
     return complex(_lib.to_host(part).sum())
 
 
@@ -183,8 +240,8 @@ class Chain:
         if R is None:
             R = np.zeros((1, 1, w), dtype=complex)
             R[0, 0, 0] = 1
-        self.M = _lib.to_device(M)
-        self.L, self.R = _lib.to_device(np.asarray(L)), _lib.to_device(np.asarray(R))
+        self.real = _all_real(M, L, R)                     # real MPO and boundaries: the whole run stays real
+        self.M, self.L, self.R = _to_device_auto(self.real, M, L, R)
         self.trunc, self.swap_conj, self.seed, self.predict, self.cutoff = trunc, swap_conj, seed, predict, cutoff
         self.A = self.B = self.S = self.S_prev = None
         self.energies, self.n_matvec, self.fidelity = [], [], []
@@ -202,9 +259,15 @@ class Chain:
         # the guess then has exact zeros on the dead states instead of products of noise that underflow step by step.
         inv = np.where(self.S_prev > self.cutoff * self.S_prev[0], 1.0 / np.maximum(self.S_prev, 1e-300), 0.0)
         cur = np.where(self.S > self.cutoff * self.S[0], self.S, 0.0)
-        theta = _lib.empty((chi, d, d, chi))
         S, Sinv = _lib.to_device(cur, np.float64), _lib.to_device(inv, np.float64)
         ws, wsn = _lib.workspace(lib.mpsb_predict_workspace(chi, chip, d))
+        if self.real:
+            theta = _lib.empty((chi, d, d, chi), "f64")
+            _lib.check(lib.mpsb_predict_theta_batched_real(1, chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S),
+                                                           _lib.ptr(Sinv), _lib.ptr(theta), ws, wsn, _lib.stream_ptr()),
+                       "mpsb_predict_theta_batched_real")
+            return theta
+        theta = _lib.empty((chi, d, d, chi))
         _lib.check(lib.mpsb_predict_theta(chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S), _lib.ptr(Sinv),
                                           _lib.ptr(theta), ws, wsn, _lib.stream_ptr()), "mpsb_predict_theta")
         return theta
@@ -218,7 +281,10 @@ class Chain:
             nrm = np.sqrt(abs(_overlap(guess, guess)))
             self.fidelity.append(abs(_overlap(guess, theta)) / nrm if nrm > 0 else 0.0)
         sh = tuple(theta.shape)
-        U, S_all, V = _halve_public(theta, sh, self.trunc)     # one SVD with carried identity: U and V share a gauge
+        if self.real:
+            U, S_all, V = _split_real(_halve_public, theta, sh, self.trunc)
+        else:
+            U, S_all, V = _halve_public(theta, sh, self.trunc)     # one SVD with carried identity: U and V share a gauge
         self.L = _env(True, self.L, U.contiguous(), self.M, self.swap_conj)
         self.R = _env(False, self.R, V.contiguous(), self.M, self.swap_conj)
         s = _lib.to_host(S_all)[:U.shape[2]]
@@ -257,6 +323,11 @@ class Chain:
 def _transpose_batched(a, conj=True):
     """[n, rows, cols] device tensor -> [n, cols, rows] (conjugated) through the library's tile-transpose kernel."""
     n, rows, cols = (int(v) for v in a.shape)
+    if _is_real_t(a):
+        out = _lib.empty((n, cols, rows), "f64")
+        _lib.check(_lib.load().mpsb_transpose_batched_real(n, rows, cols, _lib.ptr(a), cols, rows * cols, _lib.ptr(out), rows,
+                                                           rows * cols, _lib.stream_ptr()), "mpsb_transpose_batched_real")
+        return out
     out = _lib.empty((n, cols, rows))
     _lib.check(_lib.load().mpsb_transpose_batched(n, rows, cols, _lib.ptr(a), cols, rows * cols, _lib.ptr(out), rows,
                                                   rows * cols, int(conj), _lib.stream_ptr()), "mpsb_transpose_batched")
@@ -286,6 +357,9 @@ def halve_batched(theta, trunc):
     """`halve` (DMRG/iDMRG.py:17-35) for n two-site tensors [n, xl, d, d, xr] at once: U [n, xl, d, k], S_all [n, .],
     V [n, k, d, xr] (device tensors; every chain keeps k = min(trunc, S.size) states, so the shapes stay common)."""
     n, xl, d, _, xr = (int(v) for v in theta.shape)
+    if _is_real_t(theta):                                   # complex Jacobi kernels on real data stay exactly real
+        U, s_all, V = halve_batched(_as_complex(theta), trunc)
+        return U.real.contiguous(), s_all, V.real.contiguous()
     A = theta.reshape(n, xl * d, d * xr)
     if xl * d <= 256:                                       # carried-identity SVD: U and V from one decomposition
         uh, s_all, vh = _svd_batched(A, trunc, True)
@@ -308,19 +382,22 @@ def ground_state_batched(Ld, Md, Rd, seed=0, theta0=None):
     d = int(Md.shape[-1])
     sW = w * w * d * d if Md.dim() == 5 else 0
     nel = xl * d * d * xr
+    real = _is_real_t(Ld)
     if theta0 is None:
         t = _lib.torch()
         gen = t.Generator(device=_lib.device())
         gen.manual_seed(int(seed))
-        theta0 = t.view_as_complex(t.randn((n, xl, d, d, xr, 2), dtype=t.float64, device=_lib.device(), generator=gen))
+        theta0 = t.randn((n, xl, d, d, xr, 2), dtype=t.float64, device=_lib.device(), generator=gen)
+        theta0 = theta0[..., 0].contiguous() if real else t.view_as_complex(theta0)
     theta = theta0.clone()
     E = (ctypes.c_double * n)()
     resid = (ctypes.c_double * n)()
     nmv = ctypes.c_int(0)
     ws, wsn = _lib.workspace(lib.mpsb_lanczos_batched_workspace(n, xl, xr, d, w, KRYLOV))
-    _lib.check(lib.mpsb_lanczos_ground_batched(n, xl, xr, d, w, _lib.ptr(Ld), xl * xl * w, _lib.ptr(Md), sW, _lib.ptr(Rd),
-                                               xr * xr * w, _lib.ptr(theta), nel, KRYLOV, MAX_RESTARTS, TOL, E, resid,
-                                               ctypes.byref(nmv), ws, wsn, _lib.stream_ptr()), "mpsb_lanczos_ground_batched")
+    fn = lib.mpsb_lanczos_ground_batched_real if real else lib.mpsb_lanczos_ground_batched
+    _lib.check(fn(n, xl, xr, d, w, _lib.ptr(Ld), xl * xl * w, _lib.ptr(Md), sW, _lib.ptr(Rd), xr * xr * w, _lib.ptr(theta),
+                  nel, KRYLOV, MAX_RESTARTS, TOL, E, resid, ctypes.byref(nmv), ws, wsn, _lib.stream_ptr()),
+               "mpsb_lanczos_ground_batched")
     E, resid = np.array(E[:]), np.array(resid[:])
     last_info.update(n_matvec=nmv.value, residual=float(resid.max()))
     _warn_if_residual_large(E, resid)
@@ -343,8 +420,14 @@ def _env_batched(left, Ed, Td, Md, swap_conj):
     d = int(Md.shape[-1])
     chin = int(Td.shape[3]) if left else int(Td.shape[1])
     sW = w * w * d * d if Md.dim() == 5 else 0
-    out = _lib.empty((n, chin, chin, w))
     ws, wsn = _lib.workspace(lib.mpsb_env_batched_workspace(n, chi, chin, d, w))
+    if _is_real_t(Ed):
+        out = _lib.empty((n, chin, chin, w), "f64")
+        fn = lib.mpsb_env_left_batched_real if left else lib.mpsb_env_right_batched_real
+        _lib.check(fn(n, chi, chin, d, w, _lib.ptr(Ed), chi * chi * w, _lib.ptr(Td), chi * d * chin, _lib.ptr(Md), sW,
+                      _lib.ptr(out), chin * chin * w, ws, wsn, _lib.stream_ptr()), "mpsb_env_batched_real")
+        return out
+    out = _lib.empty((n, chin, chin, w))
     fn = lib.mpsb_env_left_batched if left else lib.mpsb_env_right_batched
     _lib.check(fn(n, chi, chin, d, w, _lib.ptr(Ed), chi * chi * w, _lib.ptr(Td), chi * d * chin, _lib.ptr(Md), sW,
                   int(swap_conj), _lib.ptr(out), chin * chin * w, ws, wsn, _lib.stream_ptr()), "mpsb_env_batched")
@@ -371,12 +454,12 @@ class ChainBatch:
         self.trunc, self.swap_conj = int(trunc), bool(swap_conj)
         self.predict, self.cutoff = bool(predict), float(cutoff)
         self.A = self.B = self.Sn = self.Sn_prev = None
-        self.W = _lib.to_device(W)
+        self.real = _all_real(W)                            # real MPOs (TFIM, XXZ, Heisenberg): real arithmetic throughout
         L = np.zeros((self.n, 1, 1, self.w), dtype=complex)
         R = np.zeros((self.n, 1, 1, self.w), dtype=complex)
         L[:, 0, 0, self.w - 1 if left_index is None else left_index] = 1     # boundary vectors of the lower-triangular MPO
         R[:, 0, 0, right_index] = 1
-        self.L, self.R = _lib.to_device(L), _lib.to_device(R)
+        self.W, self.L, self.R = _to_device_auto(self.real, W, L, R)
         self.energies, self.n_matvec, self.S = [], [], None
         self.sites = 0
 
@@ -391,12 +474,12 @@ class ChainBatch:
         lib = _lib.load()
         inv = np.where(self.Sn_prev > self.cutoff * self.Sn_prev[:, :1], 1.0 / np.maximum(self.Sn_prev, 1e-300), 0.0)
         cur = np.where(self.Sn > self.cutoff * self.Sn[:, :1], self.Sn, 0.0)
-        theta = _lib.empty((n, chi, d, d, chi))
+        theta = _lib.empty((n, chi, d, d, chi), "f64" if self.real else "c128")
         S, Sinv = _lib.to_device(cur, np.float64), _lib.to_device(inv, np.float64)
         ws, wsn = _lib.workspace(lib.mpsb_predict_batched_workspace(n, chi, chip, d))
-        _lib.check(lib.mpsb_predict_theta_batched(n, chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S),
-                                                  _lib.ptr(Sinv), _lib.ptr(theta), ws, wsn, _lib.stream_ptr()),
-                   "mpsb_predict_theta_batched")
+        fn = lib.mpsb_predict_theta_batched_real if self.real else lib.mpsb_predict_theta_batched
+        _lib.check(fn(n, chi, chip, d, _lib.ptr(self.A), _lib.ptr(self.B), _lib.ptr(S), _lib.ptr(Sinv), _lib.ptr(theta), ws,
+                      wsn, _lib.stream_ptr()), "mpsb_predict_theta_batched")
         return theta
 
     def step(self, seed=0):
@@ -431,7 +514,7 @@ class ChainBatch:
 def next_LR(L, R, M, trunc=None, swap_conj=False, seed=0):
     """One iDMRG growth step (`DMRG/iDMRG.py:49-61`): returns (L', R', E) where E is the total energy
     of the enlarged open chain.  numpy in, numpy out."""
-    Ld, Rd, Md = (_lib.to_device(np.asarray(a)) for a in (L, R, M))
+    Ld, Rd, Md = _to_device_auto(_all_real(L, R, M), L, R, M)
     Ln, Rn, E, _ = next_LR_device(Ld, Rd, Md, trunc=trunc, swap_conj=swap_conj, seed=seed)
     return _lib.to_host(Ln), _lib.to_host(Rn), E
 

@@ -37,6 +37,13 @@ int mpsb_zgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, co
                int ldc, int batch1, int batch2, long long sA1, long long sA2, long long sB1, long long sB2,
                long long sC1, long long sC2, int accumulate, void* stream);
 
+/* The same for real matrices of doubles (op 0 / 3 = N, 1 / 2 = T): the real-arithmetic path the reference takes when
+ * the MPO is built with MPO.tomatrix(dtype='double') (DMRG/MPO.py:68-76) - L, W, R and the two-site tensor are then
+ * real and the contractions of DMRG/iDMRG.py:40,59,60 cost a quarter of the complex flops. */
+int mpsb_dgemm(int opA, int opB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C,
+               int ldc, int batch1, int batch2, long long sA1, long long sA2, long long sB1, long long sB2,
+               long long sC1, long long sC2, int accumulate, void* stream);
+
 /* Truncated SVD  m = U diag(s) Vh  of `batch` matrices (rows x cols, row pitch lda, batch stride sA).
  * Replaces svd_truncate / truncate (DMRG/MPS.py:14-45) when normalise = 1:
  *     s /= s[0];  k = min(#{s > err}, trun);  s = s[:k] / ||s[:k]||
@@ -139,6 +146,12 @@ int mpsb_heff_matvec_batched(int batch, int chil, int chir, int d, int w, const 
                              long long sW, const void* R, long long sR, const void* theta, long long s_theta, void* out,
                              long long s_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Real-arithmetic twin (L, W, R, theta, out are tensors of doubles; strides in doubles; the workspace query of the
+ * complex call is an upper bound). */
+int mpsb_heff_matvec_batched_real(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
+                                  long long sW, const void* R, long long sR, const void* theta, long long s_theta,
+                                  void* out, long long s_out, void* ws, size_t ws_bytes, void* stream);
+
 /* Lowest eigenpair of the effective Hamiltonian by Lanczos with full reorthogonalisation and
  * restarts (replaces eigsh(k=1, which='SA'), DMRG/iDMRG.py:57).  theta holds the start vector on
  * entry (must be non-zero) and the normalised ground vector on exit.  Results (host pointers):
@@ -156,6 +169,11 @@ int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, con
                                 long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
                                 int max_restarts, double tol, double* energy_host, double* resid_host, int* n_matvec_host,
                                 void* ws, size_t ws_bytes, void* stream);
+
+int mpsb_lanczos_ground_batched_real(int batch, int chil, int chir, int d, int w, const void* L, long long sL,
+                                     const void* W, long long sW, const void* R, long long sR, void* theta,
+                                     long long s_theta, int krylov, int max_restarts, double tol, double* energy_host,
+                                     double* resid_host, int* n_matvec_host, void* ws, size_t ws_bytes, void* stream);
 
 /* Environment growth (DMRG/iDMRG.py:59-60, with the conjugation on the bra leg — SURVEY App. B1):
  *     L'[A,B,C] = sum L[i,j,k] conj(U[i,l,A]) U[j,m,B] W[k,C,l,m]        U [chi][d][chin]
@@ -175,6 +193,14 @@ int mpsb_env_right_batched(int batch, int chi, int chin, int d, int w, const voi
                            const void* W, long long sW, int swap_conj, void* R_out, long long sRo, void* ws, size_t ws_bytes,
                            void* stream);
 
+/* real twins (no conjugation to choose) */
+int mpsb_env_left_batched_real(int batch, int chi, int chin, int d, int w, const void* L, long long sL, const void* U,
+                               long long sU, const void* W, long long sW, void* L_out, long long sLo, void* ws,
+                               size_t ws_bytes, void* stream);
+int mpsb_env_right_batched_real(int batch, int chi, int chin, int d, int w, const void* R, long long sR, const void* V,
+                                long long sV, const void* W, long long sW, void* R_out, long long sRo, void* ws,
+                                size_t ws_bytes, void* stream);
+
 /* Start vector for the next growth step from the tensors of the last one (new; the reference restarts ARPACK from a
  * random vector at DMRG/iDMRG.py:57).  With theta_n = A S B from the last split (A [chip][d][chi] left-orthonormal,
  * B [chi][d][chip] right-orthonormal, S [chi] normalised, all from ONE SVD so that their gauges match) and the
@@ -190,6 +216,9 @@ size_t mpsb_predict_batched_workspace(int batch, int chi, int chip, int d);
 int mpsb_predict_theta_batched(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
                                const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream);
 
+int mpsb_predict_theta_batched_real(int batch, int chi, int chip, int d, const void* A, const void* B, const double* S,
+                                    const double* S_prev_inv, void* theta, void* ws, size_t ws_bytes, void* stream);
+
 /* out[i * ldo + j] = s[i / group] * in[i * ldi + j]: the Lambda_l scaling `self.Sl[i][:, newaxis, ...] * theta`
  * (DMRG/MPS.py:446) of a tensor viewed as a (chi_l * group) x cols matrix.  Used by the multi-site update
  * (MPS.update_k, DMRG/MPS.py:459-461), whose splits have unequal local dimensions on the two sides. */
@@ -200,6 +229,9 @@ int mpsb_scale_rows(int rows, int cols, const void* in, int ldi, const double* s
 int mpsb_transpose(int rows, int cols, const void* in, int ldi, void* out, int ldo, int conj, void* stream);
 int mpsb_transpose_batched(int batch, int rows, int cols, const void* in, int ldi, long long s_in, void* out, int ldo,
                            long long s_out, int conj, void* stream);
+
+int mpsb_transpose_batched_real(int batch, int rows, int cols, const void* in, int ldi, long long s_in, void* out, int ldo,
+                                long long s_out, void* stream);
 
 /* Diagnostics of the last SVD call on this thread: number of Jacobi sweeps of the slowest problem. */
 int mpsb_last_svd_sweeps(void);
