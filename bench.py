@@ -116,9 +116,10 @@ def idmrg_leg(with_cpu):
     from dmrg_b200 import iDMRG, _lib as L
     from dmrg_b200.MPO import MPO
     W = (-MPO('sx') - MPO('sz') ** 2).tomatrix()
-    out = {"model": "TFIM g=J=1, d=2, w=3, complex128", "unit": "ms per next_LR"}
+    out = {"model": "TFIM g=J=1, d=2, w=3, real MPO -> real arithmetic (DGEMM on DMMA); *_complex legs force complex128",
+           "unit": "ms per next_LR"}
     for chi in (32, 128):
-        Ld, Rd, Wd = L.to_device(np.array([[[0, 0, 1]]])), L.to_device(np.array([[[1, 0, 0]]])), L.to_device(W)
+        Ld, Rd, Wd = iDMRG._to_device_auto(True, np.array([[[0, 0, 1]]]), np.array([[[1, 0, 0]]]), W)
         times, nmv = [], []
         for i in range(16):
             torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -138,9 +139,11 @@ def idmrg_leg(with_cpu):
         w, d = Wm.shape[0], Wm.shape[2]
         nmv = statistics.mean(ch.n_matvec[-tail:])
         sec = statistics.mean(times[-tail:])
-        flop = 8.0 * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
+        c = 2.0 if ch.real else 8.0          # flops per multiply-add, real / complex
+        flop = c * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
         return {"ms": 1e3 * sec, "matvecs": nmv, "bond": int(ch.A.shape[2]), "one_minus_fidelity": 1 - ch.fidelity[-1],
-                "e_bond": ch.energy_per_site(), "contraction_tflops": flop / sec / 1e12}
+                "e_bond": ch.energy_per_site(), "contraction_tflops": flop / sec / 1e12,
+                "arithmetic": "real (c = 2)" if ch.real else "complex (c = 8)"}
     for chi in (32, 128):
         out[f"chi{chi}_predict"] = chain_leg(W, chi, 16, 6)
     from dmrg_b200 import spin
@@ -152,8 +155,14 @@ def idmrg_leg(with_cpu):
     ak = chain_leg(Wa, 64, 10, 3)
     ak.update(model="AKLT spin-1 (config 2), d=3, w=%d" % Wa.shape[0], e_bond_error=abs(ak["e_bond"] + 2.0 / 3.0))
     out["aklt_chi64_predict"] = ak
-    out["heisenberg_chi1024_predict"] = dict(chain_leg(Wh, 1024, 13, 2), model="Heisenberg (config 5), d=2, w=5, complex128 arithmetic",
-                                             note="contraction_tflops counts complex flops (SURVEY 8d F_iDMRG-step, c = 8)")
+    out["heisenberg_chi1024_predict"] = dict(chain_leg(Wh, 1024, 13, 2), model="Heisenberg (config 5), d=2, w=5, real MPO",
+                                             note="contraction_tflops on SURVEY 8d's F_iDMRG-step with c = 2 (real arithmetic)")
+    iDMRG.REAL_PATH = False                  # the same run forced through the complex128 kernels, for comparison
+    try:
+        out["chi128_predict_complex"] = chain_leg(W, 128, 16, 6)
+        out["heisenberg_chi1024_predict_complex"] = chain_leg(Wh, 1024, 13, 2)
+    finally:
+        iDMRG.REAL_PATH = True
     if with_cpu:
         from threadpoolctl import threadpool_limits
         from oracle import idmrg_oracle as io_
@@ -189,15 +198,17 @@ def idmrg_batch_leg(n_chains=256, chi=128):
     w, d = 3, 2
     # the batched H_eff product alone (DMRG/iDMRG.py:38-40 + the dense matvec inside eigsh, :57), CUDA events
     lib = L_.load()
-    theta = torch.randn((n_chains, chi, d, d, chi), dtype=torch.complex128, device=run.L.device)
+    theta = torch.randn((n_chains, chi, d, d, chi), dtype=torch.float64 if run.real else torch.complex128, device=run.L.device)
     out = torch.empty_like(theta)
     nel = chi * d * d * chi
     ws, wsn = L_.workspace(lib.mpsb_heff_batched_workspace(n_chains, chi, chi, d, w))
+    mv = lib.mpsb_heff_matvec_batched_real if run.real else lib.mpsb_heff_matvec_batched
+    c = 2.0 if run.real else 8.0             # flops per multiply-add, real / complex
 
     def matvec():
-        L_.check(lib.mpsb_heff_matvec_batched(n_chains, chi, chi, d, w, L_.ptr(run.L), chi * chi * w, L_.ptr(run.W), w * w * d * d,
-                                              L_.ptr(run.R), chi * chi * w, L_.ptr(theta), nel, L_.ptr(out), nel, ws, wsn,
-                                              L_.stream_ptr()), "mpsb_heff_matvec_batched")
+        L_.check(mv(n_chains, chi, chi, d, w, L_.ptr(run.L), chi * chi * w, L_.ptr(run.W), w * w * d * d,
+                    L_.ptr(run.R), chi * chi * w, L_.ptr(theta), nel, L_.ptr(out), nel, ws, wsn,
+                    L_.stream_ptr()), "mpsb_heff_matvec_batched")
     for _ in range(3):
         matvec()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -206,17 +217,19 @@ def idmrg_batch_leg(n_chains=256, chi=128):
         matvec()
     e1.record(); torch.cuda.synchronize()
     mv_ms = e0.elapsed_time(e1) / 20
-    mv_flop = n_chains * 8.0 * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2)
+    mv_flop = n_chains * c * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2)
     nmv = statistics.mean(run.n_matvec[-2:])
     sec = statistics.mean(times[-2:])
-    flop = n_chains * 8.0 * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
+    flop = n_chains * c * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
     e = run.energy_per_site()
-    return {"workload": f"{n_chains} TFIM chains, g/J = 0.2 .. 2.0, chi = {chi}, d = 2, w = 3, complex128, lock-step growth",
+    return {"workload": f"{n_chains} TFIM chains, g/J = 0.2 .. 2.0, chi = {chi}, d = 2, w = 3, "
+                        f"{'real arithmetic (real MPO)' if run.real else 'complex128'}, lock-step growth",
+            "flops_per_multiply_add": c,
             "ms_per_growth_step": 1e3 * sec, "chain_steps_per_s": n_chains / sec, "matvecs_per_step": nmv,
             "contraction_tflops": flop / sec / 1e12,
             "matvec_only": {"ms": mv_ms, "tflops": mv_flop / (mv_ms * 1e-3) / 1e12,
-                            "note": "mpsb_heff_matvec_batched alone (incl. its per-call MPO / environment preparation), "
-                                    "SURVEY 8(d) flops 8 (2 w d^2 chi^3 + 2 w^2 d^3 chi^2) per chain"},
+                            "note": "mpsb_heff_matvec_batched(_real) alone (incl. its per-call MPO / environment preparation), "
+                                    "SURVEY 8(d) flops c (2 w d^2 chi^3 + 2 w^2 d^3 chi^2) per chain"},
             "e_site_g0.2": float(e[0]), "e_site_g2.0": float(e[-1]),
             "e_site_g1_exact": -4.0 / np.pi}
 

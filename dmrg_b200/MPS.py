@@ -40,23 +40,28 @@ def svd_truncate(m, trun=20, err=1e-10):
 
 
 def _device_svd(a_dev, rows, cols, trun, err, want_u, normalise=1):
-    """mpsb_svd_trunc on one device matrix; returns device tensors cut to the rank (one sync)."""
+    """mpsb_svd_trunc on one device matrix; returns device tensors cut to the rank (one sync).  A real (float64)
+    matrix goes through mpsb_svd_trunc_real and comes back as real factors."""
     lib = _lib.load()
+    real = not a_dev.is_complex()
+    dt = "f64" if real else "c128"
     kcap = max(1, min(rows, cols, max(int(trun), 1)))
-    vh = _lib.empty((kcap, cols))
-    uh = _lib.empty((kcap, rows)) if want_u else None
+    vh = _lib.empty((kcap, cols), dt)
+    uh = _lib.empty((kcap, rows), dt) if want_u else None
     s = _lib.empty((kcap,), "f64")
     sraw = _lib.empty((min(rows, cols),), "f64")
     rank = _lib.empty((1,), "i32")
-    ws, wsn = _lib.workspace(lib.mpsb_svd_trunc_workspace(1, rows, cols, int(want_u)))
-    _lib.check(lib.mpsb_svd_trunc(1, rows, cols, _lib.ptr(a_dev), cols, 0, int(trun), float(err), int(normalise), kcap,
-                                  _lib.ptr(vh), _lib.ptr(uh), _lib.ptr(s), _lib.ptr(sraw), _lib.ptr(rank), ws, wsn,
-                                  _lib.stream_ptr()), "mpsb_svd_trunc")
+    wsq, fn = (lib.mpsb_svd_trunc_real_workspace, lib.mpsb_svd_trunc_real) if real else (lib.mpsb_svd_trunc_workspace,
+                                                                                         lib.mpsb_svd_trunc)
+    ws, wsn = _lib.workspace(wsq(1, rows, cols, int(want_u)))
+    _lib.check(fn(1, rows, cols, _lib.ptr(a_dev), cols, 0, int(trun), float(err), int(normalise), kcap,
+                  _lib.ptr(vh), _lib.ptr(uh), _lib.ptr(s), _lib.ptr(sraw), _lib.ptr(rank), ws, wsn,
+                  _lib.stream_ptr()), "mpsb_svd_trunc")
     k = int(rank.item())
     _lib.warn_if_unconverged("svd_truncate")
     u = None
     if want_u:
-        u = _lib.conj_transpose(uh[:k]) if k else _lib.empty((rows, 0))
+        u = _lib.conj_transpose(uh[:k]) if k else _lib.empty((rows, 0), dt)
     if normalise:
         return u, s[:k], vh[:k], k
     return u, sraw, vh[:k], k

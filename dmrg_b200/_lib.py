@@ -29,6 +29,8 @@ SIGNATURES = {
     "mpsb_dgemm": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _i, _vp]),
     "mpsb_svd_trunc_workspace": (_sz, [_i, _i, _i, _i]),
     "mpsb_svd_trunc": (_i, [_i, _i, _i, _vp, _i, _ll, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mpsb_svd_trunc_real_workspace": (_sz, [_i, _i, _i, _i]),
+    "mpsb_svd_trunc_real": (_i, [_i, _i, _i, _vp, _i, _ll, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_tebd_two_site_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "mpsb_tebd_two_site": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _d, _i, _vp, _ll,
                                 _vp, _ll, _vp, _ll, _vp, _vp, _sz, _vp]),
@@ -265,6 +267,12 @@ def matmul(A, B, opA=OP_N, opB=OP_N):
 def conj_transpose(A, conj=True):
     """(rows x cols) device matrix -> its (conjugate) transpose, through the library's tile-transpose kernel."""
     rows, cols = A.shape
+    if not A.is_complex():
+        out = empty((cols, rows), "f64")
+        if rows and cols:
+            check(load().mpsb_transpose_batched_real(1, rows, cols, ptr(A), cols, 0, ptr(out), rows, 0, stream_ptr()),
+                  "mpsb_transpose_batched_real")
+        return out
     out = empty((cols, rows))
     if rows and cols:
         check(load().mpsb_transpose(rows, cols, ptr(A), cols, ptr(out), rows, int(conj), stream_ptr()), "mpsb_transpose")

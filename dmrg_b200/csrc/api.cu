@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <utility>
 #include "../../include/mpsb.h"
@@ -195,6 +196,73 @@ int mpsb_svd_trunc(int batch, int rows, int cols, const void* A, int lda, long l
     o.s_raw = S_raw; o.n_raw = rows < cols ? rows : cols; o.s_raw_stride = o.n_raw;
     o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = normalise;
     return svd_finalise(pl, X, state, o, st);
+}
+
+// Real matrices (the real iDMRG path): QR on the unpacked work matrix (zero imaginary parts stay zero), then the
+// Jacobi sweeps on the copy with adjacent columns packed pairwise into complex elements - half the row length, real
+// rotations - and a finalise that writes arrays of doubles.
+namespace {
+struct SvdRealLayout {
+    SvdPlan qr, jac;           // unpacked (QR) and packed (sweeps) plans
+    int ldot_c, ltot_c;        // unpacked widths, rounded up to even
+    size_t X, Xp, state, total;
+};
+int svd_real_layout(int batch, int rows, int cols, int want_u, SvdRealLayout* L) {
+    L->ldot_c = round_up(cols, 2);
+    L->ltot_c = L->ldot_c + (want_u ? round_up(rows, 2) : 0);
+    int rc = svd_make_plan(batch, rows, L->ldot_c, L->ltot_c, &L->qr);
+    if (rc) return rc;
+    rc = svd_make_plan(batch, rows, L->ldot_c / 2, L->ltot_c / 2, &L->jac);
+    if (rc) return rc;
+    L->qr.phase = 1;
+    L->jac.phase = 2;
+    L->jac.real = 1;
+    L->jac.qr_grid = 0;
+    L->X = al((size_t)L->qr.n_pad * L->qr.ld * sizeof(cplx) * batch);
+    L->Xp = al((size_t)L->jac.n_pad * L->jac.ld * sizeof(cplx) * batch);
+    L->state = al(std::max(svd_state_bytes(L->qr), svd_state_bytes(L->jac)));
+    L->total = L->X + L->Xp + L->state;
+    return 0;
+}
+}  // namespace
+
+size_t mpsb_svd_trunc_real_workspace(int batch, int rows, int cols, int want_u) {
+    SvdRealLayout L;
+    if (svd_real_layout(batch, rows, cols, want_u, &L)) return 0;
+    return L.total;
+}
+
+int mpsb_svd_trunc_real(int batch, int rows, int cols, const void* A, int lda, long long sA, int trun, double err,
+                        int normalise, int k_cap, void* Vh, void* Uh, double* S, double* S_raw, int* rank, void* ws,
+                        size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(batch >= 1 && rows >= 1 && cols >= 1 && k_cap >= 1 && trun >= 0, "svd_trunc_real: bad arguments");
+    SvdRealLayout L;
+    int rc = svd_real_layout(batch, rows, cols, Uh ? 1 : 0, &L);
+    if (rc) return rc;
+    MPSB_REQUIRE(ws && ws_bytes >= L.total, "svd_trunc_real: workspace %zu B < required %zu B", ws_bytes, L.total);
+    Arena ar(ws, ws_bytes);
+    cplx* X = static_cast<cplx*>(ar.take(L.X));
+    cplx* Xp = static_cast<cplx*>(ar.take(L.Xp));
+    void* state = ar.take(L.state);
+    rc = pack_real_matrix(X, L.qr.n_pad, L.qr.ld, rows, cols, L.ldot_c, static_cast<const double*>(A), lda, sA, Uh ? 1 : 0, st,
+                          batch);
+    if (rc) return rc;
+    rc = svd_orthogonalise(L.qr, X, state, st, nullptr);
+    if (rc) return rc;
+    rc = compact_real_pairs(X, L.qr.n_pad, L.qr.ld, rows, Xp, L.jac.n_pad, L.jac.ld, L.jac.ltot, st, batch);
+    if (rc) return rc;
+    rc = svd_orthogonalise(L.jac, Xp, state, st, &g_last_sweeps);
+    if (rc) return rc;
+    SvdOutputs o;
+    memset(&o, 0, sizeof(o));
+    o.real = 1; o.real_cols = cols; o.real_naug = Uh ? rows : 0;
+    o.vh = static_cast<cplx*>(Vh); o.vh_stride = (long long)k_cap * cols; o.vh_ld = cols;
+    o.aug = static_cast<cplx*>(Uh); o.aug_stride = (long long)k_cap * rows; o.aug_ld = rows; o.aug_conj = 0;
+    o.s = S; o.s_stride = k_cap;
+    o.s_raw = S_raw; o.n_raw = rows < cols ? rows : cols; o.s_raw_stride = o.n_raw;
+    o.rank = rank; o.k_cap = k_cap; o.trun = trun; o.err = err; o.normalise = normalise;
+    return svd_finalise(L.jac, Xp, state, o, st);
 }
 
 // ---- update_double -------------------------------------------------------------------------------------

@@ -37,6 +37,39 @@ pack_kernel(cplx* __restrict__ X, int n_pad, int ld, int rows, int ldot, int lto
     X[(size_t)b * n_pad * ld + e] = v;
 }
 
+// Real path of the SVD (mpsb_svd_trunc_real): the real matrix enters the complex work matrix with a zero imaginary
+// part (the QR kernels then stay real, every product with an exact zero being zero) ...
+__global__ void __launch_bounds__(256)
+pack_real_kernel(cplx* __restrict__ X, int n_pad, int ld, int rows, int cols, int ldot, const double* __restrict__ A,
+                 int lda, long long sA, int identity) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_pad * ld) return;
+    const int b = blockIdx.y;
+    const int j = (int)(e % ld), i = (int)(e / ld);
+    double v = 0.0;
+    if (i < rows) {
+        if (j < cols) v = A[(size_t)b * sA + (size_t)i * lda + j];
+        else if (identity && j == ldot + i) v = 1.0;
+    }
+    X[(size_t)b * n_pad * ld + e] = make_double2(v, 0.0);
+}
+// ... and after the QR adjacent columns are packed into one complex element each for the Jacobi sweeps, which halves
+// the row length (and lets rotate_pair & co. run real rotations on the packed rows).
+__global__ void __launch_bounds__(256)
+compact_pairs_kernel(const cplx* __restrict__ X, int n_pad, int ld, int rows, cplx* __restrict__ Xp, int n_pad_p, int ld_p,
+                     int ltot_p) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_pad_p * ld_p) return;
+    const int b = blockIdx.y;
+    const int j = (int)(e % ld_p), i = (int)(e / ld_p);
+    cplx v = make_double2(0.0, 0.0);
+    if (i < rows && j < ltot_p) {
+        const double4 two = *reinterpret_cast<const double4*>(X + (size_t)b * n_pad * ld + (size_t)i * ld + 2 * j);
+        v = make_double2(two.x, two.z);
+    }
+    Xp[(size_t)b * n_pad_p * ld_p + e] = v;
+}
+
 // 32x32 tile transpose through shared memory (padded against bank conflicts).
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -151,6 +184,28 @@ int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, c
     MPSB_REQUIRE(batch >= 1 && batch <= 65535, "pack: batch %d exceeds grid.y", batch);
     dim3 grid((unsigned)((total + 255) / 256), batch);
     pack_kernel<<<grid, 256, 0, st>>>(X, n_pad, ld, rows, ldot, ltot, dot, aug, identity);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pack_real_matrix(cplx* X, int n_pad, int ld, int rows, int cols, int ldot, const double* A, int lda, long long sA,
+                     int identity, cudaStream_t st, int batch) {
+    const long long total = (long long)n_pad * ld;
+    MPSB_REQUIRE(batch >= 1 && batch <= 65535, "pack: batch %d exceeds grid.y", batch);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    pack_real_kernel<<<grid, 256, 0, st>>>(X, n_pad, ld, rows, cols, ldot, A, lda, sA, identity);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int compact_real_pairs(const cplx* X, int n_pad, int ld, int rows, cplx* Xp, int n_pad_p, int ld_p, int ltot_p,
+                       cudaStream_t st, int batch) {
+    const long long total = (long long)n_pad_p * ld_p;
+    MPSB_REQUIRE(batch >= 1 && batch <= 65535 && 2 * ltot_p <= ld, "compact: bad batch %d / widths %d, %d", batch, ltot_p, ld);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    compact_pairs_kernel<<<grid, 256, 0, st>>>(X, n_pad, ld, rows, Xp, n_pad_p, ld_p, ltot_p);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;

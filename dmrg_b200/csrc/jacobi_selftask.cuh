@@ -80,7 +80,7 @@ struct __align__(16) SelfSmem {
 
 template <int CPL, bool EXACT, int KIND, int T>
 __device__ __forceinline__ void sg_step(cplx (&x)[8][CPL], const bool (&indot)[CPL], SelfSmem& sm, int sg, int wsg,
-                                        int lane, int duty, double tol2) {
+                                        int lane, int duty, double tol2, bool real) {
     // ---- A. partial inner products of this lane's columns, the 4 pairs of the step ------------------------------
     double v[8];
 #pragma unroll
@@ -110,7 +110,7 @@ __device__ __forceinline__ void sg_step(cplx (&x)[8][CPL], const bool (&indot)[C
             const double2 s0 = *reinterpret_cast<const double2*>(&sm.part[sg][0][2 * lane]);
             const double2 s1 = *reinterpret_cast<const double2*>(&sm.part[sg][1][2 * lane]);
             a = sm.a[sg][p]; b = sm.a[sg][q]; ep = sm.e[sg][p]; eq = sm.e[sg][q];
-            const double crs = s0.x + s1.x, cis = s0.y + s1.y;
+            const double crs = s0.x + s1.x, cis = real ? 0.0 : s0.y + s1.y;   // real: packed real rows (rotate_pair)
             ac2 = (ep * eq) * fma(crs, crs, cis * cis);              // |c|^2 of the true rows
             double tpr = 0.0, tpi = 0.0, sqr = 0.0, sqi = 0.0;
             if (ac2 > fma(tol2 * a, b, PAIR_FLOOR)) {
@@ -180,7 +180,7 @@ __device__ __forceinline__ void sg_step(cplx (&x)[8][CPL], const bool (&indot)[C
 template <int CPL, bool EXACT>
 __device__ __forceinline__ void selftask_body(cplx* __restrict__ X, int ld, int ldot, int ltot_r, int bA, int bB,
                                               int* __restrict__ rot_mat, double tol2, int* __restrict__ stp, int unit,
-                                              int launch_id) {
+                                              int launch_id, bool real) {
     __shared__ SelfSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, sg = w >> 1, wsg = w & 1;
     if (stp) {                                               // verified clean since both blocks last changed
@@ -222,13 +222,13 @@ __device__ __forceinline__ void selftask_body(cplx* __restrict__ X, int ld, int 
     }
     __syncthreads();        // part[] is rewritten by the first step
 
-    sg_step<CPL, EXACT, 1, 0>(x, indot, sm, sg, wsg, lane, 0, tol2);
-    sg_step<CPL, EXACT, 1, 1>(x, indot, sm, sg, wsg, lane, 1, tol2);
-    sg_step<CPL, EXACT, 1, 2>(x, indot, sm, sg, wsg, lane, 0, tol2);
-    sg_step<CPL, EXACT, 0, 0>(x, indot, sm, sg, wsg, lane, 1, tol2);
-    sg_step<CPL, EXACT, 0, 1>(x, indot, sm, sg, wsg, lane, 0, tol2);
-    sg_step<CPL, EXACT, 0, 2>(x, indot, sm, sg, wsg, lane, 1, tol2);
-    sg_step<CPL, EXACT, 0, 3>(x, indot, sm, sg, wsg, lane, 0, tol2);
+    sg_step<CPL, EXACT, 1, 0>(x, indot, sm, sg, wsg, lane, 0, tol2, real);
+    sg_step<CPL, EXACT, 1, 1>(x, indot, sm, sg, wsg, lane, 1, tol2, real);
+    sg_step<CPL, EXACT, 1, 2>(x, indot, sm, sg, wsg, lane, 0, tol2, real);
+    sg_step<CPL, EXACT, 0, 0>(x, indot, sm, sg, wsg, lane, 1, tol2, real);
+    sg_step<CPL, EXACT, 0, 1>(x, indot, sm, sg, wsg, lane, 0, tol2, real);
+    sg_step<CPL, EXACT, 0, 2>(x, indot, sm, sg, wsg, lane, 1, tol2, real);
+    sg_step<CPL, EXACT, 0, 3>(x, indot, sm, sg, wsg, lane, 0, tol2, real);
     __syncthreads();         // all bookkeeping of both sub-groups is in shared memory
 
     const int dirty = sm.dirty[sg];

@@ -816,8 +816,11 @@ __device__ __forceinline__ void jacobi_angle(double a, double b, double cr, doub
 // the butterfly reduction leaves bit-identical sums in every lane.
 // Fast path (ltot_r <= 256): both rows are pulled into registers once (8 complex per lane per row, all
 // loads in flight together), the inner products and the rotation run from registers.
+// real: the rows hold a REAL matrix with adjacent column pairs packed into one complex element; a left rotation by a
+// real matrix acts on both halves alike, the real inner product is the real part of the complex one, and a zero
+// imaginary part makes every term with gi below vanish - the real Jacobi rotation, bit for bit.
 __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restrict__ Q, int ldot, int ltot_r,
-                                           double F2, double tol2, double eabs2, int lane) {
+                                           double F2, double tol2, double eabs2, int lane, bool real = false) {
     (void)F2; (void)eabs2;
     if (ltot_r <= 256) {
         cplx x[8], y[8];
@@ -844,7 +847,7 @@ __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restric
             }
         }
         const double a = warp_sum(a0 + a1), b = warp_sum(b0 + b1);
-        const double cr = warp_sum(cr0 + cr1), ci = warp_sum(ci0 + ci1);
+        const double cr = warp_sum(cr0 + cr1), ci = real ? 0.0 : warp_sum(ci0 + ci1);
         const double ac2 = cr * cr + ci * ci;
         if (!(ac2 > fma(tol2 * a, b, PAIR_FLOOR))) return 0;
         double cs, gr, gi;
@@ -872,7 +875,7 @@ __device__ __forceinline__ int rotate_pair(cplx* __restrict__ P, cplx* __restric
         cr = fma(x.x, y.x, fma(x.y, y.y, cr));     // x * conj(y)
         ci = fma(x.y, y.x, fma(-x.x, y.y, ci));
     }
-    a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
+    a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = real ? 0.0 : warp_sum(ci);
     const double ac2 = cr * cr + ci * ci;
     if (!(ac2 > fma(tol2 * a, b, PAIR_FLOOR))) return 0;
     double cs, gr, gi;
@@ -898,7 +901,7 @@ __global__ void __launch_bounds__(32 * B)
 jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r,
                     int nblk, int round, int full, int inner_sweeps, const double* __restrict__ frob2,
                     int* __restrict__ rot, const int* __restrict__ done, double tol2, double eabs2,
-                    unsigned long long* __restrict__ phase_clk) {
+                    unsigned long long* __restrict__ phase_clk, int real) {
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rows = reinterpret_cast<cplx*>(smraw);            // [2B][ltot_r]
     const long long t_start = phase_clk ? clock64() : 0;
@@ -936,14 +939,14 @@ jacobi_round_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
                 int p, q;
                 rr_pair(2 * B, s, w, p, q);
                 nrot += rotate_pair(rows + (size_t)p * ltot_r, rows + (size_t)q * ltot_r, ldot, ltot_r, F2, tol2,
-                                    eabs2, lane);
+                                    eabs2, lane, real != 0);
                 __syncthreads();
             }
         } else {
             for (int s = 0; s < B; ++s) {
                 const int p = w, q = B + ((w + s) % B);
                 nrot += rotate_pair(rows + (size_t)p * ltot_r, rows + (size_t)q * ltot_r, ldot, ltot_r, F2, tol2,
-                                    eabs2, lane);
+                                    eabs2, lane, real != 0);
                 __syncthreads();
             }
         }
@@ -1007,7 +1010,9 @@ struct RegRow {
 // FULL: all 256 columns take part in the inner product (no per-column predicates in the hot loop).
 // sort: de Rijk's rule - if the rotation leaves the register row (lower block) with the smaller norm, the two
 // results trade places (free: only the names of the registers change).
-template <bool FULL>
+// REAL: rows of a real matrix with column pairs packed into complex elements (see rotate_pair): the inner product
+// keeps its real part only and the rotation parameters are real - 6 instead of 12 FMAs per packed column.
+template <bool FULL, bool REAL>
 __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, double& eq, double& bq, int ldot,
                                           double tol2, int lane, bool sort) {
     double cr0 = 0.0, ci0 = 0.0, cr1 = 0.0, ci1 = 0.0;
@@ -1015,14 +1020,14 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
     for (int j = 0; j < 8; j += 2) {
         if (FULL || lane + 32 * j < ldot) {
             cr0 = fma(r.x[j].x, y[j].x, fma(r.x[j].y, y[j].y, cr0));
-            ci0 = fma(r.x[j].y, y[j].x, fma(-r.x[j].x, y[j].y, ci0));
+            if (!REAL) ci0 = fma(r.x[j].y, y[j].x, fma(-r.x[j].x, y[j].y, ci0));
         }
         if (FULL || lane + 32 * (j + 1) < ldot) {
             cr1 = fma(r.x[j + 1].x, y[j + 1].x, fma(r.x[j + 1].y, y[j + 1].y, cr1));
-            ci1 = fma(r.x[j + 1].y, y[j + 1].x, fma(-r.x[j + 1].x, y[j + 1].y, ci1));
+            if (!REAL) ci1 = fma(r.x[j + 1].y, y[j + 1].x, fma(-r.x[j + 1].x, y[j + 1].y, ci1));
         }
     }
-    const double crs = warp_sum(cr0 + cr1), cis = warp_sum(ci0 + ci1);      // scaled inner product x_p . x_q^H
+    const double crs = warp_sum(cr0 + cr1), cis = REAL ? 0.0 : warp_sum(ci0 + ci1);   // scaled inner product x_p . x_q^H
     const double ac2 = r.e * eq * fma(crs, crs, cis * cis);                  // |c|^2 of the true rows
     if (!(ac2 > fma(tol2 * r.a, bq, PAIR_FLOOR))) return 0;
     // t/|c| = sgn(z) / (|z| + sqrt(z^2 + |c|^2)) from MUFU seeds + one Newton step each; the tangent may be
@@ -1052,10 +1057,17 @@ __device__ __forceinline__ int cross_pair(RegRow& r, cplx (&y)[8], double& dq, d
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const cplx xo = r.x[j], yo = y[j];
-        r.x[j].x = fma(-tpr, yo.x, fma(tpi, yo.y, xo.x));
-        r.x[j].y = fma(-tpr, yo.y, fma(-tpi, yo.x, xo.y));
-        y[j].x = fma(sqr, xo.x, fma(-sqi, xo.y, yo.x));
-        y[j].y = fma(sqr, xo.y, fma(sqi, xo.x, yo.y));
+        if (REAL) {
+            r.x[j].x = fma(-tpr, yo.x, xo.x);
+            r.x[j].y = fma(-tpr, yo.y, xo.y);
+            y[j].x = fma(sqr, xo.x, yo.x);
+            y[j].y = fma(sqr, xo.y, yo.y);
+        } else {
+            r.x[j].x = fma(-tpr, yo.x, fma(tpi, yo.y, xo.x));
+            r.x[j].y = fma(-tpr, yo.y, fma(-tpi, yo.x, xo.y));
+            y[j].x = fma(sqr, xo.x, fma(-sqi, xo.y, yo.x));
+            y[j].y = fma(sqr, xo.y, fma(sqi, xo.x, yo.y));
+        }
     }
     // de Rijk's rule: the register row (lower block) keeps the larger norm.  With rows that start sorted (pivoted QR)
     // this fires for well under 1 % of the rotations of the first sweeps and never later; the caller then exchanges
@@ -1087,7 +1099,7 @@ __device__ __forceinline__ void swap_rows_via_smem(RegRow& r, cplx (&y)[8], cplx
     }
 }
 
-template <bool FULL>
+template <bool FULL, bool REAL>
 __global__ void __launch_bounds__(CROSS_THREADS, MPSB_CROSS_MINBLOCKS)
 jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                     int round, int* __restrict__ rot, const int* __restrict__ done, double tol2,
@@ -1172,9 +1184,9 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
             y[j] = (FULL || c < ltot_r) ? rq[c] : make_double2(0.0, 0.0);
         }
         double dq = dqs[q], eq = eqs[q], bq = nq[q];
-        int n0 = cross_pair<FULL>(r0, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
+        int n0 = cross_pair<FULL, REAL>(r0, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
         if (n0 == 2) { swap_rows_via_smem<FULL>(r0, y, rq, ltot_r, lane); n0 = 1; }
-        int n1 = cross_pair<FULL>(r1, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
+        int n1 = cross_pair<FULL, REAL>(r1, y, dq, eq, bq, ldot, tol2, lane, modulus != 0);
         if (n1 == 2) { swap_rows_via_smem<FULL>(r1, y, rq, ltot_r, lane); n1 = 1; }
         nrot += n0 + n1;
         // Even rows of block J are visited in even steps, odd rows in odd steps, so steps 6 and 7 are the last
@@ -1248,13 +1260,14 @@ template <int CPL, bool EXACT>
 __global__ void __launch_bounds__(128, 3)
 jacobi_self_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk, int round,
                    int* __restrict__ rot, const int* __restrict__ done, double tol2, int* __restrict__ stamps,
-                   int stamp_stride, int launch_id) {
+                   int stamp_stride, int launch_id, int real) {
     const int mat = mat0 + blockIdx.x;
     if (done[mat]) return;
     cplx* X = Xall + (size_t)mat * strideX;
     int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
     const int bA = round >> 1, bB = bA + (nblk >> 1);
-    selftask_body<CPL, EXACT>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, stamp_self_index(nblk, bA), launch_id);
+    selftask_body<CPL, EXACT>(X, ld, ldot, ltot_r, bA, bB, rot + mat, tol2, stp, stamp_self_index(nblk, bA), launch_id,
+                              real != 0);
 }
 
 // ---- Gram-assisted round (block of 16 rows per CTA, FP64 tensor cores) -------------------------------
@@ -1352,6 +1365,9 @@ __device__ __forceinline__ int gram_tournament(GramSmem& sm, int nsteps, double 
     return nrot;
 }
 
+// REAL (both Gram kernels): packed real rows (see rotate_pair) - G keeps its real part (2 of the 4 DMMAs of phase A),
+// the tournament then produces a real Q, and phase C drops the 2 DMMAs that carry Im Q.
+template <bool REAL>
 __global__ void __launch_bounds__(GRAM_THREADS, 3)
 jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                    int round, int inner_sweeps, int* __restrict__ rot, const int* __restrict__ done, double tol2,
@@ -1415,8 +1431,10 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
                 if (4 * ks + t >= ldot) { a = make_double2(0.0, 0.0); b = make_double2(0.0, 0.0); }
                 dmma884(re0, re1, a.x, b.x);
                 dmma884(re0, re1, a.y, b.y);
-                dmma884(im0, im1, a.y, b.x);
-                dmma884(im0, im1, -a.x, b.y);
+                if (!REAL) {
+                    dmma884(im0, im1, a.y, b.x);
+                    dmma884(im0, im1, -a.x, b.y);
+                }
             }
             cplx* dst = khalf == 0 ? &sm.G[8 * ti + g][8 * tj + 2 * t] : &sm.Q[8 * ti + g][8 * tj + 2 * t];
             dst[0] = make_double2(re0, im0);
@@ -1466,9 +1484,11 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         dmma884(cre[mt][0], cre[mt][1], af[mt][ks].x, bf[ks].x);
-                        dmma884(cre[mt][0], cre[mt][1], -af[mt][ks].y, bf[ks].y);
                         dmma884(cim[mt][0], cim[mt][1], af[mt][ks].x, bf[ks].y);
-                        dmma884(cim[mt][0], cim[mt][1], af[mt][ks].y, bf[ks].x);
+                        if (!REAL) {
+                            dmma884(cre[mt][0], cre[mt][1], -af[mt][ks].y, bf[ks].y);
+                            dmma884(cim[mt][0], cim[mt][1], af[mt][ks].y, bf[ks].x);
+                        }
                     }
                 __syncwarp();
 #pragma unroll
@@ -1518,6 +1538,7 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
 // re-reads every tile, applies Q^H and writes it back with an asynchronous bulk store that overlaps the next tile.
 // Traffic per CTA and round: 16 rows x (ldot + 2 ltot) x 16 B; one CTA per SM (140 KB of shared memory).
 constexpr int TILE_W = 256;
+template <bool REAL>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk,
                          int round, int inner_sweeps, int* __restrict__ rot, const int* __restrict__ done, double tol2,
@@ -1586,8 +1607,10 @@ jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, i
                     if (4 * ks + t >= lim) { a = make_double2(0.0, 0.0); b = make_double2(0.0, 0.0); }
                     dmma884(re0, re1, a.x, b.x);
                     dmma884(re0, re1, a.y, b.y);
-                    dmma884(im0, im1, a.y, b.x);
-                    dmma884(im0, im1, -a.x, b.y);
+                    if (!REAL) {
+                        dmma884(im0, im1, a.y, b.x);
+                        dmma884(im0, im1, -a.x, b.y);
+                    }
                 }
                 __syncthreads();                          // buffer free for the load issued two tiles ahead
             }
@@ -1643,9 +1666,11 @@ jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, i
 #pragma unroll
                         for (int mt = 0; mt < 2; ++mt) {
                             dmma884(cre[mt][0], cre[mt][1], af[mt][ks].x, bf[ks].x);
-                            dmma884(cre[mt][0], cre[mt][1], -af[mt][ks].y, bf[ks].y);
                             dmma884(cim[mt][0], cim[mt][1], af[mt][ks].x, bf[ks].y);
-                            dmma884(cim[mt][0], cim[mt][1], af[mt][ks].y, bf[ks].x);
+                            if (!REAL) {
+                                dmma884(cre[mt][0], cre[mt][1], -af[mt][ks].y, bf[ks].y);
+                                dmma884(cim[mt][0], cim[mt][1], af[mt][ks].y, bf[ks].x);
+                            }
                         }
                     __syncwarp();
 #pragma unroll
@@ -1685,7 +1710,8 @@ jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, i
 // shuffles, both rows in registers, NJ = row length / 32 columns per lane), the CTA synchronises between steps and
 // stops after the first sweep that applied no rotation.
 template <int NJ>
-__device__ __forceinline__ int rotate_rows(cplx* __restrict__ P, cplx* __restrict__ Q, int ldot, double tol2, int lane) {
+__device__ __forceinline__ int rotate_rows(cplx* __restrict__ P, cplx* __restrict__ Q, int ldot, double tol2, int lane,
+                                           bool real) {
     cplx x[NJ], y[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { x[j] = P[lane + 32 * j]; y[j] = Q[lane + 32 * j]; }     // pitch padding is zero
@@ -1699,7 +1725,7 @@ __device__ __forceinline__ int rotate_rows(cplx* __restrict__ P, cplx* __restric
             ci = fma(x[j].y, y[j].x, fma(-x[j].x, y[j].y, ci));
         }
     }
-    a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = warp_sum(ci);
+    a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr); ci = real ? 0.0 : warp_sum(ci);
     const double ac2 = cr * cr + ci * ci;
     if (!(ac2 > fma(tol2 * a, b, PAIR_FLOOR))) return 0;
     double cs, gr, gi;
@@ -1721,7 +1747,7 @@ template <int NJ>      // 1..8: columns per lane; 0: rows of any length, streame
 __global__ void __launch_bounds__((NJ >= 1 && NJ <= 4) ? 1024 : 512, 1)
 jacobi_resident_kernel(cplx* __restrict__ Xall, long long strideX, int n_pad, int ld, int ldot, int max_sweeps,
                        double tol2, unsigned long long* __restrict__ rot_total,
-                       unsigned long long* __restrict__ sweep_total, int* __restrict__ max_sweeps_seen) {
+                       unsigned long long* __restrict__ sweep_total, int* __restrict__ max_sweeps_seen, int real) {
     extern __shared__ __align__(128) unsigned char smraw[];
     cplx* rows = reinterpret_cast<cplx*>(smraw);            // [n_pad][ld]
     __shared__ __align__(8) uint64_t bar;
@@ -1754,8 +1780,8 @@ jacobi_resident_kernel(cplx* __restrict__ Xall, long long strideX, int n_pad, in
                 rr_pair(n_pad, s, slot, p, q);
                 cplx* P = rows + (size_t)p * ld;
                 cplx* Q = rows + (size_t)q * ld;
-                if (NJ > 0) nrot += rotate_rows<(NJ > 0 ? NJ : 1)>(P, Q, ldot, tol2, lane);
-                else nrot += rotate_pair(P, Q, ldot, ld, 0.0, tol2, 0.0, lane);
+                if (NJ > 0) nrot += rotate_rows<(NJ > 0 ? NJ : 1)>(P, Q, ldot, tol2, lane, real != 0);
+                else nrot += rotate_pair(P, Q, ldot, ld, 0.0, tol2, 0.0, lane, real != 0);
             }
             __syncthreads();
         }
@@ -1852,7 +1878,8 @@ finalise_kernel(const cplx* __restrict__ Xall, long long strideX, int n, int n_p
     }
     // truncation rule.  Reference `truncate` (DMRG/MPS.py:33-38): s /= s[0]; k = min(#(s > err), trun);
     // s = s[:k] / ||s[:k]||.   Reference `halve` (DMRG/iDMRG.py:26-31): k = min(trunc, S.size), raw S.
-    const int nsv = n < ldot ? n : ldot;
+    const int lcols = o.real ? o.real_cols : ldot;      // packed real rows: two real columns per element
+    const int nsv = n < lcols ? n : lcols;
     if (tid == 0) {
         const double s0 = key[0] > 0.0 ? sqrt(key[0]) : 0.0;
         int k = 0;
@@ -1887,6 +1914,19 @@ finalise_kernel(const cplx* __restrict__ Xall, long long strideX, int n, int n_p
         const bool keep = i < k && key[i] > ROW_DEAD;
         const cplx* row = X + (size_t)(keep ? idx[i] : 0) * ld;
         const double inv = keep ? 1.0 / sqrt(key[i]) : 0.0;
+        if (o.real) {
+            // packed real rows: double c of a row is real column c; outputs are arrays of doubles (strides in doubles)
+            const double* rr = reinterpret_cast<const double*>(row);
+            if (o.vh) {
+                double* dst = reinterpret_cast<double*>(o.vh) + (size_t)mat * o.vh_stride + (size_t)i * o.vh_ld;
+                for (int c = lane; c < o.real_cols; c += 32) dst[c] = keep ? rr[c] * inv : 0.0;
+            }
+            if (o.aug && o.real_naug > 0) {
+                double* dst = reinterpret_cast<double*>(o.aug) + (size_t)mat * o.aug_stride + (size_t)i * o.aug_ld;
+                for (int c = lane; c < o.real_naug; c += 32) dst[c] = keep ? rr[2 * ldot + c] : 0.0;
+            }
+            continue;
+        }
         if (o.vh) {
             cplx* dst = o.vh + (size_t)mat * o.vh_stride + (size_t)i * o.vh_ld;
             for (int c = lane; c < ldot; c += 32) {
@@ -1922,7 +1962,7 @@ int launch_round(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int co
     dim3 grid(nblk / 2, count);
     jacobi_round_kernel<B><<<grid, 32 * B, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
                                                       nblk, round, full, inner, s.frob2, s.rot, s.done, tol2, eabs2,
-                                                      g_prof.enabled > 1 ? s.phase_clk : nullptr);
+                                                      g_prof.enabled > 1 ? s.phase_clk : nullptr, pl.real);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1974,14 +2014,15 @@ int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int cou
                 double tol2, int launch_id, cudaStream_t st) {
     const int ltot_r = round_up(pl.ltot, 32);
     const size_t smem = gram_smem_bytes(ltot_r);
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_gram_kernel), smem)) return rc;
+    auto kern = pl.real ? jacobi_gram_kernel<true> : jacobi_gram_kernel<false>;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
     const int nblk = pl.n_pad / 8;
     dim3 grid(nblk / 2, count);
-    jacobi_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
-                                                        nblk, round, inner, s.rot, s.done, tol2,
-                                                        g_prof.enabled > 1 ? s.phase_clk : nullptr,
-                                                        nblk == pl.n_pad / pl.bsz ? s.stamps : nullptr, s.stamp_stride,
-                                                        launch_id);
+    kern<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
+                                          nblk, round, inner, s.rot, s.done, tol2,
+                                          g_prof.enabled > 1 ? s.phase_clk : nullptr,
+                                          nblk == pl.n_pad / pl.bsz ? s.stamps : nullptr, s.stamp_stride,
+                                          launch_id);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1994,15 +2035,23 @@ int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, i
                       double tol2, int launch_id, cudaStream_t st) {
     const int ltot_r = round_up(pl.ltot, 32);
     const size_t smem = gram_tiled_smem_bytes();
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(jacobi_gram_tiled_kernel), smem)) return rc;
+    auto kern = pl.real ? jacobi_gram_tiled_kernel<true> : jacobi_gram_tiled_kernel<false>;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
     const int nblk = pl.n_pad / 8;
     dim3 grid(nblk / 2, count);
-    jacobi_gram_tiled_kernel<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot,
-                                                              ltot_r, nblk, round, inner, s.rot, s.done, tol2, s.stamps,
-                                                              s.stamp_stride, launch_id);
+    kern<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot,
+                                          ltot_r, nblk, round, inner, s.rot, s.done, tol2, s.stamps,
+                                          s.stamp_stride, launch_id);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+typedef void (*CrossKernel)(cplx*, long long, int, int, int, int, int, int, int*, const int*, double, unsigned long long*,
+                            int*, int, int, int);
+CrossKernel cross_kernel_for(bool full, bool real) {
+    if (real) return full ? jacobi_cross_kernel<true, true> : jacobi_cross_kernel<false, true>;
+    return full ? jacobi_cross_kernel<true, false> : jacobi_cross_kernel<false, false>;
 }
 
 // Modulus ordering (rows of <= 256 columns, 8-row blocks): step `round` in [0, nblk) = one launch of the register-
@@ -2020,24 +2069,17 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
     unsigned long long* pc = g_prof.enabled > 1 ? s.phase_clk : nullptr;
     const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
     const bool full = (ltot_r == 256 && pl.ldot == 256);
-    if (int rc = ensure_dynamic_smem(full ? reinterpret_cast<const void*>(jacobi_cross_kernel<true>)
-                                          : reinterpret_cast<const void*>(jacobi_cross_kernel<false>), smem))
-        return rc;
+    auto kern = cross_kernel_for(full, pl.real != 0);
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
     dim3 grid(mod_cross_pairs(nblk, round), count);
-    if (full)
-        jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
-                                                                     s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride,
-                                                                     launch_id, 1);
-    else
-        jacobi_cross_kernel<false><<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
-                                                                      s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride,
-                                                                      launch_id, 1);
+    kern<<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, tol2, pc,
+                                           s.stamps, s.stamp_stride, launch_id, 1);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     if ((round & 1) == 0) {
 #define MPSB_SELF(CPL, EXACT)                                                                                              \
     jacobi_self_kernel<CPL, EXACT><<<count, 128, 0, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, \
-                                                          tol2, s.stamps, s.stamp_stride, launch_id)
+                                                          tol2, s.stamps, s.stamp_stride, launch_id, pl.real)
         if (full) MPSB_SELF(4, true);
         else if (ltot_r > 128) MPSB_SELF(4, false);
         else if (ltot_r > 64) MPSB_SELF(2, false);
@@ -2056,20 +2098,13 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
     if (cross_enabled && pl.bsz == 8 && ltot_r <= 256 && round > 0 && pl.n_pad / 8 > 2) {
         const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
         const bool full = (ltot_r == 256 && pl.ldot == 256);
-        if (int rc = ensure_dynamic_smem(full ? reinterpret_cast<const void*>(jacobi_cross_kernel<true>)
-                                              : reinterpret_cast<const void*>(jacobi_cross_kernel<false>), smem))
-            return rc;
+        auto kern = cross_kernel_for(full, pl.real != 0);
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
         const int nblk = pl.n_pad / 8;
         dim3 grid(nblk / 2, count);
         unsigned long long* pc = g_prof.enabled > 1 ? s.phase_clk : nullptr;
-        if (full)
-            jacobi_cross_kernel<true><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
-                                                                         pl.ldot, ltot_r, nblk, round, s.rot, s.done,
-                                                                         tol2, pc, s.stamps, s.stamp_stride, launch_id, 0);
-        else
-            jacobi_cross_kernel<false><<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld,
-                                                                          pl.ldot, ltot_r, nblk, round, s.rot, s.done,
-                                                                          tol2, pc, s.stamps, s.stamp_stride, launch_id, 0);
+        kern<<<grid, CROSS_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r, nblk, round,
+                                               s.rot, s.done, tol2, pc, s.stamps, s.stamp_stride, launch_id, 0);
         MPSB_COUNT_LAUNCH();
         MPSB_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -2098,7 +2133,7 @@ int launch_resident_t(const SvdPlan& pl, cplx* X, const SvdState& s, double tol2
     const int nw = std::max(1, std::min(cap, pl.n_pad / 2));
     jacobi_resident_kernel<NJ><<<pl.batch, 32 * nw, smem, st>>>(X, (long long)pl.n_pad * pl.ld, pl.n_pad, pl.ld, pl.ldot,
                                                                pl.max_sweeps, tol2, s.rot_total, s.sweep_total,
-                                                               s.n_active);
+                                                               s.n_active, pl.real);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -2172,6 +2207,8 @@ int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan) {
     static const int qr_grid_min = env_int("MPSB_SVD_QR_GRID_MIN", 160);
     p.qr_grid = (qr_grid_enabled && batch <= 4 && std::min(n, ldot) >= qr_grid_min) ? 1 : 0;
     if (p.qr_grid) p.chunk = batch;          // the cooperative QR factors the whole (tiny) batch in one launch
+    p.real = 0;
+    p.phase = 0;
     *plan = p;
     return 0;
 }
@@ -2256,9 +2293,18 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     int launch_id = 1;
     const int trace = env_int("MPSB_SVD_TRACE", 0);
 
-    if (pl.resident) {
+    if (pl.phase == 1) {                                     // QR only (real path: the sweeps run on the packed copy)
         if (int rc = launch_qr(pl, X, s, state, 0, pl.batch, st)) return rc;
         prof_mark(3, st);
+        if (sweeps_out) *sweeps_out = 0;
+        return 0;
+    }
+    const bool with_qr = pl.phase == 0;
+    if (pl.resident) {
+        if (with_qr) {
+            if (int rc = launch_qr(pl, X, s, state, 0, pl.batch, st)) return rc;
+            prof_mark(3, st);
+        }
         if (int rc = launch_resident(pl, X, s, tol2, st)) return rc;
         MPSB_CHECK_CUDA(cudaMemcpyAsync(&max_sweeps_seen, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -2266,13 +2312,15 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
         const int nchunks = (pl.batch + pl.chunk - 1) / pl.chunk;
         // With one chunk the QR of the batch is timed as its own phase; otherwise QR and sweeps of different chunks
         // alternate and the "qr" phase of the profile reads zero (its time is inside "jacobi").
-        if (nchunks > 1) prof_mark(3, st);
+        if (nchunks > 1 && with_qr) prof_mark(3, st);
         static int last_sweeps = 0;                       // sweeps the previous call needed (any shape: a hint only)
         const int poll_from = std::max(0, last_sweeps - 2);
         for (int mat0 = 0; mat0 < pl.batch; mat0 += pl.chunk) {
             const int count = std::min(pl.chunk, pl.batch - mat0);
-            if (int rc = launch_qr(pl, X, s, state, mat0, count, st)) return rc;
-            if (nchunks == 1) prof_mark(3, st);
+            if (with_qr) {
+                if (int rc = launch_qr(pl, X, s, state, mat0, count, st)) return rc;
+                if (nchunks == 1) prof_mark(3, st);
+            }
             int sweep = 0;
             for (; sweep < pl.max_sweeps; ++sweep) {
                 for (int r = 0; r < rounds; ++r) {

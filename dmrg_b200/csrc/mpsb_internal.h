@@ -64,6 +64,8 @@ struct SvdPlan {
     int qr_grid;     // 1: few large problems - the QR of each is spread over many CTAs (cooperative launch)
     int tiled;       // 1: rows longer than shared memory allows stream through the tiled Gram kernel
     int resident;    // 1: the whole work matrix of a problem lives in one CTA's shared memory (single launch)
+    int real;        // 1: rows hold a REAL matrix, adjacent column pairs packed into complex elements; rotations are real
+    int phase;       // 0: QR + sweeps; 1: QR only; 2: sweeps only (the real path runs the QR on the unpacked matrix)
 };
 int svd_make_plan(int batch, int n, int ldot, int ltot, SvdPlan* plan);
 size_t svd_state_bytes(const SvdPlan& plan);   // per-call scratch besides X (flags, counters, order)
@@ -83,6 +85,8 @@ struct SvdOutputs {
     int k_cap;                                       // rows written per problem (>= trun not required)
     int trun; double err;
     int normalise;                                   // 1: reference `truncate`; 0: iDMRG `halve` (no eps, raw S)
+    int real;                                        // packed real rows: vh / aug are arrays of doubles, strides in doubles
+    int real_cols, real_naug;                        // real columns of the dot part / of the carried part
 };
 int svd_finalise(const SvdPlan& plan, const cplx* X, void* state, const SvdOutputs& out, cudaStream_t st);
 
@@ -114,6 +118,12 @@ struct MatSrc {
 // Batched: problem b reads dot.src + b * dot.bs (scale + b * scale_bs), writes X + b * n_pad * ld - one launch.
 int pack_work_matrix(cplx* X, int n_pad, int ld, int rows, int ldot, int ltot, const MatSrc& dot, const MatSrc& aug,
                      int identity, cudaStream_t st, int batch = 1);
+// Real path: X[b][i][j] = (A[b][i][j], 0) for j < cols, (1, 0) at j = ldot + i when identity, zero elsewhere.
+int pack_real_matrix(cplx* X, int n_pad, int ld, int rows, int cols, int ldot, const double* A, int lda, long long sA,
+                     int identity, cudaStream_t st, int batch);
+// Xp[b][i][j] = (Re X[b][i][2j], Re X[b][i][2j+1]) for i < rows, j < ltot_p; zero in the padding of the packed matrix.
+int compact_real_pairs(const cplx* X, int n_pad, int ld, int rows, cplx* Xp, int n_pad_p, int ld_p, int ltot_p,
+                       cudaStream_t st, int batch);
 // out[j * ldo + i] = conj?(in[i * ldi + j]),  i < rows, j < cols; batched with element strides s_in / s_out
 int transpose_conj(const cplx* in, int ldi, int rows, int cols, cplx* out, int ldo, int conj, cudaStream_t st,
                    int batch = 1, long long s_in = 0, long long s_out = 0);

@@ -62,20 +62,16 @@ def _as_complex(x):
     return t.complex(x, t.zeros_like(x)) if not x.is_complex() else x
 
 
-def _split_real(split, theta, sh, trunc):
-    """SVD split of a real two-site tensor: the Jacobi kernels are complex128, and complex arithmetic on data with a
-    zero imaginary part stays exactly real (every product with 0 is 0), so the factors are the real parts."""
-    U, S, V = split(_as_complex(theta), sh, trunc)
-    return U.real.contiguous(), S, V.real.contiguous()
-
-
 def halve(psi, sh, trunc=10):
     """SVD-split psi[(chi_l d), (d chi_r)] and keep `trunc` states (`DMRG/iDMRG.py:17-35`):
     returns U[chi_l, d, k], the FULL unnormalised S, V[k, d, chi_r] with k = min(trunc, S.size).
     Accepts a numpy array (returns numpy) or a device tensor (returns device tensors)."""
     on_host = isinstance(psi, np.ndarray)
     lsize, rsize = sh[0] * sh[1], sh[2] * sh[3]
-    dev = _lib.to_device(psi.reshape(lsize, rsize)) if on_host else psi.reshape(lsize, rsize)
+    if on_host:
+        dev, = _to_device_auto(np.isrealobj(psi) and REAL_PATH, psi.reshape(lsize, rsize))
+    else:
+        dev = psi.reshape(lsize, rsize)      # a real (float64) tensor takes the real SVD (mpsb_svd_trunc_real)
     u, s_all, vh, k = _device_svd(dev, lsize, rsize, trunc, 0.0, want_u=True, normalise=0)
     U = u.reshape(sh[0], sh[1], k)
     V = vh.reshape(k, sh[2], sh[3])
@@ -191,15 +187,12 @@ def next_LR_device(Ld, Rd, Md, trunc=None, swap_conj=False, seed=0):
     """`next_LR` on device-resident tensors (no host round trip): returns (L', R', E, S_all)."""
     E, theta = ground_state(Ld, Md, Rd, seed=seed)
     sh = tuple(theta.shape)
-    real = _is_real_t(theta)
     if trunc is None and halve is not _halve_public:       # somebody rebound the module-level halve (reference idiom)
         U, S, V = halve(theta, sh)
-    elif sh[0] * sh[1] <= 256:                             # carried-identity SVD is faster while rows stay short
-        split, tr = halve, 10 if trunc is None else trunc
-        U, S, V = _split_real(split, theta, sh, tr) if real else split(theta, sh, tr)
+    elif sh[0] * sh[1] <= (512 if _is_real_t(theta) else 256):   # carried-identity SVD is faster while rows stay short
+        U, S, V = halve(theta, sh, 10 if trunc is None else trunc)
     else:
-        split, tr = _halve_split, 10 if trunc is None else trunc
-        U, S, V = _split_real(split, theta, sh, tr) if real else split(theta, sh, tr)
+        U, S, V = _halve_split(theta, sh, 10 if trunc is None else trunc)
     Ln = _env(True, Ld, U.contiguous(), Md, swap_conj)
     Rn = _env(False, Rd, V.contiguous(), Md, swap_conj)
     last_info["S"] = _lib.to_host(S)
@@ -281,10 +274,7 @@ class Chain:
             nrm = np.sqrt(abs(_overlap(guess, guess)))
             self.fidelity.append(abs(_overlap(guess, theta)) / nrm if nrm > 0 else 0.0)
         sh = tuple(theta.shape)
-        if self.real:
-            U, S_all, V = _split_real(_halve_public, theta, sh, self.trunc)
-        else:
-            U, S_all, V = _halve_public(theta, sh, self.trunc)     # one SVD with carried identity: U and V share a gauge
+        U, S_all, V = _halve_public(theta, sh, self.trunc)     # one SVD with carried identity: U and V share a gauge
         self.L = _env(True, self.L, U.contiguous(), self.M, self.swap_conj)
         self.R = _env(False, self.R, V.contiguous(), self.M, self.swap_conj)
         s = _lib.to_host(S_all)[:U.shape[2]]
@@ -339,15 +329,19 @@ def _svd_batched(A, trunc, want_u):
     with Uh [n, k, rows] = U^H, Vh [n, k, cols], k = min(trunc, rows, cols) for every chain."""
     lib = _lib.load()
     n, rows, cols = (int(v) for v in A.shape)
+    real = _is_real_t(A)
+    dt = "f64" if real else "c128"
     k = max(1, min(rows, cols, int(trunc)))
-    vh = _lib.empty((n, k, cols))
-    uh = _lib.empty((n, k, rows)) if want_u else None
+    vh = _lib.empty((n, k, cols), dt)
+    uh = _lib.empty((n, k, rows), dt) if want_u else None
     s = _lib.empty((n, k), "f64")
     sraw = _lib.empty((n, min(rows, cols)), "f64")
     rank = _lib.empty((n,), "i32")
-    ws, wsn = _lib.workspace(lib.mpsb_svd_trunc_workspace(n, rows, cols, int(want_u)))
-    _lib.check(lib.mpsb_svd_trunc(n, rows, cols, _lib.ptr(A), cols, rows * cols, int(trunc), 0.0, 0, k, _lib.ptr(vh),
-                                  _lib.ptr(uh), _lib.ptr(s), _lib.ptr(sraw), _lib.ptr(rank), ws, wsn, _lib.stream_ptr()),
+    wsq, fn = (lib.mpsb_svd_trunc_real_workspace, lib.mpsb_svd_trunc_real) if real else (lib.mpsb_svd_trunc_workspace,
+                                                                                         lib.mpsb_svd_trunc)
+    ws, wsn = _lib.workspace(wsq(n, rows, cols, int(want_u)))
+    _lib.check(fn(n, rows, cols, _lib.ptr(A), cols, rows * cols, int(trunc), 0.0, 0, k, _lib.ptr(vh),
+                  _lib.ptr(uh), _lib.ptr(s), _lib.ptr(sraw), _lib.ptr(rank), ws, wsn, _lib.stream_ptr()),
                "mpsb_svd_trunc")
     _lib.warn_if_unconverged("halve (batched)")
     return uh, sraw, vh
@@ -357,11 +351,8 @@ def halve_batched(theta, trunc):
     """`halve` (DMRG/iDMRG.py:17-35) for n two-site tensors [n, xl, d, d, xr] at once: U [n, xl, d, k], S_all [n, .],
     V [n, k, d, xr] (device tensors; every chain keeps k = min(trunc, S.size) states, so the shapes stay common)."""
     n, xl, d, _, xr = (int(v) for v in theta.shape)
-    if _is_real_t(theta):                                   # complex Jacobi kernels on real data stay exactly real
-        U, s_all, V = halve_batched(_as_complex(theta), trunc)
-        return U.real.contiguous(), s_all, V.real.contiguous()
     A = theta.reshape(n, xl * d, d * xr)
-    if xl * d <= 256:                                       # carried-identity SVD: U and V from one decomposition
+    if xl * d <= (512 if _is_real_t(theta) else 256):       # (real rows pack two columns into one element)                                       # carried-identity SVD: U and V from one decomposition
         uh, s_all, vh = _svd_batched(A, trunc, True)
         U = _transpose_batched(uh)
     else:                                                   # two row-orthogonalisations (see _halve_split)

@@ -60,6 +60,15 @@ int mpsb_svd_trunc(int batch, int rows, int cols, const void* A, int lda, long l
                    int normalise, int k_cap, void* Vh, void* Uh, double* S, double* S_raw, int* rank, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* The same for REAL matrices (A, Vh, Uh are arrays of doubles; lda, sA in doubles): the split of the real iDMRG path
+ * (halve on a real two-site tensor, DMRG/iDMRG.py:17-35 with MPO.tomatrix(dtype='double'), DMRG/MPO.py:68-76).
+ * Householder QR on the matrix itself, then the Jacobi sweeps on rows whose adjacent real columns are packed
+ * pairwise into complex elements (half the row length, real rotations). */
+size_t mpsb_svd_trunc_real_workspace(int batch, int rows, int cols, int want_u);
+int mpsb_svd_trunc_real(int batch, int rows, int cols, const void* A, int lda, long long sA, int trun, double err,
+                        int normalise, int k_cap, void* Vh, void* Uh, double* S, double* S_raw, int* rank, void* ws,
+                        size_t ws_bytes, void* stream);
+
 /* TEBD two-site update, batched over independent bonds (MPS.update_double, DMRG/MPS.py:428-457):
  *     thetaB[l,a,b,k] = sum_{c,j,r} Bi[l,c,r] Bj[r,j,k] U[a,b,c,j]          (:445)
  *     m = Sl[l] * thetaB;  (s, Vh) = svd_truncate(m as (chil*d) x (d*chir), trun, err)   (:446-449)

@@ -66,18 +66,79 @@ def test_real_heff_matvec_and_env(lib):
         np.testing.assert_allclose(lib.to_host(Rn), io_.env_right(R, V, W, False).real, atol=1e-11 * np.abs(R).max() * xr)
 
 
-def test_complex_svd_of_real_matrix_stays_real(lib):
-    """The split of the real path runs the complex Jacobi kernels on data with a zero imaginary part; every product
-    with an exact zero is zero, so the factors come back exactly real."""
+def _svd_real(lib, A, trunc, want_u, normalise=0, err=0.0):
+    """mpsb_svd_trunc_real on a batch [n, rows, cols] of real matrices: (Uh | None, S_raw, S, Vh, rank) as numpy."""
+    l = lib.load()
+    n, rows, cols = A.shape
+    k = max(1, min(rows, cols, trunc))
+    Ad = lib.to_device(A, np.float64)
+    vh, uh = lib.empty((n, k, cols), "f64"), (lib.empty((n, k, rows), "f64") if want_u else None)
+    s, sraw, rank = lib.empty((n, k), "f64"), lib.empty((n, min(rows, cols)), "f64"), lib.empty((n,), "i32")
+    ws, wsn = lib.workspace(l.mpsb_svd_trunc_real_workspace(n, rows, cols, int(want_u)))
+    lib.check(l.mpsb_svd_trunc_real(n, rows, cols, lib.ptr(Ad), cols, rows * cols, trunc, err, normalise, k, lib.ptr(vh),
+                                    lib.ptr(uh), lib.ptr(s), lib.ptr(sraw), lib.ptr(rank), ws, wsn, lib.stream_ptr()),
+              "mpsb_svd_trunc_real")
+    return (lib.to_host(uh) if want_u else None), lib.to_host(sraw), lib.to_host(s), lib.to_host(vh), lib.to_host(rank)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 2, 3), (2, 5, 4), (3, 7, 5), (4, 16, 16), (3, 33, 17), (2, 17, 40), (5, 64, 64),
+                                   (3, 100, 100), (2, 128, 256), (6, 256, 256), (1, 320, 320), (1, 512, 512),
+                                   (1, 1024, 1024)])
+@pytest.mark.parametrize("want_u", [False, True])
+def test_real_svd_matches_lapack(lib, shape, want_u):
+    """Real SVD (QR unpacked, Jacobi sweeps on pair-packed rows) against LAPACK: singular values 1e-11 relative,
+    Vh (and U) orthonormal to 1e-12, A V = U S; even and odd shapes, all kernel families (resident, cross / self,
+    Gram, tiled Gram)."""
+    n, rows, cols = shape
+    if want_u and rows >= 1024:
+        pytest.skip("carried identity at 1024 rows: covered by the split path")
+    rs = np.random.RandomState(rows * 7 + cols + n)
+    A = rs.randn(n, rows, cols) * np.exp(-0.03 * np.arange(cols))[None, None, :]      # decaying column scales
+    trunc = min(rows, cols, 48)
+    uh, sraw, s, vh, rank = _svd_real(lib, A, trunc, want_u)
+    for b in range(n):
+        s_ref = np.linalg.svd(A[b], compute_uv=False)
+        np.testing.assert_allclose(sraw[b], s_ref, rtol=1e-11, atol=1e-13 * s_ref[0])
+        k = int(rank[b])
+        assert k == trunc
+        V = vh[b, :k]
+        np.testing.assert_allclose(V @ V.T, np.eye(k), atol=1e-12)
+        if want_u:
+            U = uh[b, :k].T
+            np.testing.assert_allclose(U.T @ U, np.eye(k), atol=1e-12)
+            np.testing.assert_allclose(A[b] @ V.T, U * sraw[b, :k], atol=1e-11 * s_ref[0])
+        else:                                               # the projector onto the kept right singular space
+            _, _, vr = np.linalg.svd(A[b])
+            gap_ok = k == min(rows, cols) or s_ref[k - 1] - s_ref[k] > 1e-6 * s_ref[0]
+            if gap_ok:
+                np.testing.assert_allclose(V.T @ V, vr[:k].T @ vr[:k], atol=1e-8)
+
+
+def test_real_svd_truncation_rule(lib):
+    """normalise = 1: the reference's `truncate` (DMRG/MPS.py:33-38) on the real path."""
+    from oracle.mps_oracle import svd_truncate as oracle_svd_truncate
+    rs = np.random.RandomState(11)
+    A = rs.randn(1, 24, 30) @ np.diag(np.exp(-1.5 * np.arange(30)))
+    _, _, s, vh, rank = _svd_real(lib, A, 10, False, normalise=1, err=1e-9)
+    uo, so, vo = oracle_svd_truncate(A[0], 10, 1e-9)
+    assert int(rank[0]) == len(so)
+    np.testing.assert_allclose(s[0, :len(so)], so, rtol=1e-10)
+
+
+def test_real_halve_returns_real_factors(lib):
     from dmrg_b200 import iDMRG
     rs = np.random.RandomState(8)
-    for sh in ((6, 2, 2, 5), (32, 2, 2, 32), (100, 2, 2, 100), (160, 2, 2, 160)):
+    for sh in ((6, 2, 2, 5), (32, 2, 2, 32), (160, 2, 2, 160)):
         psi = rs.randn(*sh)
-        split = iDMRG.halve if sh[0] * sh[1] <= 256 else iDMRG._halve_split
-        U, S, V = split(iDMRG._as_complex(lib.to_device(psi, np.float64)), sh, 24)
-        assert float(U.imag.abs().max()) == 0.0 and float(V.imag.abs().max()) == 0.0
-        s_ref = np.linalg.svd(psi.reshape(sh[0] * sh[1], -1), compute_uv=False)
-        np.testing.assert_allclose(lib.to_host(S)[:24], s_ref[:24], rtol=1e-11)
+        U, S, V = iDMRG.halve(psi.ravel(), sh, trunc=12)
+        assert U.dtype == np.float64 and V.dtype == np.float64
+        Uo, So, Vo = io_.halve(psi, sh, 12)
+        np.testing.assert_allclose(S, So, rtol=1e-11)
+        np.testing.assert_allclose(np.tensordot(U, U, axes=([2], [2])), np.tensordot(Uo, Uo.conj(), axes=([2], [2])).real,
+                                   atol=1e-9)
+        th = np.einsum('abk,k,kcd->abcd', U, S[:12], V)
+        thk = np.einsum('abk,k,kcd->abcd', Uo, So[:12], Vo)
+        np.testing.assert_allclose(th, thk.real, atol=1e-10 * So[0])
 
 
 @pytest.mark.parametrize("model", ["tfim", "heisenberg"])

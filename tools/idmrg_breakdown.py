@@ -13,7 +13,8 @@ else:
 w = W.shape[0]
 L0 = np.zeros((1, 1, w)); L0[0, 0, w - 1] = 1
 R0 = np.zeros((1, 1, w)); R0[0, 0, 0] = 1
-Ld, Rd, Wd = _lib.to_device(L0), _lib.to_device(R0), _lib.to_device(W)
+real = 'complex' not in sys.argv
+Ld, Rd, Wd = iDMRG._to_device_auto(real, L0, R0, W)
 for i in range(max(14, int(np.log2(chi)) + 3)):
     Ld, Rd, E, S = iDMRG.next_LR_device(Ld, Rd, Wd, trunc=chi)
 def T(f, reps=2):
