@@ -12,7 +12,7 @@
 //   operand stored with k contiguous ("KC": A with op N, B with op T): ONE box of BM (BN) rows, 128 B per row;
 //   operand stored with m/n contiguous ("MC": A with op T, B with op N): BM/16 boxes of 16 k-rows, 2 KiB each.
 // The k index a lane feeds into its DMMA slot is permuted inside the 16-wide k tile (perm_k) so that the 8-byte
-// fragment loads of a warp spread over all banks for both layouts (two wavefronts per 256-byte request, the minimum).
+// fragment loads of every half-warp spread over all banks for both layouts.
 // Operands a tensor map cannot describe (odd leading dimension or stride, misaligned base) take a plain SIMT kernel;
 // those are the tiny odd-shaped products of the first growth steps.
 #include <cuda.h>
@@ -37,9 +37,17 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// k handled by DMMA slot t in sub-step kk of a 16-wide k tile: a bijection of (kk, t) onto 0..15 whose bit 2 follows
-// t & 1, so the four k-rows a warp reads from an MC tile fall into both 64-byte halves of the bank space.
-__device__ __forceinline__ int perm_k(int kk, int t) { return 8 * (kk >> 1) + 4 * (t & 1) + 2 * (kk & 1) + (t >> 1); }
+// k handled by DMMA slot t in sub-step kk of a 16-wide k tile: a bijection of (kk, t) onto 0..15 chosen so that the
+// 8-byte fragment loads of each HALF-warp (the unit in which 64-bit shared loads are served; lanes g = 0..3 x t = 0..3)
+// touch all 32 banks exactly once in both tile layouts.  With k = b0 + 2 b1 + 4 b2 + 8 b3:
+//   KC tiles (chunk = (k >> 1) ^ row, half = k & 1) need t -> (b0, b3) one-to-one,
+//   MC tiles (chunk = column-chunk ^ (k & 7))       need t -> (b1, b2) one-to-one;
+// b0 = t0 ^ kk0, b1 = t0, b2 = t1, b3 = t1 ^ kk1 satisfies both (ncu: shared-memory bank conflicts of the natural
+// order k = 4 kk + t were two extra wavefronts per load).
+__device__ __forceinline__ int perm_k(int kk, int t) {
+    const int t0 = t & 1, t1 = t >> 1;
+    return (t0 ^ (kk & 1)) | (t0 << 1) | (t1 << 2) | ((t1 ^ (kk >> 1)) << 3);
+}
 // byte offset of element (row r, k) in a KC tile (one box, rows of 128 B)
 __device__ __forceinline__ int dkc_off(int r, int k) { return r * 128 + ((((k >> 1) ^ (r & 7))) << 4) + ((k & 1) << 3); }
 // byte offset of element (k, c) in an MC tile (boxes of 16 doubles x 16 k-rows)

@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include "common.cuh"
 #include "mpsb_internal.h"
 #include "jacobi_shared.cuh"
@@ -2047,6 +2048,24 @@ int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, i
     return 0;
 }
 
+// Side stream of the calling host thread on the current device (created on first use, lives as long as the process).
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+SideStream* side_stream() {
+    static thread_local std::map<int, SideStream> table;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    auto it = table.find(dev);
+    if (it != table.end()) return &it->second;
+    SideStream ss;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess)
+        return nullptr;
+    return &table.emplace(dev, ss).first->second;
+}
+
 typedef void (*CrossKernel)(cplx*, long long, int, int, int, int, int, int, int*, const int*, double, unsigned long long*,
                             int*, int, int, int);
 CrossKernel cross_kernel_for(bool full, bool real) {
@@ -2072,13 +2091,21 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
     auto kern = cross_kernel_for(full, pl.real != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
     dim3 grid(mod_cross_pairs(nblk, round), count);
-    kern<<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, tol2, pc,
-                                           s.stamps, s.stamp_stride, launch_id, 1);
-    MPSB_COUNT_LAUNCH();
-    MPSB_CHECK_CUDA(cudaGetLastError());
     if ((round & 1) == 0) {
+        // The two self tasks of an even step touch blocks no cross pair of the step touches, and their kernel is bound
+        // by latency (one 128-thread CTA per problem, ~2000 clocks per tournament step): it runs on a side stream,
+        // forked before and joined after the cross launch, so that its CTAs share the SMs with the cross CTAs
+        // instead of following them.
+        static const int overlap = env_int("MPSB_SELF_OVERLAP", 1);
+        SideStream* side = overlap ? side_stream() : nullptr;
+        cudaStream_t ss = st;
+        if (side) {
+            MPSB_CHECK_CUDA(cudaEventRecord(side->fork, st));
+            MPSB_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            ss = side->stream;
+        }
 #define MPSB_SELF(CPL, EXACT)                                                                                              \
-    jacobi_self_kernel<CPL, EXACT><<<count, 128, 0, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, \
+    jacobi_self_kernel<CPL, EXACT><<<count, 128, 0, ss>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, \
                                                           tol2, s.stamps, s.stamp_stride, launch_id, pl.real)
         if (full) MPSB_SELF(4, true);
         else if (ltot_r > 128) MPSB_SELF(4, false);
@@ -2087,7 +2114,18 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
 #undef MPSB_SELF
         MPSB_COUNT_LAUNCH();
         MPSB_CHECK_CUDA(cudaGetLastError());
+        if (side) MPSB_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+        kern<<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, tol2, pc,
+                                               s.stamps, s.stamp_stride, launch_id, 1);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+        if (side) MPSB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+        return 0;
     }
+    kern<<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, tol2, pc,
+                                           s.stamps, s.stamp_stride, launch_id, 1);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
