@@ -17,7 +17,8 @@
 // reference truncation rule, coalesced scatter into the MPS tensors).
 //
 // Which kernels run is decided by the plan (svd_make_plan) from the batch size and the shape:
-//   QR      qr_blocked_kernel      large batches: 256 threads and ~40 KB per problem, 4 problems per SM
+//   QR      qr_panel_dmma_kernel   large batches: columns in pivot order, panels of 8, trailing update on DMMA;
+//           qr_blocked_kernel      its predecessor (one thread per column), kept for shapes whose row buffer does not fit
 //           qr_precond_kernel      batch <= 148: one SM per problem, 1024 threads (half the latency)
 //           qr_grid_kernel         <= 4 large problems: columns of each dealt out to up to 148 CTAs (cooperative)
 //   Jacobi  jacobi_cross_kernel    rounds >= 1, rows of <= 256 columns: register-resident rows, TMA-streamed partners
@@ -792,6 +793,318 @@ qr_blocked_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, i
                 }
                 X[(size_t)i * ld + j] = x;
             }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- blocked Householder QR with the trailing update on FP64 tensor cores -------------------------------------------
+// qr_blocked_kernel above spends its time in step 3: one thread per column needs 8 complex accumulators (W) and 8
+// coefficients (Z), which at the 64 registers that 4 CTAs per SM allow spill, and the scattered pivot columns make
+// every panel gather a strided read.  Here
+//   0. the dot columns are first moved into pivot order IN PLACE (one pass over the matrix), so panels are contiguous
+//      column ranges and the trailing matrix is "all columns to the right of the panel"; the inverse permutation is
+//      applied at the end, so callers see the same R (up to rounding) in the original column order;
+//   1./2. panel factorisation and T exactly as in qr_blocked_kernel (shared-memory panel, row pitch QD_VS = 9 elements
+//      so that both fragment patterns below are conflict-free);
+//   3. trailing update by DMMA, one warp per group of 8 columns:
+//         W = V^H X   (8 x 8 accumulator tile, K = rows, V^H fragments from the shared panel, X fragments from global)
+//         Z = T^H W   (8 x 8 x 8, W passes from accumulator to operand layout through a per-warp staging tile)
+//         X -= V Z    (per 8-row tile: X is loaded in accumulator layout, 8 DMMAs, stored back)
+//      four registers of accumulators instead of 32, no spills, a quarter of the issue slots.
+constexpr int QD_VS = 9;               // row pitch of the shared panel in elements (8 columns + 1 pad)
+#ifndef MPSB_QD_TILES
+#define MPSB_QD_TILES 2
+#endif
+#ifndef MPSB_QD_WU
+#define MPSB_QD_WU 4
+#endif
+constexpr int QD_TILES = MPSB_QD_TILES;   // 8-row tiles of X in flight per warp in the update pass
+constexpr int QD_WU = MPSB_QD_WU;         // 4-row slices of X in flight per warp in the W pass
+
+__global__ void __launch_bounds__(QB_THREADS, 4)
+qr_panel_dmma_kernel(cplx* __restrict__ Xall, long long strideX, int n, int ldot, int ltot, int ld,
+                     double* __restrict__ frob2) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr int NB = QB_NB, NT = QB_THREADS, NW = QB_THREADS / 32, VS = QD_VS;
+    const size_t nal = align_up(n, 8);
+    cplx* Vp = reinterpret_cast<cplx*>(smraw);                          // [nal][VS] panel / reflectors; row buffer in step 0
+    double* cn = reinterpret_cast<double*>(Vp + nal * VS);              // [ldot]
+    int* order = reinterpret_cast<int*>(cn + align_up(ldot, 8));        // [ldot]
+    __shared__ double scratch[(NW + 1) * 2 * NB];
+    __shared__ cplx Tm[NB][NB];
+    __shared__ cplx vdiag[NB], betas[NB];
+    __shared__ double taus[NB];
+    __shared__ cplx stage[NW][8][VS];                                   // per-warp fragment transposes
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    cplx* X = Xall + (size_t)blockIdx.x * strideX;
+
+    // column norms of the dot part, descending-norm pivot order (ties by index)
+    double fl = 0.0;
+    for (int j = tid; j < ldot; j += NT) {
+        double acc = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const cplx x = X[(size_t)i * ld + j];
+            acc = fma(x.x, x.x, fma(x.y, x.y, acc));
+        }
+        cn[j] = acc;
+        fl += acc;
+    }
+    {
+        double v1[1] = {fl};
+        block_sum_vec<1>(v1, 1, scratch);
+        if (tid == 0) frob2[blockIdx.x] = v1[0];
+    }
+    for (int j = tid; j < ldot; j += NT) {
+        const double me = cn[j];
+        int r = 0;
+        for (int q = 0; q < ldot; ++q) {
+            const double o = cn[q];
+            r += (o > me) || (o == me && q < j);
+        }
+        order[r] = j;
+    }
+    __syncthreads();
+    // 0. dot columns into pivot order: X[i][j] <- X[i][order[j]], ROWS_PER rows at a time through the panel buffer
+    const int rows_per = (int)((nal * VS) / (size_t)ldot);             // >= 1 (checked by the launcher)
+    for (int i0 = 0; i0 < n; i0 += rows_per) {
+        const int nr = min(rows_per, n - i0);
+        for (int e = tid; e < nr * ldot; e += NT) {
+            const int r = e / ldot, j = e - r * ldot;
+            Vp[e] = X[(size_t)(i0 + r) * ld + order[j]];
+        }
+        __syncthreads();
+        for (int e = tid; e < nr * ldot; e += NT) {
+            const int r = e / ldot, j = e - r * ldot;
+            X[(size_t)(i0 + r) * ld + j] = Vp[e];
+        }
+        __syncthreads();
+    }
+
+    const int nsteps = n < ldot ? n : ldot;
+    for (int k = 0; k < nsteps; k += NB) {
+        const int nbp = (nsteps - k) < NB ? (nsteps - k) : NB;
+        // 1. the panel: rows k..nal-1 of columns k..k+nbp-1 (rows >= n and columns >= nbp are zero)
+        for (int e = tid; e < (int)(nal - k) * NB; e += NT) {
+            const int i = k + e / NB, b = e % NB;
+            Vp[(size_t)i * VS + b] = (i < n && b < nbp) ? X[(size_t)i * ld + k + b] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        // 2. factor the panel in shared memory
+        for (int b = 0; b < nbp; ++b) {
+            const int kb = k + b;
+            double acc[2 * NB];
+#pragma unroll
+            for (int q = 0; q < 2 * NB; ++q) acc[q] = 0.0;
+            for (int i = kb + 1 + tid; i < n; i += NT) {
+                const cplx pb = Vp[(size_t)i * VS + b];
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c >= b && c < nbp) {
+                        const cplx pc = Vp[(size_t)i * VS + c];
+                        acc[2 * c] = fma(pb.x, pc.x, fma(pb.y, pc.y, acc[2 * c]));
+                        acc[2 * c + 1] = fma(pb.x, pc.y, fma(-pb.y, pc.x, acc[2 * c + 1]));
+                    }
+            }
+            block_sum_vec<2 * NB>(acc, 2 * nbp, scratch);
+            const double sigma = scratch[NW * 2 * NB + 2 * b];
+            const cplx alpha = Vp[(size_t)kb * VS + b];
+            const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+            const double normx2 = a2 + sigma;
+            __syncthreads();                                   // everybody has read alpha / row kb
+            if (!(normx2 > QR_TINY)) {                             // zero column: identity reflector
+                if (tid == 0) { taus[b] = 0.0; vdiag[b] = make_double2(0.0, 0.0); betas[b] = make_double2(0.0, 0.0); }
+                __syncthreads();
+                continue;
+            }
+            const double normx = sqrt(normx2), absa = sqrt(a2);
+            cplx phase = make_double2(1.0, 0.0);
+            if (absa > 0.0) phase = make_double2(alpha.x / absa, alpha.y / absa);
+            const cplx beta = make_double2(-phase.x * normx, -phase.y * normx);
+            const cplx vk = make_double2(phase.x * (absa + normx), phase.y * (absa + normx));
+            const double tau = 2.0 / ((absa + normx) * (absa + normx) + sigma);
+            for (int i = kb + tid; i < n; i += NT) {
+                const cplx vi = (i == kb) ? vk : Vp[(size_t)i * VS + b];
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c > b && c < nbp) {
+                        const cplx top = Vp[(size_t)kb * VS + c];
+                        const double wr = tau * (vk.x * top.x + vk.y * top.y + acc[2 * c]);
+                        const double wi = tau * (vk.x * top.y - vk.y * top.x + acc[2 * c + 1]);
+                        cplx pc = Vp[(size_t)i * VS + c];
+                        if (i != kb) {
+                            pc.x -= vi.x * wr - vi.y * wi;
+                            pc.y -= vi.x * wi + vi.y * wr;
+                            Vp[(size_t)i * VS + c] = pc;
+                        }
+                    }
+            }
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c > b && c < nbp) {
+                        const cplx top = Vp[(size_t)kb * VS + c];
+                        const double wr = tau * (vk.x * top.x + vk.y * top.y + acc[2 * c]);
+                        const double wi = tau * (vk.x * top.y - vk.y * top.x + acc[2 * c + 1]);
+                        Vp[(size_t)kb * VS + c] = make_double2(top.x - (vk.x * wr - vk.y * wi), top.y - (vk.x * wi + vk.y * wr));
+                    }
+                taus[b] = tau;
+                vdiag[b] = vk;
+                betas[b] = beta;
+            }
+            __syncthreads();
+        }
+        // finished panel columns back to X (R on and above the diagonal, zeros below); Vp becomes V proper
+        for (int e = tid; e < (n - k) * NB; e += NT) {
+            const int i = k + e / NB, b = e % NB;
+            if (b < nbp) {
+                const int kb = k + b;
+                cplx* dst = X + (size_t)i * ld + kb;
+                cplx& v = Vp[(size_t)i * VS + b];
+                if (i < kb) { *dst = v; v = make_double2(0.0, 0.0); }
+                else if (i == kb) {
+                    const bool ident = taus[b] == 0.0;
+                    *dst = ident ? v : betas[b];
+                    v = vdiag[b];
+                } else {
+                    if (taus[b] == 0.0) v = make_double2(0.0, 0.0);   // identity reflector
+                    *dst = make_double2(0.0, 0.0);
+                }
+            }
+        }
+        __syncthreads();
+        // T: T[b][b] = tau_b ;  T[0:b, b] = -tau_b T[0:b, 0:b] (V[:, 0:b]^H v_b); everything else zero
+        for (int e = tid; e < NB * NB; e += NT) Tm[e / NB][e % NB] = make_double2(0.0, 0.0);
+        __syncthreads();
+        if (tid == 0) Tm[0][0] = make_double2(taus[0], 0.0);
+        __syncthreads();
+        for (int b = 1; b < nbp; ++b) {
+            double acc[2 * NB];
+#pragma unroll
+            for (int q = 0; q < 2 * NB; ++q) acc[q] = 0.0;
+            for (int i = k + b + tid; i < n; i += NT) {
+                const cplx vb = Vp[(size_t)i * VS + b];
+#pragma unroll
+                for (int a = 0; a < NB; ++a)
+                    if (a < b) {
+                        const cplx va = Vp[(size_t)i * VS + a];
+                        acc[2 * a] = fma(va.x, vb.x, fma(va.y, vb.y, acc[2 * a]));            // conj(va) vb
+                        acc[2 * a + 1] = fma(va.x, vb.y, fma(-va.y, vb.x, acc[2 * a + 1]));
+                    }
+            }
+            block_sum_vec<2 * NB>(acc, 2 * b, scratch);
+            if (tid == 0) {
+                const double tb = taus[b];
+                for (int a = 0; a < b; ++a) {
+                    double re = 0.0, im = 0.0;
+                    for (int c = a; c < b; ++c) {                // T[a][c] (upper triangular) times g_c
+                        const cplx tt = Tm[a][c];
+                        const double gr = scratch[NW * 2 * NB + 2 * c], gi = scratch[NW * 2 * NB + 2 * c + 1];
+                        re += tt.x * gr - tt.y * gi;
+                        im += tt.x * gi + tt.y * gr;
+                    }
+                    Tm[a][b] = make_double2(-tb * re, -tb * im);
+                }
+                Tm[b][b] = make_double2(tb, 0.0);
+            }
+            __syncthreads();
+        }
+        // 3. trailing update on DMMA: warp -> groups of 8 columns to the right of the panel
+        const int c_first = k + NB;                                       // k is a multiple of 8
+        const int ngroups = (ltot - c_first + 7) / 8;
+        // A fragments of T^H (m = b', k = a): conj(T[a][b']), two k-steps
+        cplx th0 = Tm[t][g], th1 = Tm[t + 4][g];
+        th0.y = -th0.y; th1.y = -th1.y;
+        for (int grp = warp; grp < ngroups; grp += NW) {
+            const int j0 = c_first + grp * 8;
+            const bool colB = (j0 + g) < ltot;                            // operand layout: column g of the group
+            const bool colC0 = (j0 + 2 * t) < ltot, colC1 = (j0 + 2 * t + 1) < ltot;      // accumulator layout
+            // --- W = V^H X over rows k .. n-1 (rows >= n: V is zero there, X is not read) ---
+            double wre0 = 0.0, wre1 = 0.0, wim0 = 0.0, wim1 = 0.0;
+            const cplx* xcol = X + j0 + g;
+            for (int i0 = k; i0 < n; i0 += 4 * QD_WU) {
+                cplx xb[QD_WU];
+#pragma unroll
+                for (int u = 0; u < QD_WU; ++u) {
+                    const int i = i0 + 4 * u + t;
+                    xb[u] = (colB && i < n) ? xcol[(size_t)i * ld] : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < QD_WU; ++u) {
+                    const int i = i0 + 4 * u + t;
+                    const cplx v = (i < (int)nal) ? Vp[(size_t)i * VS + g] : make_double2(0.0, 0.0);
+                    dmma884(wre0, wre1, v.x, xb[u].x);
+                    dmma884(wre0, wre1, v.y, xb[u].y);
+                    dmma884(wim0, wim1, v.x, xb[u].y);
+                    dmma884(wim0, wim1, -v.y, xb[u].x);
+                }
+            }
+            // --- Z = T^H W: W from accumulator layout (row g, columns 2t, 2t+1) to operand layout (row t, column g) ---
+            cplx (*sg)[VS] = stage[warp];
+            sg[g][2 * t] = make_double2(wre0, wim0);
+            sg[g][2 * t + 1] = make_double2(wre1, wim1);
+            __syncwarp();
+            const cplx w0 = sg[t][g], w1 = sg[t + 4][g];
+            __syncwarp();
+            double zre0 = 0.0, zre1 = 0.0, zim0 = 0.0, zim1 = 0.0;
+            dmma884(zre0, zre1, th0.x, w0.x); dmma884(zre0, zre1, -th0.y, w0.y);
+            dmma884(zim0, zim1, th0.x, w0.y); dmma884(zim0, zim1, th0.y, w0.x);
+            dmma884(zre0, zre1, th1.x, w1.x); dmma884(zre0, zre1, -th1.y, w1.y);
+            dmma884(zim0, zim1, th1.x, w1.y); dmma884(zim0, zim1, th1.y, w1.x);
+            sg[g][2 * t] = make_double2(zre0, zim0);
+            sg[g][2 * t + 1] = make_double2(zre1, zim1);
+            __syncwarp();
+            const cplx z0 = sg[t][g], z1 = sg[t + 4][g];                  // Z[b = t][col g], Z[b = t + 4][col g]
+            __syncwarp();
+            // --- X -= V Z, 8-row tiles, QD_TILES tiles in flight ---
+            for (int i0 = k; i0 < n; i0 += 8 * QD_TILES) {
+                cplx x0[QD_TILES], x1[QD_TILES];
+#pragma unroll
+                for (int u = 0; u < QD_TILES; ++u) {
+                    const int i = i0 + 8 * u + g;
+                    const cplx* src = X + (size_t)i * ld + j0 + 2 * t;
+                    x0[u] = (i < n && colC0) ? src[0] : make_double2(0.0, 0.0);
+                    x1[u] = (i < n && colC1) ? src[1] : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < QD_TILES; ++u) {
+                    const int i = i0 + 8 * u + g;
+                    if (i0 + 8 * u < n) {                                    // warp-uniform
+                        const cplx va = (i < (int)nal) ? Vp[(size_t)i * VS + t] : make_double2(0.0, 0.0);
+                        const cplx vb = (i < (int)nal) ? Vp[(size_t)i * VS + t + 4] : make_double2(0.0, 0.0);
+                        // x -= v z:  re -= v.x z.x - v.y z.y,  im -= v.x z.y + v.y z.x
+                        dmma884(x0[u].x, x1[u].x, -va.x, z0.x); dmma884(x0[u].x, x1[u].x, va.y, z0.y);
+                        dmma884(x0[u].y, x1[u].y, -va.x, z0.y); dmma884(x0[u].y, x1[u].y, -va.y, z0.x);
+                        dmma884(x0[u].x, x1[u].x, -vb.x, z1.x); dmma884(x0[u].x, x1[u].x, vb.y, z1.y);
+                        dmma884(x0[u].y, x1[u].y, -vb.x, z1.y); dmma884(x0[u].y, x1[u].y, -vb.y, z1.x);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < QD_TILES; ++u) {
+                    const int i = i0 + 8 * u + g;
+                    cplx* dst = X + (size_t)i * ld + j0 + 2 * t;
+                    if (i < n && colC0) dst[0] = x0[u];
+                    if (i < n && colC1) dst[1] = x1[u];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // back to the original column order: X[i][order[j]] <- X[i][j]
+    for (int i0 = 0; i0 < n; i0 += rows_per) {
+        const int nr = min(rows_per, n - i0);
+        for (int e = tid; e < nr * ldot; e += NT) {
+            const int r = e / ldot, j = e - r * ldot;
+            Vp[e] = X[(size_t)(i0 + r) * ld + j];
+        }
+        __syncthreads();
+        for (int e = tid; e < nr * ldot; e += NT) {
+            const int r = e / ldot, j = e - r * ldot;
+            X[(size_t)(i0 + r) * ld + order[j]] = Vp[e];
         }
         __syncthreads();
     }
@@ -2275,6 +2588,8 @@ int launch_qr(const SvdPlan& pl, cplx* X, const SvdState& s, void* state, int ma
     static const int qr_blocked = env_int("MPSB_SVD_QR_BLOCKED", 1);
     const size_t smem_b = align_up(pl.n, 8) * QB_NB * sizeof(cplx) + align_up(pl.ldot, 8) * (sizeof(double) + sizeof(int)) +
                           pl.ld + 64;
+    static const int qr_dmma = env_int("MPSB_SVD_QR_DMMA", 1);
+    const size_t smem_d = align_up(pl.n, 8) * QD_VS * sizeof(cplx) + align_up(pl.ldot, 8) * (sizeof(double) + sizeof(int)) + 64;
     // Very long rows (chi >= 1024 with carried columns) do not leave room for the reflector scratch; the
     // Jacobi iteration is then started from the raw matrix (more sweeps, same result).
     // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
@@ -2290,6 +2605,12 @@ int launch_qr(const SvdPlan& pl, cplx* X, const SvdState& s, void* state, int ma
         if (grid_rc > 0) return grid_rc;
     }
     if (grid_rc == 0) {
+    } else if (qr_enabled && qr_blocked && qr_dmma && !latency_mode && smem_d <= 200 * 1024 &&
+               align_up(pl.n, 8) * QD_VS >= (size_t)pl.ldot) {
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_panel_dmma_kernel), smem_d)) return rc;
+        qr_panel_dmma_kernel<<<count, QB_THREADS, smem_d, st>>>(Xc, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, frob);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
     } else if (qr_enabled && qr_blocked && !latency_mode && smem_b <= 200 * 1024) {
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(qr_blocked_kernel), smem_b)) return rc;
         qr_blocked_kernel<<<count, QB_THREADS, smem_b, st>>>(Xc, strideX, pl.n, pl.ldot, pl.ltot, pl.ld, frob);
