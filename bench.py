@@ -497,13 +497,13 @@ def main():
         pass
     traffic = None
     try:   # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2b_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
         pass
     peak_note = ("cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; profiles/r2_fp64_peak.json "
                  "holds the DFMA / DMMA / mixed micro-benchmark of this pool: 35.5 / 37.1 / 33.8 TFLOP/s - DMMA and DFMA "
                  "share one execution unit on this part)")
-    roofline = {"kernel": "jacobi_cross_kernel (all Jacobi sweeps of one step, modulus ordering; self tasks ride in the same launches)",
+    roofline = {"kernel": "jacobi_cross_kernel (all Jacobi sweeps of one step, modulus ordering; self tasks on a side stream next to the cross launches)",
                 "bound": "fp64",
                 "achieved": svd_flop / svd_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": svd_flop / svd_s / 1e12 / fp64_peak,

@@ -2595,7 +2595,10 @@ int launch_qr(const SvdPlan& pl, cplx* X, const SvdState& s, void* state, int ma
     // The blocked kernel is built for throughput (256 threads, 4 problems per SM); when every problem can have an SM
     // to itself the 1024-thread fused kernel has half the latency (tools/tebd_small_probe.py).
     static const int latency_batch = env_int("MPSB_SVD_QR_LATENCY_BATCH", 148);
-    const bool latency_mode = pl.batch <= latency_batch && smem <= 220 * 1024;
+    // ... up to ~128 rows; from 256 rows on the DMMA trailing update wins at every batch size (tools/qr_latency_probe.py:
+    // pack + QR + finalise of 256 x 256 problems, 16 / 64 / 148 of them: 3.9 / 3.9 / 6.6 ms against 2.8 / 2.8 / 3.4 ms).
+    static const int latency_max_n = env_int("MPSB_SVD_QR_LATENCY_MAXN", 191);
+    const bool latency_mode = pl.batch <= latency_batch && pl.n <= latency_max_n && smem <= 220 * 1024;
     int grid_rc = -1;
     if (qr_enabled && pl.qr_grid) {          // only for batch <= 4: never chunked
         SvdPlan base = pl;
