@@ -1584,6 +1584,192 @@ jacobi_self_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
                               real != 0);
 }
 
+// ---- persistent sweeps for a few problems (latency mode of the modulus ordering) --------------------------------------
+// One SVD of a 256 x 256 problem is ~330 steps of 16 block-pair tasks.  Launched step by step that is ~500 launches of
+// 16-CTA kernels per problem: with only a few problems in the call (one iDMRG chain, a short TEBD chain) every step
+// costs a launch latency.  Here ONE cooperative launch runs all sweeps: CTA (slot, problem) plays the slot's task of
+// every step - the cross pair mod_pair(nblk, k, slot), or on even steps in the last slot the two self tasks - and the
+// nblk/2 CTAs of a problem meet at a barrier of their own (a counter in global memory) between steps.  A sweep that
+// rotated nothing ends the problem; no host round trip until the call returns.
+// Rows move between CTAs through global memory (L2): every read below bypasses L1 (ld.global.cg / TMA), writes are
+// fenced before the barrier.  The change stamps of the multi-launch path are not used (their reads would have to
+// bypass L1 too, and skipping clean pairs saves little when the steps are latency-bound anyway).
+__device__ __forceinline__ void problem_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned seen = 0, it = 0;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen < target && ++it > (1u << 26)) __trap();      // a lost CTA must fail loudly, not hang the GPU
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// The body of jacobi_cross_kernel for one block pair, callable step after step: the mbarrier is re-armed per use
+// (`parity` flips), block-I rows are read around L1.  Returns (to every thread) whether anything rotated.
+template <bool FULL, bool REAL>
+__device__ __forceinline__ void cross_task_persistent(cplx* __restrict__ X, int ld, int ldot, int ltot_r, int bI, int bJ,
+                                                      int* __restrict__ rot_mat, double tol2, cplx* rowsJ, double* nq,
+                                                      double* dqs, double* eqs, uint64_t* bar, uint32_t parity) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
+    if (tid == 0) {
+        mbar_expect_tx(bar, rowbytes * 8);
+        for (int r = 0; r < 8; ++r) bulk_g2s(rowsJ + (size_t)r * ltot_r, X + (size_t)(bJ * 8 + r) * ld, rowbytes, bar);
+    }
+    cplx* gp0 = X + (size_t)(bI * 8 + 2 * w) * ld;
+    cplx* gp1 = gp0 + ld;
+    RegRow r0, r1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        r0.x[j] = (FULL || c < ltot_r) ? __ldcg(gp0 + c) : make_double2(0.0, 0.0);
+        r1.x[j] = (FULL || c < ltot_r) ? __ldcg(gp1 + c) : make_double2(0.0, 0.0);
+    }
+    {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (FULL || lane + 32 * j < ldot) {
+                a0 = fma(r0.x[j].x, r0.x[j].x, fma(r0.x[j].y, r0.x[j].y, a0));
+                a1 = fma(r1.x[j].x, r1.x[j].x, fma(r1.x[j].y, r1.x[j].y, a1));
+            }
+        r0.a = warp_sum(a0); r1.a = warp_sum(a1);
+        r0.d = r1.d = r0.e = r1.e = 1.0;
+        r0.dirty = r1.dirty = false;
+    }
+    if (!mbar_wait(bar, parity)) __trap();
+    for (int rr = w; rr < 8; rr += 4) {   // norms of the rows of block J
+        const cplx* r = rowsJ + (size_t)rr * ltot_r;
+        double b = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (FULL || c < ldot) { const cplx y = r[c]; b = fma(y.x, y.x, fma(y.y, y.y, b)); }
+        }
+        b = warp_sum(b);
+        if (lane == 0) { nq[rr] = b; dqs[rr] = 1.0; eqs[rr] = 1.0; }
+    }
+    __syncthreads();
+    int nrot = 0;
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) {
+        const int q = (2 * w + s) & 7;
+        cplx* rq = rowsJ + (size_t)q * ltot_r;
+        cplx y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            y[j] = (FULL || c < ltot_r) ? rq[c] : make_double2(0.0, 0.0);
+        }
+        double dq = dqs[q], eq = eqs[q], bq = nq[q];
+        int n0 = cross_pair<FULL, REAL>(r0, y, dq, eq, bq, ldot, tol2, lane, true);
+        if (n0 == 2) { swap_rows_via_smem<FULL>(r0, y, rq, ltot_r, lane); n0 = 1; }
+        int n1 = cross_pair<FULL, REAL>(r1, y, dq, eq, bq, ldot, tol2, lane, true);
+        if (n1 == 2) { swap_rows_via_smem<FULL>(r1, y, rq, ltot_r, lane); n1 = 1; }
+        nrot += n0 + n1;
+        bool store = (n0 + n1) > 0;
+        if (s >= 6 && dq != 1.0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { y[j].x *= dq; y[j].y *= dq; }
+            dq = 1.0;
+            eq = 1.0;
+            store = true;
+        }
+        if (store) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (FULL || c < ltot_r) rq[c] = y[j];
+            }
+            if (lane == 0) { dqs[q] = dq; eqs[q] = eq; nq[q] = bq; }
+        }
+        __syncthreads();
+    }
+    const int any = __syncthreads_or(nrot > 0);
+    if (!any) return;
+    if (lane == 0 && nrot > 0) atomicAdd(rot_mat, nrot);
+    if (r0.dirty) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (FULL || c < ltot_r) __stcg(gp0 + c, make_double2(r0.x[j].x * r0.d, r0.x[j].y * r0.d));
+        }
+    }
+    if (r1.dirty) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (FULL || c < ltot_r) __stcg(gp1 + c, make_double2(r1.x[j].x * r1.d, r1.x[j].y * r1.d));
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int r = 0; r < 8; ++r) bulk_s2g(X + (size_t)(bJ * 8 + r) * ld, rowsJ + (size_t)r * ltot_r, rowbytes);
+        bulk_commit();
+        bulk_wait_all();
+    }
+}
+
+// grid = (nblk / 2, batch), cooperative.  sync: [batch] barrier counters | [2][batch] rotation counters of the even / odd
+// sweeps, all zero on entry.
+template <int CPL, bool FULL, bool REAL>
+__global__ void __launch_bounds__(CROSS_THREADS, 2)
+jacobi_persistent_kernel(cplx* __restrict__ Xall, long long strideX, int ld, int ldot, int ltot_r, int nblk, int max_sweeps,
+                         double tol2, unsigned* __restrict__ sync, unsigned long long* __restrict__ rot_total,
+                         unsigned long long* __restrict__ sweep_total, int* __restrict__ max_sweeps_seen) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [8][ltot_r]
+    __shared__ double nq[8], dqs[8], eqs[8];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int mat = blockIdx.y, slot = blockIdx.x, nslots = gridDim.x, batch = gridDim.y;
+    cplx* X = Xall + (size_t)mat * strideX;
+    unsigned* counter = sync + mat;
+    int* rotbuf = reinterpret_cast<int*>(sync) + batch;      // [2][batch]
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t uses = 0;
+    unsigned epoch = 0;
+    unsigned long long rot_sum = 0ull;
+    int sweeps = 0;
+    while (sweeps < max_sweeps) {
+        int* rot_mat = rotbuf + (size_t)(sweeps & 1) * batch + mat;
+        for (int k = 0; k < nblk; ++k) {
+            const int ncross = mod_cross_pairs(nblk, k);
+            if (slot < ncross) {
+                int bI, bJ;
+                mod_pair(nblk, k, slot, bI, bJ);
+                cross_task_persistent<FULL, REAL>(X, ld, ldot, ltot_r, bI, bJ, rot_mat, tol2, rowsJ, nq, dqs, eqs, &bar, uses & 1u);
+                ++uses;
+            } else {
+                const int bA = k >> 1, bB = bA + (nblk >> 1);
+                selftask_body<CPL, FULL>(X, ld, ldot, ltot_r, bA, bB, rot_mat, tol2, nullptr, 0, 0, REAL);
+            }
+            if (k == 1 && slot == 0 && tid == 0) rotbuf[(size_t)((sweeps + 1) & 1) * batch + mat] = 0;   // next sweep's counter
+            problem_barrier(counter, ++epoch * (unsigned)nslots);
+        }
+        int nrot;
+        asm volatile("ld.relaxed.gpu.s32 %0, [%1];" : "=r"(nrot) : "l"(rot_mat) : "memory");
+        ++sweeps;
+        rot_sum += (unsigned long long)nrot;
+        if (nrot == 0) break;
+    }
+    if (slot == 0 && tid == 0) {
+        atomicAdd(rot_total, rot_sum);
+        atomicAdd(sweep_total, (unsigned long long)sweeps);
+        atomicMax(max_sweeps_seen, sweeps);
+    }
+}
+
 // ---- Gram-assisted round (block of 16 rows per CTA, FP64 tensor cores) -------------------------------
 // Same outer schedule as jacobi_round_kernel<8>, but the long-row arithmetic runs on DMMA:
 //   A. G = P P^H (16x16 Hermitian) over the first ldot columns            -- DMMA, K split over the 8 warps
@@ -2473,6 +2659,54 @@ int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, in
     return 1;
 }
 
+// Cooperative single-launch sweeps (jacobi_persistent_kernel): returns 0 when launched, -1 when the call does not
+// qualify (the caller then takes the multi-launch path), > 0 on errors.
+template <int CPL, bool FULL, bool REAL>
+int launch_persistent_t(const SvdPlan& pl, cplx* X, const SvdState& s, double tol2, cudaStream_t st, bool dry_run) {
+    const int ltot_r = round_up(pl.ltot, 32), nblk = pl.n_pad / 8;
+    const size_t smem = (size_t)8 * ltot_r * sizeof(cplx);
+    auto kern = jacobi_persistent_kernel<CPL, FULL, REAL>;
+    const void* fn = reinterpret_cast<const void*>(kern);
+    if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
+    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    MPSB_CHECK_CUDA(cudaGetDevice(&dev));
+    MPSB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MPSB_CHECK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return -1;
+    MPSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CROSS_THREADS, smem));
+    if ((long long)per_sm * sms < (long long)(nblk / 2) * pl.batch) return -1;
+    if (dry_run) return 0;
+    unsigned* sync = reinterpret_cast<unsigned*>(s.stamps);              // zeroed by the caller; 3 ints per problem
+    cplx* Xp = X;
+    long long strideX = (long long)pl.n_pad * pl.ld;
+    int ld = pl.ld, ldot = pl.ldot, ltr = ltot_r, nb = nblk, ms = pl.max_sweeps;
+    double t2 = tol2;
+    unsigned long long* rt = s.rot_total;
+    unsigned long long* swt = s.sweep_total;
+    int* seen = s.n_active;
+    void* args[] = {&Xp, &strideX, &ld, &ldot, &ltr, &nb, &ms, &t2, &sync, &rt, &swt, &seen};
+    MPSB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nblk / 2, pl.batch), dim3(CROSS_THREADS), args, smem, st));
+    MPSB_COUNT_LAUNCH();
+    return 0;
+}
+int launch_persistent(const SvdPlan& pl, cplx* X, const SvdState& s, double tol2, cudaStream_t st, bool dry_run) {
+    static const int enabled = env_int("MPSB_SVD_PERSISTENT", 1);
+    static const int max_ctas = env_int("MPSB_SVD_PERSISTENT_CTAS", 148);   // beyond one CTA per SM the launches win
+    const int nblk = pl.n_pad / 8, ltot_r = round_up(pl.ltot, 32);
+    if (!enabled || !s.stamps || s.stamp_stride < 3 || (nblk / 2) * pl.batch > max_ctas) return -1;
+    const bool full = (ltot_r == 256 && pl.ldot == 256);
+    if (pl.real) {
+        if (full) return launch_persistent_t<4, true, true>(pl, X, s, tol2, st, dry_run);
+        if (ltot_r > 128) return launch_persistent_t<4, false, true>(pl, X, s, tol2, st, dry_run);
+        if (ltot_r > 64) return launch_persistent_t<2, false, true>(pl, X, s, tol2, st, dry_run);
+        return launch_persistent_t<1, false, true>(pl, X, s, tol2, st, dry_run);
+    }
+    if (full) return launch_persistent_t<4, true, false>(pl, X, s, tol2, st, dry_run);
+    if (ltot_r > 128) return launch_persistent_t<4, false, false>(pl, X, s, tol2, st, dry_run);
+    if (ltot_r > 64) return launch_persistent_t<2, false, false>(pl, X, s, tol2, st, dry_run);
+    return launch_persistent_t<1, false, false>(pl, X, s, tol2, st, dry_run);
+}
+
 size_t resident_smem_bytes(int n_pad, int ld) { return (size_t)n_pad * ld * sizeof(cplx); }
 
 template <int NJ>
@@ -2668,6 +2902,19 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
             prof_mark(3, st);
         }
         if (int rc = launch_resident(pl, X, s, tol2, st)) return rc;
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(&max_sweeps_seen, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
+    } else if (modulus && pl.chunk >= pl.batch && !trace && launch_persistent(pl, X, s, tol2, st, true) == 0) {
+        // few problems: all sweeps in one cooperative launch (no per-step launch latency, no host poll per sweep)
+        if (with_qr) {
+            if (int rc = launch_qr(pl, X, s, state, 0, pl.batch, st)) return rc;
+            prof_mark(3, st);
+        }
+        MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
+        if (int rc = launch_persistent(pl, X, s, tol2, st, false)) {
+            if (rc < 0) set_error("svd: the persistent sweep kernel became unavailable between check and launch");
+            return rc < 0 ? 2 : rc;
+        }
         MPSB_CHECK_CUDA(cudaMemcpyAsync(&max_sweeps_seen, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
     } else {
