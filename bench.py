@@ -219,13 +219,15 @@ def idmrg_batch_leg(n_chains=256, chi=128):
     mv_ms = e0.elapsed_time(e1) / 20
     mv_flop = n_chains * c * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2)
     nmv = statistics.mean(run.n_matvec[-2:])
+    cmv = statistics.mean(run.chain_matvecs[-2:])      # products actually formed (converged chains leave the batch)
     sec = statistics.mean(times[-2:])
-    flop = n_chains * c * (nmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + 4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2)
+    flop = c * (cmv * (2 * w * d * d * chi ** 3 + 2 * w * w * d ** 3 * chi ** 2) + n_chains * (4 * w * d * chi ** 3 + 2 * w * w * d * d * chi ** 2))
     e = run.energy_per_site()
     return {"workload": f"{n_chains} TFIM chains, g/J = 0.2 .. 2.0, chi = {chi}, d = 2, w = 3, "
                         f"{'real arithmetic (real MPO)' if run.real else 'complex128'}, lock-step growth",
             "flops_per_multiply_add": c,
             "ms_per_growth_step": 1e3 * sec, "chain_steps_per_s": n_chains / sec, "matvecs_per_step": nmv,
+            "matvecs_per_chain_mean": cmv / n_chains,
             "contraction_tflops": flop / sec / 1e12,
             "matvec_only": {"ms": mv_ms, "tflops": mv_flop / (mv_ms * 1e-3) / 1e12,
                             "note": "mpsb_heff_matvec_batched(_real) alone (incl. its per-call MPO / environment preparation), "

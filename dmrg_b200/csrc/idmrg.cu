@@ -298,6 +298,8 @@ int heff_matvec_impl(int batch, int chil, int chir, int d, int w, const void* L,
 }
 
 
+unsigned long long g_last_chain_matvecs = 0ull;
+
 constexpr int LANCZOS_KEEP = 8;        // Ritz vectors carried across a (thick) restart
 constexpr int LANCZOS_NCHUNK = 64;
 
@@ -307,7 +309,29 @@ size_t lanczos_bytes(int batch, int chil, int chir, int d, int w, int krylov, si
     const size_t b = (size_t)batch;
     return heff_bytes(chil, chir, d, w, batch, esz) + b * al(n * esz) * (kk + LANCZOS_KEEP) +
            al(b * kk * (LANCZOS_NCHUNK + 1) * esz) + al(b * kk * kk * esz) * 2 + al(b * kk * esz) +
-           al(b * kk * LANCZOS_KEEP * esz);
+           al(b * kk * LANCZOS_KEEP * esz) +
+           // compacted copies of the per-chain operators for the chains still iterating, and two index lists
+           al(b * w * chil * chil * esz) + al(b * w * chir * chir * esz) + al(b * w * w * d * d * d * d * esz) +
+           al(2 * b * sizeof(int));
+}
+
+// dst[j][0:len) = src[idx[j]][0:len): moves the data of the chains that are still iterating into consecutive slots
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(T* __restrict__ dst, long long sd, const T* __restrict__ src, long long ss, const int* __restrict__ idx,
+                   long long len) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    dst[(size_t)blockIdx.y * sd + e] = src[(size_t)idx[blockIdx.y] * ss + e];
+}
+template <typename T>
+int gather_rows(T* dst, long long sd, const T* src, long long ss, const int* idx, long long len, int count, cudaStream_t st) {
+    if (count == 0 || len == 0) return 0;
+    dim3 grid((unsigned)((len + 255) / 256), count);
+    gather_rows_kernel<T><<<grid, 256, 0, st>>>(dst, sd, src, ss, idx, len);
+    MPSB_COUNT_LAUNCH();
+    MPSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // Thick-restart Lanczos with full (twice-applied) reorthogonalisation for `batch` independent chains in lock step
@@ -356,11 +380,24 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
     T* C1 = reinterpret_cast<T*>(p);                p += al(nb * kk * kk * sizeof(T));   // pass-1 coefficients, row j
     T* C2 = reinterpret_cast<T*>(p);                p += al(nb * kk * kk * sizeof(T));   // pass-2 coefficients
     T* N2 = reinterpret_cast<T*>(p);                p += al(nb * kk * sizeof(T));        // ||w_j||^2
-    T* Yd = reinterpret_cast<T*>(p);                                                          // [chain][keep][kk]
+    T* Yd = reinterpret_cast<T*>(p);                p += al(nb * kk * LANCZOS_KEEP * sizeof(T));    // [chain][keep][kk]
+    const size_t nLt = (size_t)w * chil * chil, nR = (size_t)w * chir * chir, nWW = (size_t)w * w * d * d * d * d;
+    T* Lt_c = reinterpret_cast<T*>(p);              p += al(nb * nLt * sizeof(T));
+    T* R_c = reinterpret_cast<T*>(p);               p += al(nb * nR * sizeof(T));
+    T* WW_c = reinterpret_cast<T*>(p);              p += al(nb * nWW * sizeof(T));
+    int* idx_d = reinterpret_cast<int*>(p);                                                     // [2][batch]
     T* th = static_cast<T*>(theta);
+    // Slots: the batched launches of a cycle run over the chains that are still iterating (`nact` of them, slot ->
+    // chain in slot2chain).  Chains that converge are frozen at a restart and the remaining ones move up into the first
+    // slots (their bases by gather_rows, their operators re-gathered from the full set), so a coupling sweep whose
+    // chains need 40 ... 90 products does not carry the finished ones along.
+    int nact = batch;
+    std::vector<int> slot2chain(nb);
+    for (size_t i = 0; i < nb; ++i) slot2chain[i] = (int)i;
+    const Heff<T> hfull = h;
     auto bat = [&](long long sv, long long sw, long long sc) {
         BlasBatch b;
-        b.batch = batch; b.sV = sv; b.sw = sw; b.sc = sc; b.spart = sPart;
+        b.batch = nact; b.sV = sv; b.sw = sw; b.sc = sc; b.spart = sPart;
         return b;
     };
     struct Chain {
@@ -374,6 +411,7 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
     for (auto& c : ch) c.Hp.assign((size_t)m * m, 0.0);
     std::vector<T> h1(nb * kk * kk), h2(nb * kk * kk), hn(nb * kk), hc(nb * kk * LANCZOS_KEEP);
     int n_mv = 0;
+    unsigned long long chain_mv = 0ull;          // products actually formed, summed over the chains that took part
 
     MPSB_CHECK_CUDA(cudaMemsetAsync(part, 0, al(nb * kk * (nchunk + 1) * sizeof(T)), st));
     // normalise the start vectors into V[chain][0]
@@ -406,18 +444,19 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
     // Ritz data of the bases V[chain][0 .. formed): per live chain T (eigenvalues on the diagonal), Y, idx (ascending),
     // E, resid, mm.
     auto evaluate = [&](int formed) -> int {
+        const size_t na = (size_t)nact;
         MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h1.data(), kk * kk * sizeof(T), C1, kk * kk * sizeof(T),
-                                          sizeof(T) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
+                                          sizeof(T) * kk * formed, na, cudaMemcpyDeviceToHost, st));
         MPSB_CHECK_CUDA(cudaMemcpy2DAsync(h2.data(), kk * kk * sizeof(T), C2, kk * kk * sizeof(T),
-                                          sizeof(T) * kk * formed, nb, cudaMemcpyDeviceToHost, st));
-        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(T), N2, kk * sizeof(T), sizeof(T) * formed, nb,
+                                          sizeof(T) * kk * formed, na, cudaMemcpyDeviceToHost, st));
+        MPSB_CHECK_CUDA(cudaMemcpy2DAsync(hn.data(), kk * sizeof(T), N2, kk * sizeof(T), sizeof(T) * formed, na,
                                           cudaMemcpyDeviceToHost, st));
         auto tb = now();
         MPSB_CHECK_CUDA(cudaStreamSynchronize(st));
         auto tc = now();
         t_wait += us(tb, tc);
-        auto solve_chain = [&](size_t ci) {
-            Chain& c = ch[ci];
+        auto solve_chain = [&](size_t ci) {             // ci: slot
+            Chain& c = ch[slot2chain[ci]];
             if (c.frozen) return;
             const T* a1 = h1.data() + ci * kk * kk;
             const T* a2 = h2.data() + ci * kk * kk;
@@ -451,13 +490,13 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
             c.resid = std::fabs(c.beta_last * c.Y[(size_t)(mm - 1) * mm + best]);
         };
         // the projected eigenproblems of the chains are independent: spread them over a few host threads
-        const unsigned nthr = (unsigned)std::max<size_t>(1, std::min<size_t>({nb / 8, (size_t)16, (size_t)std::thread::hardware_concurrency()}));
+        const unsigned nthr = (unsigned)std::max<size_t>(1, std::min<size_t>({na / 8, (size_t)16, (size_t)std::thread::hardware_concurrency()}));
         if (nthr <= 1) {
-            for (size_t ci = 0; ci < nb; ++ci) solve_chain(ci);
+            for (size_t ci = 0; ci < na; ++ci) solve_chain(ci);
         } else {
             std::vector<std::thread> pool;
             for (unsigned t = 0; t < nthr; ++t)
-                pool.emplace_back([&, t] { for (size_t ci = t; ci < nb; ci += nthr) solve_chain(ci); });
+                pool.emplace_back([&, t] { for (size_t ci = t; ci < na; ci += nthr) solve_chain(ci); });
             for (auto& th_ : pool) th_.join();
         }
         t_host += us(tc, now());
@@ -475,6 +514,7 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
             rc = heff_apply(h, vj, wv, st, sV, sV);
             if (rc) return rc;
             ++n_mv;
+            chain_mv += (unsigned long long)nact;
             // Gram-Schmidt in two passes.  Pass 1 is the Lanczos recurrence itself: it removes the large components
             // along v_j and v_{j-1} (right after a (re)start: along every basis vector, the kept Ritz vectors all couple
             // to the continued one), so that pass 2 - the full reorthogonalisation - subtracts only rounding-level
@@ -518,34 +558,40 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
         auto tc = now();
         const bool last = restart + 1 == max_restarts;
         all_done = true;
-        std::vector<char> finish(nb, 0);
-        for (size_t ci = 0; ci < nb; ++ci) {
-            Chain& c = ch[ci];
+        const size_t na = (size_t)nact;
+        std::vector<char> finish(na, 0);                 // per slot
+        for (size_t si = 0; si < na; ++si) {
+            Chain& c = ch[slot2chain[si]];
             if (c.frozen) continue;
-            if (small_enough(c) || c.mm < formed || formed < m || last) finish[ci] = 1;
+            if (small_enough(c) || c.mm < formed || formed < m || last) finish[si] = 1;
             else all_done = false;
         }
         const int keep = all_done ? 1 : std::min(LANCZOS_KEEP, m - 1);
         // Ritz vectors Vk[chain][i] = sum_q Y[q][idx[i]] V[chain][q]   (zero coefficients beyond a chain's own mm)
         std::fill(hc.begin(), hc.end(), Sc<T>::zero());
-        for (size_t ci = 0; ci < nb; ++ci) {
-            const Chain& c = ch[ci];
+        for (size_t si = 0; si < na; ++si) {
+            const Chain& c = ch[slot2chain[si]];
             if (c.frozen) continue;
             const int kc = std::min(keep, c.mm);
             for (int i = 0; i < kc; ++i)
                 for (int q = 0; q < c.mm; ++q)
-                    hc[ci * kk * LANCZOS_KEEP + (size_t)i * kk + q] = Sc<T>::from_re(c.Y[(size_t)q * c.mm + c.idx[i]]);
+                    hc[si * kk * LANCZOS_KEEP + (size_t)i * kk + q] = Sc<T>::from_re(c.Y[(size_t)q * c.mm + c.idx[i]]);
         }
-        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(T) * nb * kk * LANCZOS_KEEP, cudaMemcpyHostToDevice, st));
-        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, nb * al(n * sizeof(T)) * LANCZOS_KEEP, st));
+        MPSB_CHECK_CUDA(cudaMemcpyAsync(Yd, hc.data(), sizeof(T) * na * kk * LANCZOS_KEEP, cudaMemcpyHostToDevice, st));
+        MPSB_CHECK_CUDA(cudaMemsetAsync(Vk, 0, na * al(n * sizeof(T)) * LANCZOS_KEEP, st));
         for (int i = 0; i < keep; ++i) {
             rc = zaxpy_multi(V, (long long)vstride, formed, (long long)n, Yd + (size_t)i * kk, 1.0, Vk + (size_t)i * vstride, st,
                              bat(sV, sVk, sY));
             if (rc) return rc;
         }
-        for (size_t ci = 0; ci < nb; ++ci) {          // freeze the chains that finished in this cycle
-            if (!finish[ci]) continue;
-            MPSB_CHECK_CUDA(cudaMemcpyAsync(th + ci * (size_t)s_theta, Vk + ci * (size_t)sVk, n * sizeof(T),
+        std::vector<int> keep_slots, keep_chains;      // slots (chains) that go on iterating, ascending
+        for (size_t si = 0; si < na; ++si) {           // freeze the chains that finished in this cycle
+            const int ci = slot2chain[si];
+            if (!finish[si]) {
+                if (!ch[ci].frozen) { keep_slots.push_back((int)si); keep_chains.push_back(ci); }
+                continue;
+            }
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(th + (size_t)ci * (size_t)s_theta, Vk + si * (size_t)sVk, n * sizeof(T),
                                             cudaMemcpyDeviceToDevice, st));
             ch[ci].frozen = true;
         }
@@ -556,11 +602,34 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
             MPSB_CHECK_CUDA(cudaMemcpyAsync(V + (size_t)keep * vstride, V + (size_t)m * vstride, n * sizeof(T),
                                             cudaMemcpyDeviceToDevice, st));
             MPSB_CHECK_CUDA(cudaMemcpyAsync(V, Vk, al(n * sizeof(T)) * keep, cudaMemcpyDeviceToDevice, st));
-        } else {
+        } else if ((int)keep_slots.size() == nact) {   // nobody left: same slots
             MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V + (size_t)keep * vstride, (size_t)sV * sizeof(T), V + (size_t)m * vstride,
-                                              (size_t)sV * sizeof(T), n * sizeof(T), nb, cudaMemcpyDeviceToDevice, st));
+                                              (size_t)sV * sizeof(T), n * sizeof(T), na, cudaMemcpyDeviceToDevice, st));
             MPSB_CHECK_CUDA(cudaMemcpy2DAsync(V, (size_t)sV * sizeof(T), Vk, (size_t)sVk * sizeof(T),
-                                              al(n * sizeof(T)) * keep, nb, cudaMemcpyDeviceToDevice, st));
+                                              al(n * sizeof(T)) * keep, na, cudaMemcpyDeviceToDevice, st));
+        } else {
+            // The survivors move up into slots 0 .. nkeep-1.  Within V only index m of a slot is read and only indices
+            // 0 .. keep (< m) of a slot are written, so the in-place gather of the residual vectors is safe.
+            const int nkeep = (int)keep_slots.size();
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(idx_d, keep_slots.data(), sizeof(int) * nkeep, cudaMemcpyHostToDevice, st));
+            MPSB_CHECK_CUDA(cudaMemcpyAsync(idx_d + nb, keep_chains.data(), sizeof(int) * nkeep, cudaMemcpyHostToDevice, st));
+            rc = gather_rows<T>(V + (size_t)keep * vstride, sV, V + (size_t)m * vstride, sV, idx_d, (long long)n, nkeep, st);
+            if (rc) return rc;
+            rc = gather_rows<T>(V, sV, Vk, sVk, idx_d, (long long)(vstride * keep), nkeep, st);
+            if (rc) return rc;
+            rc = gather_rows<T>(Lt_c, (long long)nLt, hfull.Lt, (long long)nLt, idx_d + nb, (long long)nLt, nkeep, st);
+            if (rc) return rc;
+            rc = gather_rows<T>(R_c, (long long)nR, hfull.R, hfull.sR, idx_d + nb, (long long)nR, nkeep, st);
+            if (rc) return rc;
+            h.Lt = Lt_c; h.R = R_c; h.sR = (long long)nR;
+            if (hfull.sWW != 0) {
+                rc = gather_rows<T>(WW_c, (long long)nWW, hfull.WW, hfull.sWW, idx_d + nb, (long long)nWW, nkeep, st);
+                if (rc) return rc;
+                h.WW = WW_c;
+            }
+            for (int i = 0; i < nkeep; ++i) slot2chain[i] = keep_chains[i];
+            nact = nkeep;
+            h.batch = nact;
         }
         for (Chain& c : ch) {
             if (c.frozen) continue;
@@ -574,6 +643,9 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
     if (dbg) fprintf(stderr, "[mpsb] lanczos: %d chains, %d matvecs, enqueue %.0f us, wait %.0f us, host ritz %.0f us\n", batch,
                      n_mv, t_enq, t_wait, t_host);
     // returned vectors: lowest Ritz vectors, renormalised; Rayleigh quotients and true residuals with one more product
+    // (all chains again, with the operators as given)
+    nact = batch;
+    h = hfull;
     rc = zdotc_multi(th, 0, 1, (long long)n, th, N2, part, nchunk, (int)kk, st, bat(s_theta, s_theta, sN));
     if (rc) return rc;
     rc = znormalise((long long)n, N2, th, st, bat(0, s_theta, sN));
@@ -582,6 +654,8 @@ int lanczos_impl(int batch, int chil, int chir, int d, int w, const void* L, lon
     rc = heff_apply(h, th, hv, st, s_theta, sV);
     if (rc) return rc;
     ++n_mv;
+    chain_mv += (unsigned long long)batch;
+    g_last_chain_matvecs = chain_mv;
     rc = zdotc_multi(th, 0, 1, (long long)n, hv, C1, part, nchunk, (int)kk, st, bat(s_theta, sV, sC));
     if (rc) return rc;
     rc = zaxpy_multi(th, 0, 1, (long long)n, C1, -1.0, hv, st, bat(s_theta, sV, sC));
@@ -720,6 +794,8 @@ int mpsb_heff_matvec(int chil, int chir, int d, int w, const void* L, const void
                      void* out, void* ws, size_t ws_bytes, void* stream) {
     return mpsb_heff_matvec_batched(1, chil, chir, d, w, L, 0, W, 0, R, 0, theta, 0, out, 0, ws, ws_bytes, stream);
 }
+
+unsigned long long mpsb_last_lanczos_chain_matvecs(void) { return g_last_chain_matvecs; }
 
 size_t mpsb_lanczos_batched_workspace(int batch, int chil, int chir, int d, int w, int krylov) {
     return lanczos_bytes(batch, chil, chir, d, w, krylov, sizeof(cplx));

@@ -390,7 +390,8 @@ def ground_state_batched(Ld, Md, Rd, seed=0, theta0=None):
                   nel, KRYLOV, MAX_RESTARTS, TOL, E, resid, ctypes.byref(nmv), ws, wsn, _lib.stream_ptr()),
                "mpsb_lanczos_ground_batched")
     E, resid = np.array(E[:]), np.array(resid[:])
-    last_info.update(n_matvec=nmv.value, residual=float(resid.max()))
+    last_info.update(n_matvec=nmv.value, residual=float(resid.max()),
+                     chain_matvecs=int(lib.mpsb_last_lanczos_chain_matvecs()))
     _warn_if_residual_large(E, resid)
     return E, theta
 
@@ -452,6 +453,7 @@ class ChainBatch:
         R[:, 0, 0, right_index] = 1
         self.W, self.L, self.R = _to_device_auto(self.real, W, L, R)
         self.energies, self.n_matvec, self.S = [], [], None
+        self.chain_matvecs = []       # H_eff products per step summed over the chains that formed them (frozen chains drop out)
         self.sites = 0
 
     def _prediction(self):
@@ -487,6 +489,7 @@ class ChainBatch:
         self.sites += 2
         self.energies.append(E)
         self.n_matvec.append(last_info["n_matvec"])
+        self.chain_matvecs.append(last_info["chain_matvecs"])
         return E
 
     def energy_per_site(self):

@@ -171,8 +171,9 @@ int mpsb_lanczos_ground(int chil, int chir, int d, int w, const void* L, const v
                         int* n_matvec_host, void* ws, size_t ws_bytes, void* stream);
 
 /* The same for `batch` chains in lock step: every product, orthogonalisation pass and update is one batched launch;
- * a chain that has converged is frozen (its vector is final) while the others finish.  energy_host and resid_host
- * receive `batch` values, n_matvec_host the common number of products. */
+ * a chain that has converged is frozen at the next restart (its vector is final) and leaves the batch: the chains still
+ * iterating move up into consecutive slots, so later cycles only pay for them.  energy_host and resid_host receive
+ * `batch` values, n_matvec_host the number of products of the slowest chain. */
 size_t mpsb_lanczos_batched_workspace(int batch, int chil, int chir, int d, int w, int krylov);
 int mpsb_lanczos_ground_batched(int batch, int chil, int chir, int d, int w, const void* L, long long sL, const void* W,
                                 long long sW, const void* R, long long sR, void* theta, long long s_theta, int krylov,
@@ -183,6 +184,11 @@ int mpsb_lanczos_ground_batched_real(int batch, int chil, int chir, int d, int w
                                      const void* W, long long sW, const void* R, long long sR, void* theta,
                                      long long s_theta, int krylov, int max_restarts, double tol, double* energy_host,
                                      double* resid_host, int* n_matvec_host, void* ws, size_t ws_bytes, void* stream);
+
+/* H_eff products formed by the last (batched) Lanczos call of this process, summed over the chains that took part in
+ * each: chains that have converged are frozen at a restart and leave the batched launches, so this is less than
+ * batch * n_matvec for a coupling sweep whose chains need different numbers of products. */
+unsigned long long mpsb_last_lanczos_chain_matvecs(void);
 
 /* Environment growth (DMRG/iDMRG.py:59-60, with the conjugation on the bra leg — SURVEY App. B1):
  *     L'[A,B,C] = sum L[i,j,k] conj(U[i,l,A]) U[j,m,B] W[k,C,l,m]        U [chi][d][chin]
