@@ -1913,6 +1913,8 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
     // Round 0 of a sweep (and the single-CTA case) plays the complete 16-row tournament so that pairs inside a
     // block are covered; later rounds only need the 8 x 8 cross pairs between the two blocks.
     const int nsteps = (round == 0 || nblk == 2) ? GR - 1 : 8;
+    const int b_reps = (inner_sweeps >> 16) > 0 ? (inner_sweeps >> 16) : 1;      // high half: tournament repetitions
+    inner_sweeps &= 0xffff;
     const int ei = tid >> 4, ej = tid & 15;          // element of G / Q owned by this thread
     int total_rot = 0;
     for (int sw = 0; sw < inner_sweeps; ++sw) {
@@ -1952,7 +1954,14 @@ jacobi_gram_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld,
         __syncthreads();
         // ---- B. tournament on G ------------------------------------------------------------------------
         const long long tB = phase_clk ? clock64() : 0;
-        const int nrot = gram_tournament(sm, nsteps, tol2, tid, ei, ej);
+        // the tournament may be repeated on the maintained Gram block (G <- Q^H G Q stays current), so that a visit
+        // orthogonalises its 16 rows further without another pass over the long rows
+        int nrot = 0;
+        for (int rep = 0; rep < b_reps; ++rep) {
+            const int r = gram_tournament(sm, nsteps, tol2, tid, ei, ej);
+            nrot += r;
+            if (r == 0) break;
+        }
         const long long tC = phase_clk ? clock64() : 0;
         if (phase_clk && tid == 0) {
             atomicAdd(&phase_clk[4], (unsigned long long)(tB - tA));
@@ -2083,6 +2092,8 @@ jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, i
     };
 
     const int nsteps = (round == 0 || nblk == 2) ? GR - 1 : 8;
+    const int b_reps = (inner_sweeps >> 16) > 0 ? (inner_sweeps >> 16) : 1;
+    inner_sweeps &= 0xffff;
     const int ei = tid >> 4, ej = tid & 15;
     const int ntA = (ldot + TILE_W - 1) / TILE_W, ntC = (ltot_r + TILE_W - 1) / TILE_W;
     int total_rot = 0;
@@ -2129,7 +2140,14 @@ jacobi_gram_tiled_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, i
         }
         __syncthreads();
         // ---- B. tournament on G ------------------------------------------------------------------------------
-        const int nrot = gram_tournament(sm, nsteps, tol2, tid, ei, ej);
+        // the tournament may be repeated on the maintained Gram block (G <- Q^H G Q stays current), so that a visit
+        // orthogonalises its 16 rows further without another pass over the long rows
+        int nrot = 0;
+        for (int rep = 0; rep < b_reps; ++rep) {
+            const int r = gram_tournament(sm, nsteps, tol2, tid, ei, ej);
+            nrot += r;
+            if (r == 0) break;
+        }
         if (nrot == 0) break;
         total_rot += nrot;
         // ---- C. P <- Q^H P, tile by tile ------------------------------------------------------------------------
@@ -2503,6 +2521,10 @@ int launch_qr_grid(const SvdPlan& pl, cplx* X, double* frob2, unsigned char* scr
     return 0;
 }
 
+int gram_reps() {
+    static const int r = std::max(1, std::min(16, env_int("MPSB_GRAM_REPS", 1)));
+    return r;
+}
 size_t gram_smem_bytes(int ltot_r) {
     return ((sizeof(GramSmem) + 127) / 128) * 128 + (size_t)GR * (ltot_r + GRAM_PAD) * sizeof(cplx);
 }
@@ -2519,7 +2541,7 @@ int launch_gram(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int cou
     const int nblk = pl.n_pad / 8;
     dim3 grid(nblk / 2, count);
     kern<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot, ltot_r,
-                                          nblk, round, inner, s.rot, s.done, tol2,
+                                          nblk, round, inner | (gram_reps() << 16), s.rot, s.done, tol2,
                                           g_prof.enabled > 1 ? s.phase_clk : nullptr,
                                           nblk == pl.n_pad / pl.bsz ? s.stamps : nullptr, s.stamp_stride,
                                           launch_id);
@@ -2540,7 +2562,7 @@ int launch_gram_tiled(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, i
     const int nblk = pl.n_pad / 8;
     dim3 grid(nblk / 2, count);
     kern<<<grid, GRAM_THREADS, smem, st>>>(X, (long long)pl.n_pad * pl.ld, mat0, pl.ld, pl.ldot,
-                                          ltot_r, nblk, round, inner, s.rot, s.done, tol2, s.stamps,
+                                          ltot_r, nblk, round, inner | (gram_reps() << 16), s.rot, s.done, tol2, s.stamps,
                                           s.stamp_stride, launch_id);
     MPSB_COUNT_LAUNCH();
     MPSB_CHECK_CUDA(cudaGetLastError());
