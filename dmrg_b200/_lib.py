@@ -54,6 +54,8 @@ SIGNATURES = {
     "mpsb_predict_theta_batched_real": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mpsb_transpose_batched_real": (_i, [_i, _i, _i, _vp, _i, _ll, _vp, _i, _ll, _vp]),
     "mpsb_last_lanczos_chain_matvecs": (_c.c_ulonglong, []),
+    "mpsb_left_vectors_workspace": (_sz, [_i, _i, _i, _i]),
+    "mpsb_left_vectors": (_i, [_i, _i, _i, _i, _vp, _i, _ll, _vp, _vp, _ll, _vp, _i, _vp, _sz, _vp]),
     "mpsb_lanczos_batched_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mpsb_lanczos_ground_batched": (_i, [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _d, _pd, _pd, _pi,
                                          _vp, _sz, _vp]),

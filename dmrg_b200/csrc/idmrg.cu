@@ -764,6 +764,90 @@ int env_common(int right, int batch, int chi, int chin, int d, int w, const void
 }
 
 
+// ---- left singular vectors from the right ones (split of large two-site tensors) ----------------------------------
+// halve (DMRG/iDMRG.py:17-35) needs U and V.  For rows too long to carry an identity through the Jacobi sweeps the
+// second factor used to come from a second SVD (of A^H).  With Vh and S of the first one,
+//     Y = A Vh^H diag(1/S)                       (one GEMM; columns orthonormal up to eps * S_0 / S_i)
+//     U = two Newton-Schulz steps  Y <- Y (3 I - Y^H Y) / 2  (the defect e becomes ~ e^2, then ~ e^4)
+// gives the partner basis of V (the same phases, the same choice inside degenerate multiplets) at the cost of three
+// GEMMs.  The caller uses it only while S_k / S_0 is large enough for e << 1 (iDMRG.SPLIT_CUTOFF).
+template <typename T>
+__global__ void __launch_bounds__(256)
+inv_scale_rows_kernel(int rows, int cols, const T* __restrict__ in, const double* __restrict__ sv, T* __restrict__ out,
+                      long long s_in, long long s_sv, long long s_out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)rows * cols) return;
+    const int i = (int)(e / cols);
+    const double v = sv[(size_t)blockIdx.y * s_sv + i];
+    out[(size_t)blockIdx.y * s_out + e] = Sc<T>::scale(in[(size_t)blockIdx.y * s_in + e], v > 0.0 ? 1.0 / v : 0.0);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) ns_matrix_kernel(int k, const T* __restrict__ G, T* __restrict__ M) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)k * k) return;
+    const size_t off = (size_t)blockIdx.y * k * k + e;
+    const int i = (int)(e / k), j = (int)(e - (long long)i * k);
+    M[off] = Sc<T>::add(Sc<T>::from_re(i == j ? 1.5 : 0.0), Sc<T>::scale(G[off], -0.5));
+}
+
+size_t left_vectors_bytes(int batch, int rows, int cols, int k, size_t esz) {
+    const size_t b = (size_t)batch;
+    return al(b * k * cols * esz) + al(b * rows * k * esz) + 2 * al(b * k * k * esz);
+}
+
+// A [batch][rows][cols] (pitch lda, stride sA), Vh [batch][k][cols], S [batch][.] (stride sS, first k used),
+// U_out [batch][rows][k]
+template <typename T>
+int left_vectors_impl(int batch, int rows, int cols, int k, const void* A, int lda, long long sA, const void* Vh,
+                      const double* S, long long sS, void* U_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MPSB_REQUIRE(batch >= 1 && batch <= 65535 && rows >= 1 && cols >= 1 && k >= 1 && k <= rows && k <= cols && A && Vh && S && U_out,
+                 "left_vectors: bad arguments");
+    const size_t need = left_vectors_bytes(batch, rows, cols, k, sizeof(T));
+    MPSB_REQUIRE(ws && ws_bytes >= need, "left_vectors: workspace %zu B < required %zu B", ws_bytes, need);
+    const size_t b = (size_t)batch;
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    T* Vs = reinterpret_cast<T*>(p); p += al(b * k * cols * sizeof(T));
+    T* Y = reinterpret_cast<T*>(p);  p += al(b * rows * k * sizeof(T));
+    T* G = reinterpret_cast<T*>(p);  p += al(b * k * k * sizeof(T));
+    T* M = reinterpret_cast<T*>(p);
+    {
+        dim3 grid((unsigned)(((long long)k * cols + 255) / 256), batch);
+        inv_scale_rows_kernel<T><<<grid, 256, 0, st>>>(k, cols, static_cast<const T*>(Vh), S, Vs, (long long)k * cols, sS,
+                                                       (long long)k * cols);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+    }
+    GemmArgsT<T> g;
+    g.batch1 = batch; g.batch2 = 1; g.sA2 = g.sB2 = g.sC2 = 0; g.accumulate = 0;
+    // Y = A Vs^H
+    g.A = static_cast<const T*>(A); g.B = Vs; g.C = Y; g.M = rows; g.N = k; g.K = cols; g.lda = lda; g.ldb = cols; g.ldc = k;
+    g.opA = 0; g.opB = 2; g.sA1 = sA; g.sB1 = (long long)k * cols; g.sC1 = (long long)rows * k;
+    int rc = gemm(g, st);
+    if (rc) return rc;
+    // two Newton-Schulz steps  Y <- Y (3 I - Y^H Y) / 2:  a defect e = |Y^H Y - I| becomes ~e^2, then ~e^4
+    T* src = Y;
+    T* dst = static_cast<T*>(U_out);
+    for (int step = 0; step < 2; ++step) {
+        g.A = src; g.B = src; g.C = G; g.M = k; g.N = k; g.K = rows; g.lda = k; g.ldb = k; g.ldc = k; g.opA = 2; g.opB = 0;
+        g.sA1 = (long long)rows * k; g.sB1 = (long long)rows * k; g.sC1 = (long long)k * k;
+        rc = gemm(g, st);
+        if (rc) return rc;
+        dim3 grid((unsigned)(((long long)k * k + 255) / 256), batch);
+        ns_matrix_kernel<T><<<grid, 256, 0, st>>>(k, G, M);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+        g.A = src; g.B = M; g.C = dst; g.M = rows; g.N = k; g.K = k; g.lda = k; g.ldb = k; g.ldc = k;
+        g.opA = 0; g.opB = 0; g.sA1 = (long long)rows * k; g.sB1 = (long long)k * k; g.sC1 = (long long)rows * k;
+        rc = gemm(g, st);
+        if (rc) return rc;
+        T* t = src; src = dst; dst = t;
+    }
+    // after two steps the result sits in Y again
+    MPSB_CHECK_CUDA(cudaMemcpyAsync(U_out, Y, b * rows * k * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 }  // namespace
 }  // namespace mpsb
 
@@ -873,6 +957,15 @@ int mpsb_env_right_batched_real(int batch, int chi, int chin, int d, int w, cons
                                 long long sV, const void* W, long long sW, void* R_out, long long sRo, void* ws,
                                 size_t ws_bytes, void* stream) {
     return env_common<double>(1, batch, chi, chin, d, w, R, sR, V, sV, W, sW, 0, R_out, sRo, ws, ws_bytes, stream);
+}
+
+size_t mpsb_left_vectors_workspace(int batch, int rows, int cols, int k) {
+    return left_vectors_bytes(batch, rows, cols, k, sizeof(cplx));
+}
+int mpsb_left_vectors(int batch, int rows, int cols, int k, const void* A, int lda, long long sA, const void* Vh,
+                      const double* S, long long sS, void* U_out, int real, void* ws, size_t ws_bytes, void* stream) {
+    if (real) return left_vectors_impl<double>(batch, rows, cols, k, A, lda, sA, Vh, S, sS, U_out, ws, ws_bytes, stream);
+    return left_vectors_impl<cplx>(batch, rows, cols, k, A, lda, sA, Vh, S, sS, U_out, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -19,6 +19,10 @@ from .MPO import MPO  # noqa: F401  (re-exported like the reference does)
 from .MPS import _device_svd
 
 REAL_PATH = True     # real L, W, R (MPO.tomatrix(dtype='double'), DMRG/MPO.py:68-76) run in real arithmetic (DGEMM on DMMA)
+# large splits: U = theta V^H S^-1 (+ two Newton-Schulz steps) while S_k / S_0 stays above this.  The columns start
+# orthonormal to e = eps S_0 / S_k; the symmetric re-orthonormalisation spreads that defect over ALL columns, the
+# dominant ones included, so e <= 2e-11 is what keeps them at the 1e-10 level of the parity target
+SPLIT_CUTOFF = 1e-5
 KRYLOV = 24          # Lanczos basis size between restarts
 MAX_RESTARTS = 60
 TOL = 1e-13          # residual target relative to max(1, |E|)
@@ -81,17 +85,43 @@ def halve(psi, sh, trunc=10):
 
 
 def _halve_split(theta, sh, trunc):
-    """U and V of the two-site tensor from two independent row-orthogonalisations (of psi and of psi^H) instead of
-    one with carried identity columns: rows stay half as long, which keeps chi <= 128 on the register-resident
-    Jacobi kernel.  U and V then carry unrelated phases per singular vector - harmless for `next_LR`, whose two
-    environment updates use them separately (DMRG/iDMRG.py:59-60)."""
+    """Split of a two-site tensor whose rows are too long to carry an identity through the Jacobi sweeps: V and S
+    from a row-orthogonalisation of psi (rows stay short: register-resident kernel up to chi = 128, half the tile
+    traffic beyond), then U = psi V^H S^-1 re-orthonormalised by two Newton-Schulz steps (`mpsb_left_vectors`) - the
+    Schmidt partners of V, also inside a degenerate multiplet that `trunc` cuts.  When the kept spectrum reaches below
+    SPLIT_CUTOFF * S_0 that product is not orthonormal to working precision any more and U comes from a second,
+    independent row-orthogonalisation of psi^H (orthonormal always; its phases and its choice inside a cut multiplet
+    are then unrelated to V's - harmless for `next_LR`, whose two environment updates use U and V separately,
+    DMRG/iDMRG.py:59-60)."""
     lsize, rsize = sh[0] * sh[1], sh[2] * sh[3]
     A = theta.reshape(lsize, rsize)
     _, s_all, vh, k = _device_svd(A, lsize, rsize, trunc, 0.0, want_u=False, normalise=0)
+    U = _left_vectors(A.reshape(1, lsize, rsize), vh.reshape(1, k, rsize), s_all.reshape(1, -1), k)
+    if U is not None:                                       # Schmidt partners of V from three GEMMs
+        return U.reshape(sh[0], sh[1], k), s_all, vh.reshape(k, sh[2], sh[3])
     _, _, uh, k2 = _device_svd(_lib.conj_transpose(A), rsize, lsize, trunc, 0.0, want_u=False, normalise=0)
     assert k == k2
     U = _lib.conj_transpose(uh)
     return U.reshape(sh[0], sh[1], k), s_all, vh.reshape(k, sh[2], sh[3])
+
+
+def _left_vectors(A, vh, s_all, k):
+    """U [n, rows, k] = A Vh^H S^-1, re-orthonormalised by two Newton-Schulz steps (`mpsb_left_vectors`), or None when
+    some chain's kept spectrum reaches below SPLIT_CUTOFF * S_0 (the columns of the small values would then not be
+    orthonormal to working precision and the caller takes them from a second SVD)."""
+    s_host = _lib.to_host(s_all)[:, :k]
+    if not np.all(s_host[:, k - 1] > SPLIT_CUTOFF * s_host[:, 0]):
+        return None
+    lib = _lib.load()
+    n, rows, cols = (int(v) for v in A.shape)
+    real = _is_real_t(A)
+    U = _lib.empty((n, rows, k), "f64" if real else "c128")
+    A = A.contiguous()
+    ws, wsn = _lib.workspace(lib.mpsb_left_vectors_workspace(n, rows, cols, k))
+    _lib.check(lib.mpsb_left_vectors(n, rows, cols, k, _lib.ptr(A), cols, rows * cols, _lib.ptr(vh.contiguous()),
+                                     _lib.ptr(s_all), int(s_all.shape[1]), _lib.ptr(U), int(real), ws, wsn,
+                                     _lib.stream_ptr()), "mpsb_left_vectors")
+    return U
 
 
 _halve_public = halve
@@ -357,8 +387,10 @@ def halve_batched(theta, trunc):
         U = _transpose_batched(uh)
     else:                                                   # two row-orthogonalisations (see _halve_split)
         _, s_all, vh = _svd_batched(A, trunc, False)
-        _, _, uh = _svd_batched(_transpose_batched(A), trunc, False)
-        U = _transpose_batched(uh)
+        U = _left_vectors(A, vh, s_all, int(vh.shape[1]))
+        if U is None:
+            _, _, uh = _svd_batched(_transpose_batched(A), trunc, False)
+            U = _transpose_batched(uh)
     k = int(vh.shape[1])
     return U.reshape(n, xl, d, k), s_all, vh.reshape(n, k, d, xr)
 

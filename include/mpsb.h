@@ -216,6 +216,17 @@ int mpsb_env_right_batched_real(int batch, int chi, int chin, int d, int w, cons
                                 long long sV, const void* W, long long sW, void* R_out, long long sRo, void* ws,
                                 size_t ws_bytes, void* stream);
 
+/* Left singular vectors from the right ones, for the split of two-site tensors whose rows are too long to carry an
+ * identity through the SVD (halve, DMRG/iDMRG.py:17-35, at chi d > 256):  with Vh [batch][k][cols] and the singular
+ * values S (first k of each chain, stride sS) of A [batch][rows][cols],
+ *     Y = A Vh^H diag(1/S),     U = Y after two Newton-Schulz steps  Y <- Y (3 I - Y^H Y) / 2
+ * U_out [batch][rows][k] holds the Schmidt partners of the rows of Vh, orthonormal to rounding; the symmetric
+ * re-orthonormalisation moves every column (the dominant ones too) by ~eps S_0 / S_k, so use it while S_k / S_0 >~ 1e-5
+ * and take U from an SVD of A^H otherwise.  real = 1: arrays of doubles. */
+size_t mpsb_left_vectors_workspace(int batch, int rows, int cols, int k);
+int mpsb_left_vectors(int batch, int rows, int cols, int k, const void* A, int lda, long long sA, const void* Vh,
+                      const double* S, long long sS, void* U_out, int real, void* ws, size_t ws_bytes, void* stream);
+
 /* Start vector for the next growth step from the tensors of the last one (new; the reference restarts ARPACK from a
  * random vector at DMRG/iDMRG.py:57).  With theta_n = A S B from the last split (A [chip][d][chi] left-orthonormal,
  * B [chi][d][chip] right-orthonormal, S [chi] normalised, all from ONE SVD so that their gauges match) and the

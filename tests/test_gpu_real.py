@@ -192,3 +192,33 @@ def test_real_chain_batch_matches_complex(lib):
         finally:
             iDMRG.REAL_PATH = True
     np.testing.assert_allclose(out[True], out[False], rtol=1e-12)
+
+
+@pytest.mark.parametrize("real", [True, False])
+def test_large_split_left_vectors_from_right_ones(lib, real):
+    """`_halve_split` (rows too long for a carried identity): U = A V^H S^-1 + one Newton-Schulz step gives orthonormal
+    Schmidt partners of V - also when `trunc` cuts a degenerate multiplet, where U S V must still be a best rank-k
+    approximation (||A - U S V||_F^2 = sum of the discarded S^2) - and falls back to a second SVD when the kept
+    spectrum reaches below SPLIT_CUTOFF."""
+    from dmrg_b200 import iDMRG
+    rs = np.random.RandomState(31 + real)
+    n, k = 288, 48
+    def unitary(m):
+        z = rs.randn(m, m) if real else rs.randn(m, m) + 1j * rs.randn(m, m)
+        return np.linalg.qr(z)[0]
+    for floor, fast in ((1e-3, True), (1e-20, True), (1e-40, False)):    # S_k / S_0 = 0.32, 5.3e-4, 2.8e-7
+        sv = np.exp(np.linspace(0, np.log(floor), n))
+        sv[k - 2:k + 2] = sv[k]                              # a four-fold multiplet cut in the middle
+        A = (unitary(n) * sv) @ unitary(n)
+        sh = (n // 2, 2, 2, n // 2)
+        Ad = lib.to_device(A, np.float64 if real else np.complex128)
+        U, S, V = iDMRG._halve_split(Ad.reshape(sh), sh, k)
+        took_fast = bool(sv[k - 1] > iDMRG.SPLIT_CUTOFF * sv[0])
+        assert took_fast == fast
+        U, S, V = lib.to_host(U).reshape(n, k), lib.to_host(S), lib.to_host(V).reshape(k, n)
+        np.testing.assert_allclose(S, np.sort(sv)[::-1], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(U.conj().T @ U, np.eye(k), atol=1e-12)
+        np.testing.assert_allclose(V @ V.conj().T, np.eye(k), atol=1e-12)
+        if fast:
+            err2 = np.linalg.norm(A - (U * S[:k]) @ V) ** 2
+            np.testing.assert_allclose(err2, np.sum(np.sort(sv)[::-1][k:] ** 2), rtol=1e-6, atol=1e-26)
