@@ -1566,6 +1566,199 @@ jacobi_cross_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld
     }
 }
 
+// ---- modulus ordering on SUPER blocks of 16 rows: four cross tasks per CTA ------------------------------------------
+// jacobi_cross_kernel streams 16 rows in and out of the SM for 64 pairs; with 512 problems in a call that is 1 GiB per
+// step and ~330 GB per SVD batch - at ~4 TB/s the sweeps sit closer to the HBM roofline than to the FP64 one.  Here the
+// blocks are paired up: super block S = blocks {2S, 2S+1}, step K in [0, nblk/2) holds the super pairs with
+// SI + SJ = K (mod nblk/2), and ONE CTA plays the four cross tasks (2SI+a, 2SJ+b): the 16 rows of the J side stay in
+// shared memory for all four, the I side passes through the registers one 8-row block after the other - 32 rows moved
+// for 256 pairs, half the traffic per pair, half the launches.  inner = 1: the cross task INSIDE the two super blocks
+// that meet themselves on even steps, (2u, 2u+1) for u = K/2 and K/2 + nblk/4 (their self tasks run in jacobi_self_kernel
+// before it on the same side stream).  Stamps: task t of the CTA writes launch_id + t, so that a pair verified clean
+// after an earlier task of the same CTA changed one of its blocks still counts as clean next time.
+template <bool FULL, bool REAL>
+__global__ void __launch_bounds__(CROSS_THREADS, MPSB_CROSS_MINBLOCKS)
+jacobi_quad_kernel(cplx* __restrict__ Xall, long long strideX, int mat0, int ld, int ldot, int ltot_r, int nblk, int kstep,
+                   int inner, int* __restrict__ rot, const int* __restrict__ done, double tol2, int* __restrict__ stamps,
+                   int stamp_stride, int launch_id) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    cplx* rowsJ = reinterpret_cast<cplx*>(smraw);            // [16][ltot_r] (8 rows when inner)
+    __shared__ double nq[16], dqs[16], eqs[16];              // true norm^2, scale d and d^2 of the rows of the J side
+    __shared__ __align__(8) uint64_t bar;
+
+    const int mat = mat0 + blockIdx.y;
+    if (done[mat]) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nsup = nblk >> 1;
+    int bI0, bJ0, nsub;
+    if (inner) {
+        bI0 = 2 * ((kstep >> 1) + (int)blockIdx.x * (nsup >> 1));
+        bJ0 = bI0 + 1;
+        nsub = 1;
+    } else {
+        int SI, SJ;
+        mod_pair(nsup, kstep, blockIdx.x, SI, SJ);
+        bI0 = 2 * SI; bJ0 = 2 * SJ; nsub = 2;
+    }
+    int* stp = stamps ? stamps + (size_t)mat * stamp_stride : nullptr;
+    // pairs verified clean since both blocks last changed need no visit - unless this CTA changes a block first
+    // (bit 2a + b of `need`: task (bI0 + a, bJ0 + b); chI / chJ: blocks this CTA has rotated)
+    unsigned need = nsub == 2 ? 0xfu : 0x1u;
+    if (stp) {
+        unsigned m = 0;
+        for (int t = 0; t < 4; ++t) {
+            if (!(need >> t & 1u)) continue;
+            const int bi = bI0 + (t >> 1), bj = bJ0 + (t & 1);
+            const int chk = stp[stamp_pair_index(nblk, bi, bj)];
+            if (!(chk > stp[bi] && chk > stp[bj])) m |= 1u << t;
+        }
+        need = m;
+        if (!need) return;
+    }
+    unsigned chI = 0, chJ = 0;
+    cplx* X = Xall + (size_t)mat * strideX;
+    const uint32_t rowbytes = (uint32_t)ltot_r * sizeof(cplx);
+    const int nrowsJ = 8 * nsub;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, rowbytes * nrowsJ);
+        for (int r = 0; r < nrowsJ; ++r) bulk_g2s(rowsJ + (size_t)r * ltot_r, X + (size_t)(bJ0 * 8 + r) * ld, rowbytes, &bar);
+    }
+    bool waitedJ = false;
+    int nrot = 0;
+#pragma unroll 1
+    for (int a = 0; a < nsub; ++a) {
+        if (!((need >> (2 * a) & 3u) | chJ)) continue;
+        // rows 2w, 2w+1 of block bI0 + a: global -> registers (512 contiguous bytes per warp load)
+        cplx* gp0 = X + (size_t)((bI0 + a) * 8 + 2 * w) * ld;
+        cplx* gp1 = gp0 + ld;
+        RegRow r0, r1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            r0.x[j] = (FULL || c < ltot_r) ? gp0[c] : make_double2(0.0, 0.0);
+            r1.x[j] = (FULL || c < ltot_r) ? gp1[c] : make_double2(0.0, 0.0);
+        }
+        {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (FULL || lane + 32 * j < ldot) {
+                    a0 = fma(r0.x[j].x, r0.x[j].x, fma(r0.x[j].y, r0.x[j].y, a0));
+                    a1 = fma(r1.x[j].x, r1.x[j].x, fma(r1.x[j].y, r1.x[j].y, a1));
+                }
+            r0.a = warp_sum(a0); r1.a = warp_sum(a1);
+            r0.d = r1.d = r0.e = r1.e = 1.0;
+            r0.dirty = r1.dirty = false;
+        }
+        if (!waitedJ) {
+            if (!mbar_wait(&bar, 0)) __trap();
+            for (int rr = w; rr < nrowsJ; rr += 4) {          // norms of the rows of the J side
+                const cplx* r = rowsJ + (size_t)rr * ltot_r;
+                double b = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j;
+                    if (FULL || c < ldot) { const cplx y = r[c]; b = fma(y.x, y.x, fma(y.y, y.y, b)); }
+                }
+                b = warp_sum(b);
+                if (lane == 0) { nq[rr] = b; dqs[rr] = 1.0; eqs[rr] = 1.0; }
+            }
+            __syncthreads();
+            waitedJ = true;
+        }
+#pragma unroll 1
+        for (int b = 0; b < nsub; ++b) {
+            if (!((need >> (2 * a + b) & 1u) | (chI >> a & 1u) | (chJ >> b & 1u))) continue;
+            cplx* blockJ = rowsJ + (size_t)(8 * b) * ltot_r;
+            double* nqb = nq + 8 * b;
+            double* dqb = dqs + 8 * b;
+            double* eqb = eqs + 8 * b;
+            int trot = 0;
+#pragma unroll 1
+            for (int s = 0; s < 8; ++s) {
+                const int q = (2 * w + s) & 7;                // the 4 warps meet 4 distinct rows of the block in every step
+                cplx* rq = blockJ + (size_t)q * ltot_r;
+                cplx y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j;
+                    y[j] = (FULL || c < ltot_r) ? rq[c] : make_double2(0.0, 0.0);
+                }
+                double dq = dqb[q], eq = eqb[q], bq = nqb[q];
+                int n0 = cross_pair<FULL, REAL>(r0, y, dq, eq, bq, ldot, tol2, lane, true);
+                if (n0 == 2) { swap_rows_via_smem<FULL>(r0, y, rq, ltot_r, lane); n0 = 1; }
+                int n1 = cross_pair<FULL, REAL>(r1, y, dq, eq, bq, ldot, tol2, lane, true);
+                if (n1 == 2) { swap_rows_via_smem<FULL>(r1, y, rq, ltot_r, lane); n1 = 1; }
+                trot += n0 + n1;
+                bool store = (n0 + n1) > 0;
+                if (s >= 6 && dq != 1.0) {                    // last visit of this row in the task: fold its scale back
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { y[j].x *= dq; y[j].y *= dq; }
+                    dq = 1.0;
+                    eq = 1.0;
+                    store = true;
+                }
+                if (store) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = lane + 32 * j;
+                        if (FULL || c < ltot_r) rq[c] = y[j];
+                    }
+                    if (lane == 0) { dqb[q] = dq; eqb[q] = eq; nqb[q] = bq; }
+                }
+                __syncthreads();
+            }
+            const int any = __syncthreads_or(trot > 0);
+            nrot += trot;
+            const int id = launch_id + 2 * a + b;
+            if (any) {
+                chI |= 1u << a;
+                chJ |= 1u << b;
+                if (stp && tid == 0) { stp[bI0 + a] = id; stp[bJ0 + b] = id; }
+            } else if (stp && tid == 0) {
+                stp[stamp_pair_index(nblk, bI0 + a, bJ0 + b)] = id;      // verified clean at this task
+            }
+        }
+        // fold the scales back: register rows on their way to global memory
+        if (r0.dirty) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (FULL || c < ltot_r) gp0[c] = make_double2(r0.x[j].x * r0.d, r0.x[j].y * r0.d);
+            }
+        }
+        if (r1.dirty) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (FULL || c < ltot_r) gp1[c] = make_double2(r1.x[j].x * r1.d, r1.x[j].y * r1.d);
+            }
+        }
+    }
+    if (lane == 0 && nrot > 0) atomicAdd(&rot[mat], nrot);
+    if (!waitedJ) {                                           // nothing visited: the loads must still land before exit
+        if (!mbar_wait(&bar, 0)) __trap();
+        return;
+    }
+    if (!chJ) return;
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int b = 0; b < nsub; ++b)
+            if (chJ >> b & 1u)
+                for (int r = 0; r < 8; ++r)
+                    bulk_s2g(X + (size_t)((bJ0 + b) * 8 + r) * ld, rowsJ + (size_t)(8 * b + r) * ltot_r, rowbytes);
+        bulk_commit();
+        bulk_wait_all();
+    }
+}
+
 // ---- self tasks of the modulus ordering (jacobi_selftask.cuh) --------------------------------------------------------
 // Even steps: blocks round/2 and round/2 + nblk/2 meet nobody, one 128-thread CTA per problem orthogonalises the pairs
 // inside them.  A kernel of its own: compiled into jacobi_cross_kernel its 4.5 k straight-line instructions cost the
@@ -2650,6 +2843,70 @@ int launch_modulus_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0,
     return 0;
 }
 
+// Super-block form of the modulus ordering (jacobi_quad_kernel) for calls with enough problems to fill the GPU with
+// CTAs that live four times as long: step K in [0, nblk/2) = one launch over the step's super pairs; on even steps the
+// two super blocks K/2 and K/2 + nblk/4 meet themselves on the side stream - the self tasks of their four 8-row blocks
+// (the existing kernel, old rounds 2K and 2K+2) followed by the two cross tasks inside them.
+// launch_id is a multiple of 8: tasks of a CTA stamp launch_id + 0..3, the side-stream launches + 0, 1, 2.
+typedef void (*QuadKernel)(cplx*, long long, int, int, int, int, int, int, int, int*, const int*, double, int*, int, int);
+QuadKernel quad_kernel_for(bool full, bool real) {
+    if (real) return full ? jacobi_quad_kernel<true, true> : jacobi_quad_kernel<false, true>;
+    return full ? jacobi_quad_kernel<true, false> : jacobi_quad_kernel<false, false>;
+}
+bool use_quad_order(const SvdPlan& pl, int count) {
+    static const int enabled = env_int("MPSB_JACOBI_QUAD", 1);
+    static const int min_ctas = env_int("MPSB_JACOBI_QUAD_MIN_CTAS", 1776);      // four waves of 3 CTAs on 148 SMs
+    const int nblk = pl.n_pad / 8;
+    return enabled && use_modulus_order(pl) && (nblk & 3) == 0 && nblk >= 8 && stamp_ints(pl.n_pad, pl.bsz) > 0 &&
+           (long long)count * (nblk / 4) >= min_ctas;
+}
+int launch_quad_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int kstep, double tol2,
+                     int launch_id, cudaStream_t st) {
+    const int ltot_r = round_up(pl.ltot, 32), nblk = pl.n_pad / 8, nsup = nblk / 2;
+    const long long strideX = (long long)pl.n_pad * pl.ld;
+    const size_t smem = (size_t)16 * ltot_r * sizeof(cplx);
+    const bool full = (ltot_r == 256 && pl.ldot == 256);
+    auto kern = quad_kernel_for(full, pl.real != 0);
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
+    dim3 grid(mod_cross_pairs(nsup, kstep), count);
+    SideStream* side = nullptr;
+    if ((kstep & 1) == 0) {
+        side = side_stream();
+        cudaStream_t ss = st;
+        if (side) {
+            MPSB_CHECK_CUDA(cudaEventRecord(side->fork, st));
+            MPSB_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            ss = side->stream;
+        }
+        for (int half = 0; half < 2; ++half) {
+            const int round = 2 * kstep + 2 * half;          // blocks kstep + half and kstep + half + nblk/2
+#define MPSB_SELF(CPL, EXACT)                                                                                              \
+    jacobi_self_kernel<CPL, EXACT><<<count, 128, 0, ss>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, round, s.rot, s.done, \
+                                                          tol2, s.stamps, s.stamp_stride, launch_id + half, pl.real)
+            if (full) MPSB_SELF(4, true);
+            else if (ltot_r > 128) MPSB_SELF(4, false);
+            else if (ltot_r > 64) MPSB_SELF(2, false);
+            else MPSB_SELF(1, false);
+#undef MPSB_SELF
+            MPSB_COUNT_LAUNCH();
+            MPSB_CHECK_CUDA(cudaGetLastError());
+        }
+        kern<<<dim3(2, count), CROSS_THREADS, smem, ss>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, kstep, 1, s.rot, s.done,
+                                                          tol2, s.stamps, s.stamp_stride, launch_id + 2);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+        if (side) MPSB_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+    }
+    if (grid.x > 0) {
+        kern<<<grid, CROSS_THREADS, smem, st>>>(X, strideX, mat0, pl.ld, pl.ldot, ltot_r, nblk, kstep, 0, s.rot, s.done, tol2,
+                                               s.stamps, s.stamp_stride, launch_id);
+        MPSB_COUNT_LAUNCH();
+        MPSB_CHECK_CUDA(cudaGetLastError());
+    }
+    if (side) MPSB_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    return 0;
+}
+
 int launch_round_dyn(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int round, int full,
                      int inner, double tol2, double eabs2, int launch_id, cudaStream_t st) {
     static const int cross_enabled = env_int("MPSB_JACOBI_CROSS", 1);
@@ -2905,7 +3162,8 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     const double tol2 = tol * tol, eabs2 = eabs * eabs;
     const int nblk = pl.n_pad / pl.bsz;
     const bool modulus = use_modulus_order(pl);
-    const int rounds = modulus ? nblk : nblk - 1;
+    const bool quad = modulus && use_quad_order(pl, std::min(pl.chunk, pl.batch));
+    const int rounds = quad ? nblk / 2 : modulus ? nblk : nblk - 1;
     const int inner = (nblk == 2) ? pl.max_sweeps : 1;
     int max_sweeps_seen = 0;
     int launch_id = 1;
@@ -2955,8 +3213,9 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
             int sweep = 0;
             for (; sweep < pl.max_sweeps; ++sweep) {
                 for (int r = 0; r < rounds; ++r) {
-                    int rc = modulus ? launch_modulus_step(pl, X, s, mat0, count, r, tol2, ++launch_id, st)
-                                     : launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
+                    int rc = quad ? launch_quad_step(pl, X, s, mat0, count, r, tol2, launch_id += 8, st)
+                             : modulus ? launch_modulus_step(pl, X, s, mat0, count, r, tol2, ++launch_id, st)
+                                       : launch_round_dyn(pl, X, s, mat0, count, r, r == 0, inner, tol2, eabs2, ++launch_id, st);
                     if (rc) return rc;
                 }
                 MPSB_CHECK_CUDA(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));

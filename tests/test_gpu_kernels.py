@@ -1,4 +1,6 @@
 """GPU: each C-ABI entry point against numpy / the oracle on seeded inputs (run with -m gpu)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.linalg as la
@@ -376,3 +378,19 @@ def test_svd_rows_at_underflow_scale(lib):
             uu = lib.to_host(u)
             np.testing.assert_allclose(uu[:, live].conj().T @ uu[:, live], np.eye(7), atol=1e-11)
             np.testing.assert_allclose((uu[:, live] * s[:k][live]) @ v[live], m, atol=1e-12)
+
+
+@pytest.mark.skipif(bool(os.environ.get("MPSB_JACOBI_QUAD_MIN_CTAS")), reason="already inside the child run")
+def test_super_block_ordering_forced_on_small_batches(lib):
+    """jacobi_quad_kernel (modulus ordering on 16-row super blocks, four cross tasks per CTA) only serves calls with
+    >= 1776 CTAs per step.  The library reads its knobs once per process, so a child process with
+    MPSB_JACOBI_QUAD_MIN_CTAS=1 re-runs the SVD and two-site tests of this file with that path taken wherever the
+    modulus ordering applies (complex and real, full and ragged row lengths, stamps, de Rijk swaps)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MPSB_JACOBI_QUAD="1", MPSB_JACOBI_QUAD_MIN_CTAS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "svd or tebd or chi128",
+                        os.path.join(root, "tests", "test_gpu_kernels.py"), os.path.join(root, "tests", "test_gpu_real.py")],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
