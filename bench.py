@@ -499,17 +499,23 @@ def main():
         pass
     traffic = None
     try:   # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2b_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2d_dominant_kernel_traffic.json")))
+        # captured at 256 problems per launch; a launch of this run covers n problems (same bytes per problem)
+        traffic = int(tj["dram_bytes_per_launch"] * n / tj["problems_in_capture"])
     except (OSError, ValueError, KeyError):
         pass
     peak_note = ("cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; profiles/r2_fp64_peak.json "
                  "holds the DFMA / DMMA / mixed micro-benchmark of this pool: 35.5 / 37.1 / 33.8 TFLOP/s - DMMA and DFMA "
                  "share one execution unit on this part)")
-    roofline = {"kernel": "jacobi_cross_kernel (all Jacobi sweeps of one step, modulus ordering; self tasks on a side stream next to the cross launches)",
+    roofline = {"kernel": "jacobi_quad_kernel (all Jacobi sweeps of one step: modulus ordering on 16-row super blocks, four cross tasks "
+                          "per CTA; self tasks on a side stream next to the launches; calls below 1776 CTAs per step use "
+                          "jacobi_cross_kernel)",
                 "bound": "fp64",
                 "achieved": svd_flop / svd_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": svd_flop / svd_s / 1e12 / fp64_peak,
                 "traffic": traffic,
+                "traffic_note": "DRAM read + write bytes of one step launch (ncu --set full, profiles/r2d_dominant_kernel_traffic.json: "
+                                "482 MB at 256 problems against 537 MB algorithmic), scaled to this run's problems per launch",
                 "flop_model": "SURVEY 8(d): 4*21*n^3 = 1.409 GFLOP per truncated SVD (n = 256), over QR + Jacobi time",
                 "lean": {"achieved": jac_flop / jac_s / 1e12, "frac": jac_flop / jac_s / 1e12 / fp64_peak,
                          "flop_model": "8*L per visited pair + 16*L per rotation (L = 256 columns), library counters, Jacobi time only",
