@@ -23,6 +23,7 @@ SIGNATURES = {
     "mpsb_last_error": (_c.c_char_p, []),
     "mpsb_launch_count": (_c.c_ulonglong, []),
     "mpsb_last_svd_sweeps": (_i, []),
+    "mpsb_debug_sweep_schedule": (_i, [_i, _i, _pi, _i]),
     "mpsb_profile_enable": (None, [_i]),
     "mpsb_profile_read": (_i, [_pd, _c.POINTER(_c.c_ulonglong), _c.POINTER(_c.c_ulonglong)]),
     "mpsb_zgemm": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _i, _vp]),

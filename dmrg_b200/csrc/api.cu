@@ -105,6 +105,7 @@ int mpsb_version(void) { return 100; }
 const char* mpsb_last_error(void) { return g_error; }
 unsigned long long mpsb_launch_count(void) { return g_launch_count; }
 int mpsb_last_svd_sweeps(void) { return g_last_sweeps; }
+int mpsb_debug_sweep_schedule(int nblk, int quad, int* out_host, int cap) { return sweep_schedule(nblk, quad, out_host, cap); }
 
 void mpsb_profile_enable(int on) {
     g_prof.enabled = on;

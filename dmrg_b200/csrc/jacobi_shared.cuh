@@ -29,7 +29,7 @@ __device__ __forceinline__ void rr_pair(int m, int r, int s, int& p, int& q) {
 // k even: slots t = 1 .. m/2-1 are cross pairs, blocks k/2 and k/2 + m/2 meet themselves (separate "self" tasks);
 // k odd : slots t = 0 .. m/2-1 are all cross pairs.  `slot` counts the cross pairs of the step from 0; bI < bJ.
 __host__ __device__ inline int mod_cross_pairs(int m, int k) { return (k & 1) ? m / 2 : m / 2 - 1; }
-__device__ __forceinline__ void mod_pair(int m, int k, int slot, int& bI, int& bJ) {
+__host__ __device__ __forceinline__ void mod_pair(int m, int k, int slot, int& bI, int& bJ) {
     int a, b;
     if (k & 1) { a = (k - 1) / 2 - slot; b = (k + 1) / 2 + slot; }
     else { a = k / 2 - (slot + 1); b = k / 2 + (slot + 1); }

@@ -3261,6 +3261,51 @@ int svd_orthogonalise(const SvdPlan& pl, cplx* X, void* state, cudaStream_t st, 
     return 0;
 }
 
+// Host-side listing of one sweep of the block orderings, built from the same pairing helpers the kernels and launchers
+// use (mod_pair, mod_cross_pairs, the self-task rounds of launch_modulus_step / launch_quad_step): entries
+// (step, stream, block I, block J), stream 0 = the step's main launch, 1 = its side stream, I == J = self task of a
+// block.  For the CPU tests of the schedule (every block pair once per sweep, no block touched twice by concurrent
+// launches of a step); returns the number of entries, or -1 if `cap` is too small.
+int sweep_schedule(int nblk, int quad, int* out, int cap) {
+    int n = 0;
+    auto emit = [&](int step, int stream, int bI, int bJ) {
+        if (n < cap) { out[4 * n] = step; out[4 * n + 1] = stream; out[4 * n + 2] = bI; out[4 * n + 3] = bJ; }
+        ++n;
+    };
+    if (!quad) {
+        for (int k = 0; k < nblk; ++k) {
+            if ((k & 1) == 0) { emit(k, 1, k >> 1, k >> 1); emit(k, 1, (k >> 1) + (nblk >> 1), (k >> 1) + (nblk >> 1)); }
+            for (int slot = 0; slot < mod_cross_pairs(nblk, k); ++slot) {
+                int bI, bJ;
+                mod_pair(nblk, k, slot, bI, bJ);
+                emit(k, 0, bI, bJ);
+            }
+        }
+    } else {
+        const int nsup = nblk / 2;
+        for (int k = 0; k < nsup; ++k) {
+            if ((k & 1) == 0) {
+                for (int half = 0; half < 2; ++half) {               // jacobi_self_kernel with round = 2k + 2 half
+                    const int bA = (2 * k + 2 * half) >> 1;
+                    emit(k, 1, bA, bA);
+                    emit(k, 1, bA + (nblk >> 1), bA + (nblk >> 1));
+                }
+                for (int x = 0; x < 2; ++x) {                        // jacobi_quad_kernel, inner = 1
+                    const int b0 = 2 * ((k >> 1) + x * (nsup >> 1));
+                    emit(k, 1, b0, b0 + 1);
+                }
+            }
+            for (int slot = 0; slot < mod_cross_pairs(nsup, k); ++slot) {
+                int SI, SJ;
+                mod_pair(nsup, k, slot, SI, SJ);
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) emit(k, 0, 2 * SI + a, 2 * SJ + b);
+            }
+        }
+    }
+    return n <= cap ? n : -1;
+}
+
 int svd_finalise(const SvdPlan& pl, const cplx* X, void* state, const SvdOutputs& out, cudaStream_t st) {
     (void)state;
     MPSB_REQUIRE(out.s && out.rank && out.k_cap >= 1, "svd_finalise: s, rank and k_cap are required");

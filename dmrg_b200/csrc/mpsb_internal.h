@@ -89,6 +89,7 @@ struct SvdOutputs {
     int real_cols, real_naug;                        // real columns of the dot part / of the carried part
 };
 int svd_finalise(const SvdPlan& plan, const cplx* X, void* state, const SvdOutputs& out, cudaStream_t st);
+int sweep_schedule(int nblk, int quad, int* out, int cap);      // host listing of one sweep's block pairs (tests)
 
 // ---- small fused element-wise kernels (tebd.cu, gauge.cu, heff.cu) ------------------------------
 int gate_scale(int batch, int chil, int chir, int d, const cplx* theta0, long long s_theta0,

@@ -262,6 +262,13 @@ int mpsb_transpose_batched_real(int batch, int rows, int cols, const void* in, i
 /* Diagnostics of the last SVD call on this thread: number of Jacobi sweeps of the slowest problem. */
 int mpsb_last_svd_sweeps(void);
 
+/* Diagnostics (host only, no GPU needed): one sweep of the Jacobi block ordering as the launchers and kernels compute it,
+ * for nblk 8-row blocks (nblk even; quad = 1: the 16-row super-block form, nblk a multiple of 4).  Writes up to `cap`
+ * entries (step, stream, block I, block J) into out_host - stream 0 = the step's main launch, 1 = its side stream,
+ * I == J = the pairs inside a block - and returns the number of entries (-1 if cap is too small).  Every pair of
+ * blocks appears exactly once per sweep and the launches of one step touch disjoint blocks (tests/test_host.py). */
+int mpsb_debug_sweep_schedule(int nblk, int quad, int* out_host, int cap);
+
 /* Phase timing of mpsb_tebd_two_site for the roofline report (bench.py).  When enabled, CUDA events are
  * recorded on the caller's stream at the phase boundaries; mpsb_profile_read returns the 6 phase
  * durations in ms (theta GEMM, gate, QR, Jacobi sweeps, finalise, back-projection GEMM) of the last

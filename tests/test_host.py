@@ -196,3 +196,38 @@ def test_bond_grouping_for_batched_half_sweeps():
     assert any(k[1] == 4 for k in g) and any(k[1] == 128 for k in g)
     # a single class stays as it is
     assert MPS._group_bonds(np.array([8, 8, 8, 8, 8]), [0, 2], 2) == {(8, 8, 8): [0, 2]}
+
+
+@pytest.mark.parametrize("nblk,quad", [(4, 0), (6, 0), (8, 0), (32, 0), (8, 1), (12, 1), (16, 1), (32, 1), (64, 1)])
+def test_jacobi_sweep_schedule_is_a_complete_ordering(lib, nblk, quad):
+    """One sweep of the block ordering, listed on the host by the helpers the kernels and launchers use
+    (mpsb_debug_sweep_schedule; quad = 1: the 16-row super-block form of jacobi_quad_kernel): every pair of 8-row blocks
+    meets exactly once, every block meets itself exactly once, and the launches of one step - main stream and side
+    stream run concurrently - never touch a block twice except in the side stream's own serial order."""
+    import ctypes
+    cap = 4 * nblk * nblk
+    buf = (ctypes.c_int * (4 * cap))()
+    n = lib.load().mpsb_debug_sweep_schedule(nblk, quad, buf, cap)
+    assert n > 0
+    tasks = [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+    pairs = [(i, j) for _, _, i, j in tasks]
+    assert all(0 <= i <= j < nblk for i, j in pairs)
+    assert sorted(pairs) == sorted((i, j) for i in range(nblk) for j in range(i, nblk))       # each exactly once
+    steps = nblk // 2 if quad else nblk
+    assert {t[0] for t in tasks} == set(range(steps))
+    for k in range(steps):
+        main = [(i, j) for s, st, i, j in tasks if s == k and st == 0]
+        side = [(i, j) for s, st, i, j in tasks if s == k and st == 1]
+        side_blocks = {b for p in side for b in p}
+        if quad:
+            # a CTA of the main launch owns the two super blocks of its four tasks; CTAs are disjoint
+            owners = {}
+            for i, j in main:
+                cta = (i // 2, j // 2)
+                for b in (i, j):
+                    assert owners.setdefault(b, cta) == cta
+        else:
+            blocks = [b for p in main for b in p]
+            assert len(blocks) == len(set(blocks))
+        assert not side_blocks & {b for p in main for b in p}
+        assert bool(side) == (k % 2 == 0)
