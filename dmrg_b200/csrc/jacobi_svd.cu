@@ -2854,11 +2854,15 @@ QuadKernel quad_kernel_for(bool full, bool real) {
     return full ? jacobi_quad_kernel<true, false> : jacobi_quad_kernel<false, false>;
 }
 bool use_quad_order(const SvdPlan& pl, int count) {
+    // 1: rows of 256 complex columns only - the shape it was measured on (512 two-site updates at chi = 128: Jacobi
+    // 83.2 -> 81.2 ms); the packed real rows of the 256-chain iDMRG split run 10 % SLOWER through it (split 62 -> 70 ms),
+    // so they stay on jacobi_cross_kernel.  2: every shape the modulus ordering serves (tests).  0: off.
     static const int enabled = env_int("MPSB_JACOBI_QUAD", 1);
     static const int min_ctas = env_int("MPSB_JACOBI_QUAD_MIN_CTAS", 1776);      // four waves of 3 CTAs on 148 SMs
     const int nblk = pl.n_pad / 8;
-    return enabled && use_modulus_order(pl) && (nblk & 3) == 0 && nblk >= 8 && stamp_ints(pl.n_pad, pl.bsz) > 0 &&
-           (long long)count * (nblk / 4) >= min_ctas;
+    const bool measured_shape = round_up(pl.ltot, 32) == 256 && pl.ldot == 256 && !pl.real;
+    return enabled && (enabled > 1 || measured_shape) && use_modulus_order(pl) && (nblk & 3) == 0 && nblk >= 8 &&
+           stamp_ints(pl.n_pad, pl.bsz) > 0 && (long long)count * (nblk / 4) >= min_ctas;
 }
 int launch_quad_step(const SvdPlan& pl, cplx* X, const SvdState& s, int mat0, int count, int kstep, double tol2,
                      int launch_id, cudaStream_t st) {

@@ -388,7 +388,7 @@ def test_super_block_ordering_forced_on_small_batches(lib):
     modulus ordering applies (complex and real, full and ragged row lengths, stamps, de Rijk swaps)."""
     import subprocess
     import sys
-    env = dict(os.environ, MPSB_JACOBI_QUAD="1", MPSB_JACOBI_QUAD_MIN_CTAS="1")
+    env = dict(os.environ, MPSB_JACOBI_QUAD="2", MPSB_JACOBI_QUAD_MIN_CTAS="1")        # 2: every shape, not only 256 complex columns
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "svd or tebd or chi128",
                         os.path.join(root, "tests", "test_gpu_kernels.py"), os.path.join(root, "tests", "test_gpu_real.py")],
